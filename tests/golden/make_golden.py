@@ -1,0 +1,172 @@
+"""Generate the golden vectors under tests/golden/ from the REAL reference.
+
+Run in the build container only (it reads /root/reference, which does not exist
+on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference's ``model`` package cannot be imported normally (``model/__init__``
+pulls in trimesh / manopth, absent here), so ``pointnet2_utils.py`` and
+``TEHNet.py`` are loaded by file path under a stand-in package name.  Nothing is
+copied: the reference code runs unmodified and only its outputs are saved.
+
+Inputs come from ``ev2hands_b200.synth`` (numpy RandomState, portable) and are
+stored alongside the outputs so the fixtures stay valid even if the generator
+changes.  FPS start indices: the reference draws them with ``torch.randint`` on
+the CPU generator (pointnet2_utils.py:75); we seed, draw the same numbers
+ourselves, re-seed, and then call the reference so it re-draws them.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from ev2hands_b200 import synth  # noqa: E402
+
+REF_DIR = "/root/reference/src/Ev2Hands/model"
+
+
+def load_reference():
+    os.environ["ERPC"] = "1"     # dataset modules set this at import (erpc.py:20)
+    pkg = types.ModuleType("refmodel")
+    pkg.__path__ = [REF_DIR]
+    sys.modules["refmodel"] = pkg
+    mods = {}
+    for name in ("pointnet2_utils", "TEHNet"):
+        spec = importlib.util.spec_from_file_location("refmodel." + name, os.path.join(REF_DIR, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["refmodel." + name] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["pointnet2_utils"], mods["TEHNet"]
+
+
+def seeded_starts(seed, n_points, batch):
+    torch.manual_seed(seed)
+    s = torch.randint(0, n_points, (batch,), dtype=torch.long)
+    torch.manual_seed(seed)      # the reference's own draw now returns the same numbers
+    return s
+
+
+def to_t(state):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}
+
+
+def small_idx(a):
+    a = np.asarray(a)
+    return a.astype(np.int16) if a.max() < 32768 else a.astype(np.int32)
+
+
+def main():
+    pu, th = load_reference()
+    torch.set_num_threads(8)
+
+    # ---- 1. FPS / square_distance / ball query on sa1-shaped windows ----------
+    ev = synth.make_windows(2, 2048, seed=1234)
+    xyz = torch.from_numpy(ev[:, :3].transpose(0, 2, 1).copy())
+    start = seeded_starts(7, 2048, 2)
+    fps_idx = pu.farthest_point_sample(xyz, 512)
+    assert torch.equal(fps_idx[:, 0], start)
+    centres = pu.index_points(xyz, fps_idx)
+    out = {"xyz": xyz.numpy(), "start": start.numpy(), "fps_idx": small_idx(fps_idx.numpy()),
+           "sqdist_w0_first8": pu.square_distance(centres[:1, :8], xyz[:1]).numpy()[0]}
+    for r, k in zip([0.1, 0.2, 0.4], [32, 64, 128]):
+        out["ball_r%g" % r] = small_idx(pu.query_ball_point(r, k, xyz, centres).numpy())
+    np.savez_compressed(os.path.join(HERE, "fps_ball.npz"), **out)
+
+    # ---- 2. edge cases ---------------------------------------------------------
+    rs = np.random.RandomState(99)
+    edge = {}
+    # (a) every point identical
+    same = np.tile(rs.rand(1, 1, 3).astype(np.float32), (1, 64, 1))
+    st = seeded_starts(3, 64, 1)
+    edge["same_xyz"], edge["same_start"] = same, st.numpy()
+    edge["same_fps"] = pu.farthest_point_sample(torch.from_numpy(same), 16).numpy()
+    edge["same_ball"] = pu.query_ball_point(0.2, 8, torch.from_numpy(same), torch.from_numpy(same[:, :4])).numpy()
+    # (b) sample every point (S == N), coarse grid => many exact distance ties
+    grid = (rs.randint(0, 5, size=(2, 96, 3)).astype(np.float32) / 4.0) * 2 - 1
+    st = seeded_starts(4, 96, 2)
+    edge["grid_xyz"], edge["grid_start"] = grid, st.numpy()
+    g_fps = pu.farthest_point_sample(torch.from_numpy(grid), 96)
+    edge["grid_fps"] = g_fps.numpy()
+    g_c = pu.index_points(torch.from_numpy(grid), g_fps[:, :24])
+    edge["grid_ball_r0.5_k16"] = pu.query_ball_point(0.5, 16, torch.from_numpy(grid), g_c).numpy()
+    # (c) radii whose fp32 square rounds UP (0.3, 0.7) and a tiny radius that only
+    #     ever contains the centre itself; N not a multiple of 32
+    pts = (rs.rand(2, 301, 3).astype(np.float32) * 2 - 1)
+    st = seeded_starts(5, 301, 2)
+    edge["odd_xyz"], edge["odd_start"] = pts, st.numpy()
+    o_fps = pu.farthest_point_sample(torch.from_numpy(pts), 40)
+    edge["odd_fps"] = o_fps.numpy()
+    o_c = pu.index_points(torch.from_numpy(pts), o_fps)
+    for r, k in [(0.3, 16), (0.7, 48), (1e-3, 4), (4.0, 301)]:
+        edge["odd_ball_r%g_k%d" % (r, k)] = pu.query_ball_point(r, k, torch.from_numpy(pts), o_c).numpy()
+    # (d) centres that are NOT input points and have no neighbour: reference leaves N
+    far = np.full((2, 2, 3), 50.0, dtype=np.float32)
+    edge["far_centres"] = far
+    edge["far_ball_r0.2_k4"] = pu.query_ball_point(0.2, 4, torch.from_numpy(pts), torch.from_numpy(far)).numpy()
+    np.savez_compressed(os.path.join(HERE, "edge.npz"), **edge)
+
+    # ---- 3. encoder sa1 -> sa2 -> sa3 with random weights ---------------------
+    net = th.TEHNet(n_pose_params=6).eval()
+    states = {n: synth.random_state_for(synth.ENCODER_SPECS[n], seed=100 + i)
+              for i, n in enumerate(("sa1", "sa2", "sa3"))}
+    for n in states:
+        getattr(net, n).load_state_dict(to_t(states[n]), strict=True)
+    events = torch.from_numpy(synth.make_windows(2, 2048, seed=1235))
+    s1 = seeded_starts(11, 2048, 2)
+    s2_probe = None
+    with torch.no_grad():
+        l0_xyz = events[:, :3, :]
+        l1_xyz, l1_points = net.sa1(l0_xyz, events)
+        # sa2 draws its own randint; capture it by seeding around the call
+        s2 = seeded_starts(12, 512, 2)
+        l2_xyz, l2_points = net.sa2(l1_xyz, l1_points)
+        l3_xyz, l3_points = net.sa3(l2_xyz, l2_points)
+    # recover index outputs by re-running the free functions on the same inputs
+    xyz0 = l0_xyz.permute(0, 2, 1).contiguous()
+    torch.manual_seed(11)
+    f1 = pu.farthest_point_sample(xyz0, 512)
+    assert torch.equal(pu.index_points(xyz0, f1).permute(0, 2, 1), l1_xyz)
+    xyz1 = l1_xyz.permute(0, 2, 1).contiguous()
+    torch.manual_seed(12)
+    f2 = pu.farthest_point_sample(xyz1, 128)
+    c2 = pu.index_points(xyz1, f2)
+    assert torch.equal(c2.permute(0, 2, 1), l2_xyz)
+    enc = {"events": events.numpy(), "start_sa1": s1.numpy(), "start_sa2": s2.numpy(),
+           "fps_sa1": small_idx(f1.numpy()), "fps_sa2": small_idx(f2.numpy()),
+           "ball_sa2_r0.4": small_idx(pu.query_ball_point(0.4, 64, xyz1, c2).numpy()),
+           "ball_sa2_r0.8": small_idx(pu.query_ball_point(0.8, 128, xyz1, c2).numpy()),
+           "l1_xyz": l1_xyz.numpy(), "l2_xyz": l2_xyz.numpy(), "l3_xyz": l3_xyz.numpy(),
+           "l1_points_w0": l1_points[0].numpy(), "l2_points_w0": l2_points[0].numpy(),
+           "l3_points": l3_points.numpy(), "weight_seeds": np.array([100, 101, 102])}
+    np.savez_compressed(os.path.join(HERE, "encoder.npz"), **enc)
+
+    # ---- 4. one hand regressor's sa1 -> sa2 ------------------------------------
+    reg = net.left_mano_regressor
+    rstates = {n: synth.random_state_for(synth.REGRESSOR_SPECS[n], seed=200 + i)
+               for i, n in enumerate(("sa1", "sa2"))}
+    for n in rstates:
+        getattr(reg, n).load_state_dict(to_t(rstates[n]), strict=True)
+    hand = torch.from_numpy(np.random.RandomState(77).randn(2, 4, 2048).astype(np.float32))
+    s3 = seeded_starts(13, 2048, 2)
+    with torch.no_grad():
+        r1_xyz, r1_points = reg.sa1(l0_xyz, hand)
+        r2_xyz, r2_points = reg.sa2(r1_xyz, r1_points)
+    np.savez_compressed(os.path.join(HERE, "regressor.npz"), events=events.numpy(), hand_feats=hand.numpy(),
+                        start_sa1=s3.numpy(), r1_xyz=r1_xyz.numpy(), r1_points_w0=r1_points[0].numpy(),
+                        r2_points=r2_points.numpy(), weight_seeds=np.array([200, 201]))
+
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
