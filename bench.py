@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the set-abstraction encoder hot path: event-windows per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One *step* is one forward of the encoder stack sa1 -> sa2 -> sa3 (TEHNet.py:172-181) over
+one batch of synthetic event windows ([B, 5, 2048] float32, ev2hands_b200.synth).  At N=1
+the workload is BASELINE.json configs[1] (64 windows on one B200); for N>1 every rank
+processes its own 64 windows (weak scaling: windows are independent, no collective on the
+inference path) and `value` is the total windows of all ranks divided by the slowest
+rank's device time.
+
+Printed JSON (one line, rank 0): the driver contract plus
+  roofline      dominant kernel (the shared-MLP layers) against the measured tensor peak
+  kernels       device ms per step and launches per step of every kernel of the path
+  cpu_baseline  the oracle port of the reference encoder timed on the host cores
+  e2e           the same metric through the public module API with host buffers
+                (pinned H2D of the windows + D2H of the features inside the timed region)
+
+--impl reference times the CPU oracle port of the reference (oracle/sa_oracle.py, the
+reference's algorithm op for op; /root/reference itself does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOWS_PER_GPU = 64
+N_POINTS = 2048
+# dense multiply-accumulates per window of sa1+sa2+sa3, 2 flops each
+MLP_MAC_PER_WINDOW = 4_468_080_640
+ALGO_BYTES_PER_WINDOW = 1_900_000       # compulsory HBM traffic per window
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {k: float(d[k]) for k in FALLBACK_PEAKS}, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ----------------------------------------------------------------------------- CPU oracle arm ----
+def oracle_states():
+    from ev2hands_b200 import synth
+    return {n: synth.random_state_for(synth.ENCODER_SPECS[n], seed=100 + i) for i, n in enumerate(("sa1", "sa2", "sa3"))}
+
+
+def time_cpu_oracle(n_windows: int, reps: int, warmup: int):
+    """Reference algorithm (oracle port) on the host: returns (windows/s, threads, seconds per rep)."""
+    from ev2hands_b200 import synth
+    from oracle import sa_oracle
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    states = oracle_states()
+    ev = torch.from_numpy(synth.make_windows(n_windows, N_POINTS, seed=1234 + 1))
+    starts = {"sa1": torch.from_numpy(synth.make_start_indices(n_windows, N_POINTS, 0)),
+              "sa2": torch.from_numpy(synth.make_start_indices(n_windows, 512, 1))}
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            sa_oracle.encoder_forward(states, synth.ENCODER_SPECS, ev, starts)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return n_windows / (sum(times) / len(times)), threads, times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = 4
+    t0 = time.perf_counter()
+    wps, threads, times = time_cpu_oracle(sample, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "encoder event-windows/s", "value": wps, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "encoder forward sa1->sa2->sa3, %d-window sample of the batch-64 workload per step, "
+                               "N=2048 points/window, random-init weights, host CPU" % sample},
+        "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": threads, "kind": "port",
+                         "sample": "%d windows per step x %d steps (oracle/sa_oracle.py, torch CPU)" % (sample, len(times))},
+        "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm -----------
+def build_encoder(device):
+    import ev2hands_b200 as e2h
+    from ev2hands_b200 import synth
+    from ev2hands_b200.encoder import load_numpy_state
+    enc = e2h.SetAbstractionEncoder()
+    for i, n in enumerate(("sa1", "sa2", "sa3")):
+        load_numpy_state(getattr(enc, n), synth.random_state_for(synth.ENCODER_SPECS[n], seed=100 + i))
+    return enc.to(device).eval()
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from ev2hands_b200 import _capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the ev2hands_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world and rank == 0:
+        print("bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+
+    B = args.windows_per_gpu
+    enc = build_encoder(device)
+    # Every rank owns its shard of the global batch; starts are generated for the global batch
+    # and sharded with the data so results do not depend on the shard count.
+    ev_all = synth.make_windows(B * world, N_POINTS, seed=1234 + 2)
+    s1_all = synth.make_start_indices(B * world, N_POINTS, 0)
+    s2_all = synth.make_start_indices(B * world, 512, 1)
+    sl = slice(rank * B, (rank + 1) * B)
+    ev_host = torch.from_numpy(ev_all[sl]).pin_memory()
+    s1 = torch.from_numpy(s1_all[sl]).to(device)
+    s2 = torch.from_numpy(s2_all[sl]).to(device)
+    ev_dev = ev_host.to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+
+    def step_resident():
+        with torch.no_grad():
+            return enc(ev_dev, fps_starts=(s1, s2))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+
+    # ---- timed region: K steps, device time per step from CUDA events, L2 flushed between steps
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    _capi.LOG.reset(timing=True)
+    evs = []
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = step_resident()
+        b.record()
+        evs.append((a, b))
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.finish()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    launches = _capi.LOG.count
+    kern = _capi.LOG.totals_ms()
+    _capi.LOG.reset(timing=False)
+
+    # ---- end to end through the module API with host buffers (H2D + forward + D2H per step)
+    out_host = torch.empty((B, 1024), dtype=torch.float32).pin_memory()
+    ev_stage = torch.empty_like(ev_dev)
+
+    def step_e2e():
+        ev_stage.copy_(ev_host, non_blocking=True)
+        with torch.no_grad():
+            o = enc(ev_stage)              # FPS start indices drawn on the host like the reference does
+        out_host.copy_(o, non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e_evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_e2e()
+        b.record()
+        e_evs.append((a, b))
+    barrier()
+    e2e_ms = float(sum(a.elapsed_time(b) for a, b in e_evs))
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_kind = load_peaks()
+    windows = B * world * args.steps
+    value = windows / (total_ms / 1e3)
+    mlp_n, mlp_ms = kern.get("ev2h_linear_relu_f32", (0, 0.0))
+    mlp_flops_per_step = 2.0 * MLP_MAC_PER_WINDOW * B
+    achieved_tflops = (mlp_flops_per_step * args.steps) / (mlp_ms / 1e3) / 1e12 if mlp_ms > 0 else None
+    # the bench's timed region is a few ms long: burst peak applies (kernel timed in isolation)
+    peak_tflops = peaks["bf16_tflops"]
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("mlp_dram_bytes_per_step")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "encoder event-windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "encoder forward sa1->sa2->sa3 (TEHNet.py:172-181), %d windows per GPU, "
+                               "N=2048 points/window, 5 channels, random-init weights, eval mode" % B,
+                   "windows_per_gpu": B, "global_windows": B * world, "mlp_path": "fp32 FFMA",
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)"},
+        "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                     "frac": (achieved_tflops / peak_tflops) if achieved_tflops else None, "traffic": traffic,
+                     "kernel": "linear_relu_kernel (shared MLP layers, %d launches/step)" % (mlp_n // max(args.steps, 1)),
+                     "peak_source": "%s bf16 dense (burst)" % peak_kind,
+                     "algorithmic_flops_per_launch_set": mlp_flops_per_step,
+                     "hbm_view": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_WINDOW * B,
+                                  "achieved_gbs_whole_step": ALGO_BYTES_PER_WINDOW * B * args.steps / (total_ms / 1e3) / 1e9,
+                                  "peak_gbs": peaks["hbm_gbs"]}},
+        "kernels": {k: {"launches_per_step": n / args.steps, "ms_per_step": ms / args.steps} for k, (n, ms) in sorted(kern.items())},
+        "e2e": {"value": windows / (e2e_ms / 1e3), "unit": "windows/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(ev_host.numel() * 4 + 2 * B * 8), "d2h_bytes_per_step": int(out_host.numel() * 4)},
+        "gpu_launches": launches, "clocks": clocks, "wall_s": wall,
+        "checksum": float(out.double().sum().item()),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        wps, threads, times = time_cpu_oracle(4, 3, 1)
+        line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": threads, "kind": "port",
+                                "sample": "4 windows per run, 1 warm-up + 3 timed runs of oracle/sa_oracle.py (torch CPU, "
+                                          "the reference's algorithm op for op)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

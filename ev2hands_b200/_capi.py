@@ -1,0 +1,272 @@
+"""ctypes binding of libev2h.so (include/ev2h.h) for torch CUDA tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every compute step
+is a call into the C ABI with raw pointers.  There is no fallback: if the
+library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libev2h.so")
+_lib = None
+
+c_int, c_i64, c_f, c_d, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+
+# name -> argtypes (restype is always int except where noted); mirrors include/ev2h.h
+_SIGNATURES = {
+    "ev2h_fps_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "ev2h_ball_query_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int,
+                            ctypes.POINTER(c_f), ctypes.POINTER(ctypes.c_int32), c_vp, c_vp],
+    "ev2h_square_distance_f32": [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_index_rows_f32": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_group_gather_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_vp, c_int, c_int,
+                              c_int, c_int, c_int, c_int, c_vp, c_int, c_vp],
+    "ev2h_group_gather_bwd_f32": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_transpose_f32": [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_vp],
+    "ev2h_fold_conv_bn_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_int, c_int, c_vp, c_vp, c_vp],
+    "ev2h_linear_relu_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
+    "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "ev2h_group_max_bwd_f32": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+}
+
+
+def declared_symbols():
+    """Every function include/ev2h.h declares (parsed from the header itself)."""
+    import re
+    with open(os.path.join(_PKG, "..", "include", "ev2h.h")) as f:
+        return sorted(set(re.findall(r"EV2H_API\s+[\w\s\*]+?\b(ev2h_\w+)\s*\(", f.read())))
+
+
+def lib() -> ctypes.CDLL:
+    """Load libev2h.so; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libev2h.so is not built (%s). Run `python -m ev2hands_b200.build` "
+                "(needs nvcc); there is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.ev2h_version.restype = c_int
+        L.ev2h_last_error.restype = ctypes.c_char_p
+        for name, args in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        _lib = L
+    return _lib
+
+
+class LaunchLog:
+    """Counts kernel launches (every compute entry point of the ABI enqueues exactly one
+    kernel) and, when ``timing`` is on, brackets each with CUDA events on its stream so
+    bench.py can report per-kernel device time from inside the timed region."""
+
+    def __init__(self):
+        self.count = 0
+        self.timing = False
+        self.events = []          # (name, start_event, end_event)
+
+    def reset(self, timing: bool = False):
+        self.count = 0
+        self.timing = timing
+        self.events = []
+
+    def totals_ms(self):
+        """{name: (launches, total_ms)}; call after a device synchronize."""
+        out = {}
+        for name, a, b in self.events:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + a.elapsed_time(b))
+        return out
+
+
+LOG = LaunchLog()
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        LOG.count += 1
+        if LOG.timing:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if LOG.timing:
+            self.b.record()
+            LOG.events.append((self.name, self.a, self.b))
+        return False
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = lib().ev2h_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (status %d): %s" % (what, status, msg))
+
+
+def _stream(t: torch.Tensor):
+    return c_vp(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t):
+    return c_vp(0) if t is None else c_vp(t.data_ptr())
+
+
+def _need_cuda_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: ev2hands_b200 has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s must be float32, got %s" % (name, t.dtype))
+
+
+def cf_strides(xyz_cf: torch.Tensor):
+    """Element strides (batch, channel, point) of a channel-first [B,3,N] tensor."""
+    return xyz_cf.stride(0), xyz_cf.stride(1), xyz_cf.stride(2)
+
+
+def rows_strides(xyz_rows: torch.Tensor):
+    """Same triple for a point-major [B,N,3] tensor."""
+    return xyz_rows.stride(0), xyz_rows.stride(2), xyz_rows.stride(1)
+
+
+def fps(xyz: torch.Tensor, strides, start: torch.Tensor, B: int, N: int, S: int,
+        want_rows=True, want_cf=True):
+    """-> (idx int32 [B,S], centres_rows [B,S,3] | None, centres_cf [B,3,S] | None)"""
+    _need_cuda_f32(xyz, "xyz")
+    dev = xyz.device
+    start = start.to(device=dev, dtype=torch.int64).contiguous()
+    idx = torch.empty((B, S), dtype=torch.int32, device=dev)
+    rows = torch.empty((B, S, 3), dtype=torch.float32, device=dev) if want_rows else None
+    cf = torch.empty((B, 3, S), dtype=torch.float32, device=dev) if want_cf else None
+    with torch.cuda.device(dev):
+        with _timed("ev2h_fps_f32"):
+            _check(lib().ev2h_fps_f32(_p(xyz), strides[0], strides[1], strides[2], _p(start), B, N, S,
+                                  _p(idx), _p(rows), _p(cf), _stream(xyz)), "ev2h_fps_f32")
+    return idx, rows, cf
+
+
+def radius_sq_f32(radius: float) -> float:
+    """float(radius**2) rounded to fp32: what aten compares against (pointnet2_utils.py:102)."""
+    return torch.tensor(float(radius) ** 2, dtype=torch.float32).item()
+
+
+def ball_query(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: int, radii, nsamples):
+    """-> idx int32 [B,S,sum(K)]"""
+    _need_cuda_f32(xyz, "xyz")
+    _need_cuda_f32(centres_rows, "centres")
+    B, S, _ = centres_rows.shape
+    ns = len(radii)
+    r2 = (c_f * ns)(*[radius_sq_f32(r) for r in radii])
+    ks = (ctypes.c_int32 * ns)(*[int(k) for k in nsamples])
+    out = torch.empty((B, S, int(sum(nsamples))), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        with _timed("ev2h_ball_query_f32"):
+            _check(lib().ev2h_ball_query_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows.contiguous()),
+                                         B, N, S, ns, r2, ks, _p(out), _stream(xyz)), "ev2h_ball_query_f32")
+    return out
+
+
+def square_distance(src_rows: torch.Tensor, dst_rows: torch.Tensor) -> torch.Tensor:
+    _need_cuda_f32(src_rows, "src")
+    _need_cuda_f32(dst_rows, "dst")
+    src_rows, dst_rows = src_rows.contiguous(), dst_rows.contiguous()
+    B, S, _ = src_rows.shape
+    N = dst_rows.shape[1]
+    out = torch.empty((B, S, N), dtype=torch.float32, device=src_rows.device)
+    with torch.cuda.device(src_rows.device):
+        with _timed("ev2h_square_distance_f32"):
+            _check(lib().ev2h_square_distance_f32(_p(src_rows), _p(dst_rows), B, S, N, _p(out), _stream(out)),
+               "ev2h_square_distance_f32")
+    return out
+
+
+def index_rows(table_rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    _need_cuda_f32(table_rows, "points")
+    table_rows = table_rows.contiguous()
+    B, N, C = table_rows.shape
+    idx32 = idx.to(device=table_rows.device, dtype=torch.int32).contiguous()
+    M = idx32[0].numel()
+    out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=table_rows.device)
+    with torch.cuda.device(table_rows.device):
+        with _timed("ev2h_index_rows_f32"):
+            _check(lib().ev2h_index_rows_f32(_p(table_rows), _p(idx32), B, N, M, C, _p(out), _stream(out)),
+               "ev2h_index_rows_f32")
+    return out
+
+
+def group_gather(xyz, strides, feats_rows, D, centres_rows, idx, k_off, B, N, S, K, out, ld_out):
+    with torch.cuda.device(xyz.device):
+        with _timed("ev2h_group_gather_f32"):
+            _check(lib().ev2h_group_gather_f32(_p(xyz), strides[0], strides[1], strides[2], _p(feats_rows), D,
+                                           _p(centres_rows), _p(idx), idx.shape[-1], k_off, B, N, S, K,
+                                           _p(out), ld_out, _stream(xyz)), "ev2h_group_gather_f32")
+
+
+def group_gather_bwd(grad_rows, ld_grad, idx, k_off, B, N, S, K, D, grad_feats_rows):
+    with torch.cuda.device(grad_rows.device):
+        with _timed("ev2h_group_gather_bwd_f32"):
+            _check(lib().ev2h_group_gather_bwd_f32(_p(grad_rows), ld_grad, _p(idx), idx.shape[-1], k_off, B, N, S, K, D,
+                                               _p(grad_feats_rows), _stream(grad_rows)), "ev2h_group_gather_bwd_f32")
+
+
+def transpose(src, src_strides, B, R, C, dst, dst_stride_b, dst_ld, dst_col_off=0):
+    """dst[b, c, dst_col_off + r] = src[b, r, c] with explicit element strides."""
+    with torch.cuda.device(src.device):
+        with _timed("ev2h_transpose_f32"):
+            _check(lib().ev2h_transpose_f32(_p(src), src_strides[0], src_strides[1], src_strides[2], B, R, C,
+                                        _p(dst), dst_stride_b, dst_ld, dst_col_off, _stream(src)), "ev2h_transpose_f32")
+
+
+def fold_conv_bn(conv_w, conv_b, gamma, beta, mean, var, eps: float):
+    """-> (wt [Cin_pad, Cout_pad], bias [Cout_pad]) fp32 on the weights' device."""
+    Cout, Cin = conv_w.shape[0], conv_w.shape[1]
+    cin_pad, cout_pad = (Cin + 15) // 16 * 16, (Cout + 127) // 128 * 128
+    dev = conv_w.device
+    wt = torch.empty((cin_pad, cout_pad), dtype=torch.float32, device=dev)
+    bias = torch.empty((cout_pad,), dtype=torch.float32, device=dev)
+    args = [t.detach().contiguous().float() for t in (conv_w.reshape(Cout, Cin), conv_b, gamma, beta, mean, var)]
+    with torch.cuda.device(dev):
+        with _timed("ev2h_fold_conv_bn_f32"):
+            _check(lib().ev2h_fold_conv_bn_f32(*[_p(a) for a in args], float(eps), Cin, Cout, _p(wt), _p(bias),
+                                           _stream(wt)), "ev2h_fold_conv_bn_f32")
+    return wt, bias
+
+
+def linear_relu(x, M, ld_x, Cin, wt, bias, Cout, pool_rows, y, ld_y, y_col_off=0):
+    with torch.cuda.device(x.device):
+        with _timed("ev2h_linear_relu_f32"):
+            _check(lib().ev2h_linear_relu_f32(_p(x), M, ld_x, Cin, _p(wt), _p(bias), Cout, pool_rows, _p(y), ld_y,
+                                          y_col_off, _stream(x)), "ev2h_linear_relu_f32")
+
+
+def group_max(x: torch.Tensor, want_arg: bool = True):
+    """x [B,C,K,S] contiguous -> (out [B,C,S], arg int32 [B,C,S] | None)"""
+    _need_cuda_f32(x, "x")
+    x = x.contiguous()
+    B, C, K, S = x.shape
+    out = torch.empty((B, C, S), dtype=torch.float32, device=x.device)
+    arg = torch.empty((B, C, S), dtype=torch.int32, device=x.device) if want_arg else None
+    with torch.cuda.device(x.device):
+        with _timed("ev2h_group_max_f32"):
+            _check(lib().ev2h_group_max_f32(_p(x), B, C, K, S, _p(out), _p(arg), _stream(x)), "ev2h_group_max_f32")
+    return out, arg
+
+
+def group_max_bwd(grad_out: torch.Tensor, arg: torch.Tensor, K: int) -> torch.Tensor:
+    grad_out = grad_out.contiguous()
+    B, C, S = grad_out.shape
+    gx = torch.empty((B, C, K, S), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        with _timed("ev2h_group_max_bwd_f32"):
+            _check(lib().ev2h_group_max_bwd_f32(_p(grad_out), _p(arg), B, C, K, S, _p(gx), _stream(gx)),
+               "ev2h_group_max_bwd_f32")
+    return gx

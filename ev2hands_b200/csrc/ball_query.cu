@@ -1,0 +1,183 @@
+// Multi-radius ball query: one thread per centre, all radii of a layer in one
+// scan over the window's points.
+//
+// Replaces query_ball_point + square_distance (reference
+// src/Ev2Hands/model/pointnet2_utils.py:87-107, :19-40).  The reference builds a
+// [B,S,N] int64 index matrix, masks it, and SORTS every row to find the first K
+// in-radius indices; scanning the points in index order yields the same list
+// directly, so memory is O(S*K) and nothing is sorted.
+//
+// Bit-exactness with the reference lives in sqdist_expanded(): same expression,
+// same rounding order as aten's  -2*matmul + |q|^2 + |p|^2  (see SURVEY.md 7.1).
+#include "common.cuh"
+
+namespace ev2h {
+
+constexpr int kMaxScales = 4;
+constexpr int kBqThreads = 64;    // centres per CTA
+constexpr int kBqTile = 1024;     // points staged per pass (16 KB of float4)
+
+struct BallParams {
+    float r2[kMaxScales];
+    int K[kMaxScales];
+    int k_off[kMaxScales];
+    int k_total;
+    float r2_max;
+};
+
+__device__ __forceinline__ float sq_norm3(float x, float y, float z) {
+    // torch.sum(v ** 2, -1): (x*x + y*y) + z*z, nothing fused
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+__device__ __forceinline__ float sqdist_expanded(float qx, float qy, float qz, float qn, const float4 p) {
+    float dot = __fmul_rn(qx, p.x);          // sgemm with K = 3: x*x', then two FMAs
+    dot = __fmaf_rn(qy, p.y, dot);
+    dot = __fmaf_rn(qz, p.z, dot);
+    float t = __fmul_rn(-2.0f, dot);         // dist = -2 * matmul           (:37)
+    t = __fadd_rn(t, qn);                    // dist += sum(src**2)          (:38)
+    t = __fadd_rn(t, p.w);                   // dist += sum(dst**2)          (:39)
+    return t;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kBqThreads)
+ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
+                  const float *__restrict__ centres, int N, int S, BallParams prm,
+                  int32_t *__restrict__ out) {
+    __shared__ float4 pts[kBqTile];
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * kBqThreads + threadIdx.x;
+    const bool live = s < S;
+    const float *base = xyz + (int64_t)b * sb;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (live) {
+        const float *c = centres + ((int64_t)b * S + s) * 3;
+        qx = c[0]; qy = c[1]; qz = c[2];
+    }
+    const float qn = sq_norm3(qx, qy, qz);
+    int32_t *row = out + ((int64_t)b * S + (live ? s : 0)) * prm.k_total;
+
+    int cnt[NS], first[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { cnt[i] = 0; first[i] = N; }
+    bool full = !live;
+
+    for (int t0 = 0; t0 < N; t0 += kBqTile) {
+        const int n_tile = min(kBqTile, N - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_tile; i += kBqThreads) {
+            const int64_t g = (int64_t)(t0 + i) * sn;
+            const float x = base[g], y = base[sc + g], z = base[2 * sc + g];
+            pts[i] = make_float4(x, y, z, sq_norm3(x, y, z));
+        }
+        __syncthreads();
+        if (full) continue;
+        for (int i = 0; i < n_tile; ++i) {
+            const float d = sqdist_expanded(qx, qy, qz, qn, pts[i]);
+            if (d > prm.r2_max) continue;            // outside every radius
+            bool all_full = true;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                if (!(d > prm.r2[k]) && cnt[k] < prm.K[k]) {   // group_idx[sqrdists > r**2] = N  (:102)
+                    if (cnt[k] == 0) first[k] = t0 + i;
+                    row[prm.k_off[k] + cnt[k]] = t0 + i;
+                    ++cnt[k];
+                }
+                all_full = all_full && (cnt[k] >= prm.K[k]);
+            }
+            if (all_full) { full = true; break; }
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)                     // pad with the first hit (:104-106)
+        for (int j = cnt[k]; j < prm.K[k]; ++j) row[prm.k_off[k] + j] = first[k];
+}
+
+// square_distance as a standalone op (pointnet2_utils.py:19-40): out[b,s,n], bit-exact.
+__global__ void __launch_bounds__(256)
+square_distance_kernel(const float *__restrict__ src, const float *__restrict__ dst, int S, int N,
+                       float *__restrict__ out, int64_t total) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int n = (int)(e % N);
+    const int64_t bs = e / N;
+    const int64_t b = bs / S;
+    const float *q = src + bs * 3, *p = dst + (b * N + n) * 3;
+    const float4 pp = make_float4(p[0], p[1], p[2], sq_norm3(p[0], p[1], p[2]));
+    out[e] = sqdist_expanded(q[0], q[1], q[2], sq_norm3(q[0], q[1], q[2]), pp);
+}
+
+// index_points (pointnet2_utils.py:43-60): out[b,m,:] = table[b, idx[b,m], :]
+__global__ void __launch_bounds__(256)
+index_rows_kernel(const float *__restrict__ table, const int32_t *__restrict__ idx, int N, int Mi, int C,
+                  float *__restrict__ out, int64_t total) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int c = (int)(e % C);
+    const int64_t bm = e / C;
+    const int64_t b = bm / Mi;
+    const int p = idx[bm];
+    out[e] = (p >= 0 && p < N) ? table[(b * N + p) * (int64_t)C + c] : 0.f;
+}
+
+}  // namespace ev2h
+
+extern "C" int ev2h_square_distance_f32(const float *src_rows, const float *dst_rows, int B, int S, int N,
+                                        float *out, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(src_rows && dst_rows && out, "ev2h_square_distance_f32: null argument");
+    EV2H_REQUIRE(B > 0 && S > 0 && N > 0, "ev2h_square_distance_f32: bad sizes");
+    const int64_t total = (int64_t)B * S * N;
+    square_distance_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(src_rows, dst_rows, S, N, out, total);
+    return check_launch("ev2h_square_distance_f32");
+}
+
+extern "C" int ev2h_index_rows_f32(const float *table_rows, const int32_t *idx, int B, int N, int M, int C,
+                                   float *out, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(table_rows && idx && out, "ev2h_index_rows_f32: null argument");
+    EV2H_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0, "ev2h_index_rows_f32: bad sizes");
+    const int64_t total = (int64_t)B * M * C;
+    index_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(table_rows, idx, N, M, C, out, total);
+    return check_launch("ev2h_index_rows_f32");
+}
+
+extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                   const float *centres_rows, int B, int N, int S, int n_scales,
+                                   const float *radius_sq_host, const int32_t *nsample_host,
+                                   int32_t *out_idx, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(xyz && centres_rows && out_idx && radius_sq_host && nsample_host, "ev2h_ball_query_f32: null argument");
+    EV2H_REQUIRE(B > 0 && N > 0 && S > 0, "ev2h_ball_query_f32: B, N, S must be positive");
+    EV2H_REQUIRE(B <= 65535, "ev2h_ball_query_f32: B=%d exceeds 65535 windows per call", B);
+    if (n_scales < 1 || n_scales > kMaxScales)
+        return fail(EV2H_ERR_UNSUPPORTED, "ev2h_ball_query_f32: n_scales=%d not in 1..%d", n_scales, kMaxScales);
+    BallParams prm;
+    int off = 0;
+    prm.r2_max = radius_sq_host[0];
+    for (int i = 0; i < kMaxScales; ++i) {
+        const bool on = i < n_scales;
+        prm.r2[i] = on ? radius_sq_host[i] : 0.f;
+        prm.K[i] = on ? nsample_host[i] : 0;
+        prm.k_off[i] = off;
+        if (on) {
+            EV2H_REQUIRE(nsample_host[i] > 0, "ev2h_ball_query_f32: nsample[%d] must be positive", i);
+            off += nsample_host[i];
+            // NaN-safe max: keep a NaN radius out of r2_max so the prefilter never drops a candidate
+            if (radius_sq_host[i] > prm.r2_max) prm.r2_max = radius_sq_host[i];
+        }
+    }
+    prm.k_total = off;
+    dim3 grid((S + kBqThreads - 1) / kBqThreads, B);
+    cudaStream_t st = as_stream(stream);
+    switch (n_scales) {
+        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
+        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
+        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
+        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
+    }
+    return check_launch("ev2h_ball_query_f32");
+}

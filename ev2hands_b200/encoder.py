@@ -1,0 +1,69 @@
+"""The encoder stack of the model: sa1 -> sa2 -> sa3, wired exactly as
+``TEHNet.forward`` does (reference ``src/Ev2Hands/model/TEHNet.py:127-129`` for the
+constructor arguments, ``:172-181`` for the data flow), plus one hand regressor's
+``sa1 -> sa2`` (``TEHNet.py:43-44``, ``:75-79``).  This is the unit BASELINE.json's
+metric ("encoder event-windows/s") is measured on.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from .pointnet2_utils import PointNetSetAbstraction, PointNetSetAbstractionMsg
+
+
+class SetAbstractionEncoder(nn.Module):
+    """events [B, 3+extra, N] -> per-window features [B, 1024].
+
+    ``extra`` follows TEHNet.__init__ (``1 + int(os.getenv('ERPC', 0))``, TEHNet.py:122);
+    the dataset modules set ERPC=1, which gives the 5-channel windows used everywhere."""
+
+    def __init__(self, extra_channels: int | None = None):
+        super().__init__()
+        if extra_channels is None:
+            extra_channels = 1 + int(os.getenv("ERPC", 1))
+        self.sa1 = PointNetSetAbstractionMsg(512, [0.1, 0.2, 0.4], [32, 64, 128], 3 + extra_channels,
+                                             [[32, 32, 64], [64, 64, 128], [64, 96, 128]])
+        self.sa2 = PointNetSetAbstractionMsg(128, [0.4, 0.8], [64, 128], 128 + 128 + 64,
+                                             [[128, 128, 256], [128, 196, 256]])
+        self.sa3 = PointNetSetAbstraction(npoint=None, radius=None, nsample=None, in_channel=512 + 3,
+                                          mlp=[256, 512, 1024], group_all=True)
+
+    def forward(self, events, fps_starts=None, return_levels=False):
+        """``fps_starts`` = optional (start_sa1, start_sa2) int64 [B] tensors replacing the two
+        ``torch.randint`` draws the reference makes (in this order) per forward."""
+        s1, s2 = fps_starts if fps_starts is not None else (None, None)
+        l0_xyz = events[:, :3, :]
+        l1_xyz, l1_points = self.sa1(l0_xyz, events, fps_start=s1)
+        l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, fps_start=s2)
+        _, l3_points = self.sa3(l2_xyz, l2_points)
+        out = l3_points.squeeze(-1)
+        if return_levels:
+            return out, {"l1_xyz": l1_xyz, "l1_points": l1_points, "l2_xyz": l2_xyz, "l2_points": l2_points}
+        return out
+
+
+class RegressorSetAbstraction(nn.Module):
+    """The set-abstraction half of MANORegressor (TEHNet.py:43-44): (xyz [B,3,N],
+    hand features [B,4,N]) -> [B, 512]."""
+
+    def __init__(self, n_inp_features: int = 4):
+        super().__init__()
+        self.sa1 = PointNetSetAbstractionMsg(128, [0.4, 0.8], [64, 128], n_inp_features,
+                                             [[128, 128, 256], [128, 196, 256]])
+        self.sa2 = PointNetSetAbstraction(npoint=None, radius=None, nsample=None, in_channel=512 + 3,
+                                          mlp=[256, 512], group_all=True)
+
+    def forward(self, xyz, features, fps_start=None):
+        l1_xyz, l1_points = self.sa1(xyz, features, fps_start=fps_start)
+        _, l2_points = self.sa2(l1_xyz, l1_points)
+        return l2_points.squeeze(-1)
+
+
+def load_numpy_state(module: nn.Module, state: dict):
+    """strict load of a {name: numpy array} state dict (ev2hands_b200.synth.random_state_for)."""
+    module.load_state_dict({k: torch.from_numpy(v.copy()) if hasattr(v, "dtype") else v for k, v in state.items()},
+                           strict=True)
+    return module

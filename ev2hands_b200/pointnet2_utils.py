@@ -1,0 +1,439 @@
+"""Drop-in replacement for the reference's ``src/Ev2Hands/model/pointnet2_utils.py``.
+
+Same public names, constructor arguments, forward signatures, parameter and
+buffer names (so reference checkpoints load with ``strict=True``), but every
+step of the set-abstraction hot path runs in the hand-written sm_100a kernels of
+``libev2h.so`` (C ABI in ``include/ev2h.h``):
+
+    farthest_point_sample  -> ev2h_fps_f32             (reference :63-84)
+    query_ball_point       -> ev2h_ball_query_f32      (reference :87-107)
+    square_distance        -> ev2h_square_distance_f32 (reference :19-40)
+    index_points           -> ev2h_index_rows_f32      (reference :43-60)
+    grouping               -> ev2h_group_gather_f32    (reference :244-248)
+    conv1x1+BN+ReLU, max   -> ev2h_linear_relu_f32 ... (reference :253-257)
+
+There is no CPU path: tensors must live on a CUDA device and a missing library
+raises.  ``PointNetFeaturePropagation`` (the decoder, outside the hot path) is
+kept in plain PyTorch so that ``TEHNet.py:6`` can import all three names.
+
+Eval mode runs the fused inference path (BatchNorm folded into the weights).
+Training mode, or eval mode with autograd active, keeps convolution, BatchNorm
+(batch statistics) and ReLU in PyTorch and uses the CUDA kernels for FPS, ball
+query, grouping (with scatter-add backward) and max-pool (with arg-max backward).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi
+
+_WORKSPACE_BYTES = int(os.environ.get("EV2H_WORKSPACE_MB", "4096")) << 20
+
+
+def _pad4(c: int) -> int:
+    return (c + 3) // 4 * 4
+
+
+# --------------------------------------------------------------------------------------
+# free functions (same signatures as the reference; tensors are [B, N, C] point-major)
+# --------------------------------------------------------------------------------------
+def square_distance(src, dst):
+    """[B,N,3],[B,M,3] -> [B,N,M]; bit-identical to the reference's expanded form."""
+    return _capi.square_distance(src, dst)
+
+
+def index_points(points, idx):
+    """points [B,N,C], idx [B,...] -> [B,...,C]."""
+    return _capi.index_rows(points, idx)
+
+
+def farthest_point_sample(xyz, npoint, start=None):
+    """xyz [B,N,3] -> int64 [B,npoint].  ``start`` overrides the random first index,
+    which is otherwise drawn exactly like the reference does (CPU generator)."""
+    B, N, _ = xyz.shape
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long)
+    idx, _, _ = _capi.fps(xyz, _capi.rows_strides(xyz), start, B, N, npoint, want_rows=False, want_cf=False)
+    return idx.long()
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """xyz [B,N,3], new_xyz [B,S,3] -> int64 [B,S,nsample]."""
+    N = xyz.shape[1]
+    return _capi.ball_query(xyz, _capi.rows_strides(xyz), new_xyz, N, [radius], [nsample]).long()
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False):
+    """Reference :110-138 - channels are [rel_xyz, points]."""
+    B, N, C = xyz.shape
+    fps_idx = farthest_point_sample(xyz, npoint)
+    new_xyz = index_points(xyz, fps_idx)
+    idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    grouped_xyz = index_points(xyz, idx)
+    rel = grouped_xyz - new_xyz.view(B, npoint, 1, C)
+    new_points = torch.cat([rel, index_points(points, idx)], dim=-1) if points is not None else rel
+    if returnfps:
+        return new_xyz, new_points, grouped_xyz, fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """Reference :141-158 - one group of all points, channels [xyz, points]."""
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device)
+    g = xyz.view(B, 1, N, C)
+    if points is not None:
+        g = torch.cat([g, points.view(B, 1, N, -1)], dim=-1)
+    return new_xyz, g
+
+
+# --------------------------------------------------------------------------------------
+# autograd pieces for the training path
+# --------------------------------------------------------------------------------------
+class _GroupGather(torch.autograd.Function):
+    """rows(b,s,j) = [feats[b, idx] | xyz[idx] - centre]; gradient flows to feats only
+    (xyz never requires grad in the model)."""
+
+    @staticmethod
+    def forward(ctx, feats_rows, xyz, strides, N, centres_rows, idx, k_off, K):
+        B, S, _ = centres_rows.shape
+        D = 0 if feats_rows is None else feats_rows.shape[2]
+        ld = D + 3
+        out = torch.empty((B, S, K, ld), dtype=torch.float32, device=centres_rows.device)
+        _capi.group_gather(xyz, strides, feats_rows, D, centres_rows, idx, k_off, B, N, S, K, out, ld)
+        ctx.save_for_backward(idx)
+        ctx.meta = (k_off, B, N, S, K, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        k_off, B, N, S, K, D = ctx.meta
+        g_feats = None
+        if D > 0 and ctx.needs_input_grad[0]:
+            grad = grad.contiguous()
+            g_feats = torch.zeros((B, N, D), dtype=torch.float32, device=grad.device)
+            _capi.group_gather_bwd(grad, D + 3, idx, k_off, B, N, S, K, D, g_feats)
+        return g_feats, None, None, None, None, None, None, None
+
+
+class _GroupMax(torch.autograd.Function):
+    """max over dim 2 of [B,C,K,S]; the whole gradient goes to the first arg-max."""
+
+    @staticmethod
+    def forward(ctx, x):
+        out, arg = _capi.group_max(x, want_arg=True)
+        ctx.save_for_backward(arg)
+        ctx.K = x.shape[2]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (arg,) = ctx.saved_tensors
+        return _capi.group_max_bwd(grad_out, arg, ctx.K)
+
+
+# --------------------------------------------------------------------------------------
+# folded-weight cache for the inference path
+# --------------------------------------------------------------------------------------
+class _FoldedMLP:
+    """Per-device folded (conv bias + eval BatchNorm) weights of one conv/bn stack.
+
+    Rebuilt whenever any source tensor was replaced or modified in place
+    (``data_ptr`` / ``_version`` change), e.g. after ``load_state_dict`` or an
+    optimiser step, and for every ``nn.DataParallel`` replica."""
+
+    def __init__(self):
+        self.by_device = {}     # device -> (key, layers); replicas on other GPUs keep their own entry
+
+    @staticmethod
+    def _key(convs, bns):
+        k = []
+        for conv, bn in zip(convs, bns):
+            for t in (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var):
+                k.append((t.data_ptr(), t._version, t.device))
+        return tuple(k)
+
+    def get(self, convs, bns, in_perm=None):
+        key = self._key(convs, bns)
+        dev = convs[0].weight.device
+        hit = self.by_device.get(dev)
+        if hit is None or hit[0] != key:
+            layers = []
+            for j, (conv, bn) in enumerate(zip(convs, bns)):
+                w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels)
+                if j == 0 and in_perm is not None:
+                    w = w[:, in_perm]
+                wt, bias = _capi.fold_conv_bn(w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+                layers.append((wt, bias, conv.in_channels, conv.out_channels))
+            self.by_device[dev] = (key, layers)
+            return layers
+        return hit[1]
+
+
+def _mlp_rows(x, M, ld_x, layers, pool_rows, out, ld_out, out_col):
+    """Run the folded MLP over M rows of x; the last layer max-pools runs of pool_rows rows
+    into out[:, out_col : out_col + C_last]."""
+    cur, ld = x, ld_x
+    for j, (wt, bias, cin, cout) in enumerate(layers):
+        last = j == len(layers) - 1
+        if last:
+            _capi.linear_relu(cur, M, ld, cin, wt, bias, cout, pool_rows, out, ld_out, out_col)
+        else:
+            ld_y = _pad4(cout)
+            y = torch.empty((M, ld_y), dtype=torch.float32, device=x.device)
+            _capi.linear_relu(cur, M, ld, cin, wt, bias, cout, 0, y, ld_y, 0)
+            cur, ld = y, ld_y
+
+
+def _check_inputs(xyz, points):
+    if xyz.dim() != 3 or xyz.shape[1] != 3:
+        raise RuntimeError("xyz must be [B, 3, N], got %s" % (tuple(xyz.shape),))
+    if not xyz.is_cuda:
+        raise RuntimeError("ev2hands_b200 runs on CUDA devices only (xyz is on %s); there is no CPU path" % xyz.device)
+    if xyz.dtype != torch.float32 or (points is not None and points.dtype != torch.float32):
+        raise RuntimeError("xyz and points must be float32")
+    if points is not None and (points.dim() != 3 or points.shape[0] != xyz.shape[0] or points.shape[2] != xyz.shape[2]):
+        raise RuntimeError("points must be [B, D, N] matching xyz, got %s" % (tuple(points.shape),))
+
+
+def _to_rows(t_cf):
+    """[B,D,N] (any strides) -> contiguous [B,N,D] through the transpose kernel."""
+    B, D, N = t_cf.shape
+    rows = torch.empty((B, N, D), dtype=torch.float32, device=t_cf.device)
+    _capi.transpose(t_cf, (t_cf.stride(0), t_cf.stride(1), t_cf.stride(2)), B, D, N, rows, N * D, D, 0)
+    return rows
+
+
+def _rows_to_cf(rows):
+    """contiguous [B,S,C] -> contiguous [B,C,S]."""
+    B, S, C = rows.shape
+    cf = torch.empty((B, C, S), dtype=torch.float32, device=rows.device)
+    _capi.transpose(rows, (S * C, C, 1), B, S, C, cf, C * S, S, 0)
+    return cf
+
+
+def _wants_autograd(module, *tensors):
+    if module.training:
+        return True
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """Multi-scale-grouping set abstraction (reference :205-262)."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list):
+        super().__init__()
+        self.npoint = npoint
+        self.radius_list = radius_list
+        self.nsample_list = nsample_list
+        self.conv_blocks = nn.ModuleList()
+        self.bn_blocks = nn.ModuleList()
+        for widths in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            last = in_channel + 3
+            for w in widths:
+                convs.append(nn.Conv2d(last, w, 1))
+                bns.append(nn.BatchNorm2d(w))
+                last = w
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+        self._folded = [_FoldedMLP() for _ in mlp_list]
+
+    # ---- shared front end: FPS + ball query -----------------------------------------
+    def _sample(self, xyz, fps_start):
+        B, _, N = xyz.shape
+        S = self.npoint
+        if fps_start is None:
+            # same draw, from the same (CPU) generator, as pointnet2_utils.py:75
+            fps_start = torch.randint(0, N, (B,), dtype=torch.long)
+        strides = _capi.cf_strides(xyz)
+        fps_idx, centres_rows, new_xyz = _capi.fps(xyz, strides, fps_start, B, N, S)
+        ball = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list)
+        return strides, fps_idx, centres_rows, new_xyz, ball
+
+    def forward(self, xyz, points, fps_start=None):
+        """xyz [B,3,N], points [B,D,N] or None -> (new_xyz [B,3,S], new_points [B,sum D',S])."""
+        _check_inputs(xyz, points)
+        with torch.no_grad():
+            strides, fps_idx, centres_rows, new_xyz, ball = self._sample(xyz.detach(), fps_start)
+        self.last_fps_idx, self.last_ball_idx = fps_idx, ball        # exposed for parity tests
+        if _wants_autograd(self, points):
+            return new_xyz, self._forward_autograd(xyz, points, strides, centres_rows, ball)
+        with torch.no_grad():
+            return new_xyz, self._forward_fused(xyz, points, strides, centres_rows, ball)
+
+    def _forward_fused(self, xyz, points, strides, centres_rows, ball):
+        B, _, N = xyz.shape
+        S = self.npoint
+        D = 0 if points is None else points.shape[1]
+        feats_rows = _to_rows(points) if points is not None else None
+        c_total = sum(convs[-1].out_channels for convs in self.conv_blocks)
+        out_rows = torch.zeros((B, S, c_total), dtype=torch.float32, device=xyz.device)
+        ld_x = _pad4(D + 3)
+        k_off = col = 0
+        for i, K in enumerate(self.nsample_list):
+            layers = self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i])
+            per_window = S * K * 4 * (ld_x + sum(_pad4(l[3]) for l in layers[:-1]))
+            chunk = max(1, min(B, _WORKSPACE_BYTES // per_window))
+            for b0 in range(0, B, chunk):
+                nb = min(chunk, B - b0)
+                M = nb * S * K
+                x = torch.empty((M, ld_x), dtype=torch.float32, device=xyz.device)
+                _capi.group_gather(xyz[b0:b0 + nb], strides, None if feats_rows is None else feats_rows[b0:b0 + nb], D,
+                                   centres_rows[b0:b0 + nb], ball[b0:b0 + nb], k_off, nb, N, S, K, x, ld_x)
+                _mlp_rows(x, M, ld_x, layers, K, out_rows[b0:b0 + nb], c_total, col)
+            k_off += K
+            col += layers[-1][3]
+        return _rows_to_cf(out_rows)
+
+    def _forward_autograd(self, xyz, points, strides, centres_rows, ball):
+        B, _, N = xyz.shape
+        feats_rows = points.permute(0, 2, 1).contiguous() if points is not None else None
+        pooled = []
+        k_off = 0
+        for i, K in enumerate(self.nsample_list):
+            g = _GroupGather.apply(feats_rows, xyz.detach(), strides, N, centres_rows, ball, k_off, K)  # [B,S,K,D+3]
+            g = g.permute(0, 3, 2, 1).contiguous()                                                  # [B,D+3,K,S]
+            for conv, bn in zip(self.conv_blocks[i], self.bn_blocks[i]):
+                g = F.relu(bn(conv(g)))
+            pooled.append(_GroupMax.apply(g))
+            k_off += K
+        return torch.cat(pooled, dim=1)
+
+
+class PointNetSetAbstraction(nn.Module):
+    """Single-scale set abstraction (reference :161-202); the model only uses
+    ``group_all=True`` (TEHNet.py:44, :129)."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all):
+        super().__init__()
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for w in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, w, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(w))
+            last = w
+        self.group_all = group_all
+        self._folded = _FoldedMLP()
+
+    def forward(self, xyz, points, fps_start=None):
+        """xyz [B,3,N], points [B,D,N] or None -> (new_xyz [B,3,S], new_points [B,D',S])."""
+        _check_inputs(xyz, points)
+        autograd = _wants_autograd(self, points)
+        if self.group_all:
+            B = xyz.shape[0]
+            new_xyz = torch.zeros((B, 3, 1), dtype=torch.float32, device=xyz.device)
+            if autograd:
+                return new_xyz, self._group_all_autograd(xyz, points)
+            with torch.no_grad():
+                return new_xyz, self._group_all_fused(xyz, points)
+        return self._forward_sampled(xyz, points, fps_start, autograd)
+
+    # ---- group_all ---------------------------------------------------------------------
+    def _group_all_fused(self, xyz, points):
+        B, _, N = xyz.shape
+        D = 0 if points is None else points.shape[1]
+        cin = 3 + D
+        ld_x = _pad4(cin)
+        # rows = [xyz | points], the channel order of sample_and_group_all (:141-158)
+        x = torch.zeros((B * N, ld_x), dtype=torch.float32, device=xyz.device) if ld_x != cin else \
+            torch.empty((B * N, ld_x), dtype=torch.float32, device=xyz.device)
+        _capi.transpose(xyz, _capi.cf_strides(xyz), B, 3, N, x, N * ld_x, ld_x, 0)
+        if points is not None:
+            _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, x, N * ld_x, ld_x, 3)
+        layers = self._folded.get(self.mlp_convs, self.mlp_bns)
+        c_out = layers[-1][3]
+        out = torch.zeros((B, c_out), dtype=torch.float32, device=xyz.device)
+        _mlp_rows(x, B * N, ld_x, layers, N, out, c_out, 0)
+        return out.view(B, c_out, 1)
+
+    def _group_all_autograd(self, xyz, points):
+        g = xyz.unsqueeze(-1) if points is None else torch.cat([xyz, points], dim=1).unsqueeze(-1)   # [B,C,N,1]
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            g = F.relu(bn(conv(g)))
+        return _GroupMax.apply(g)
+
+    # ---- sampled single-scale (not reached by the model; API completeness) --------------
+    def _forward_sampled(self, xyz, points, fps_start, autograd):
+        B, _, N = xyz.shape
+        S, K = self.npoint, self.nsample
+        D = 0 if points is None else points.shape[1]
+        with torch.no_grad():
+            if fps_start is None:
+                fps_start = torch.randint(0, N, (B,), dtype=torch.long)
+            strides = _capi.cf_strides(xyz)
+            _, centres_rows, new_xyz = _capi.fps(xyz.detach(), strides, fps_start, B, N, S)
+            ball = _capi.ball_query(xyz.detach(), strides, centres_rows, N, [self.radius], [K])
+        # reference channel order here is [rel_xyz, points] (:128); the gather kernel emits
+        # [points, rel_xyz], so the first layer's input channels are permuted instead
+        perm = torch.tensor(list(range(3, 3 + D)) + [0, 1, 2], device=xyz.device)
+        if autograd:
+            feats_rows = points.permute(0, 2, 1).contiguous() if points is not None else None
+            g = _GroupGather.apply(feats_rows, xyz.detach(), strides, N, centres_rows, ball, 0, K)
+            g = g[..., torch.argsort(perm)].permute(0, 3, 2, 1).contiguous()
+            for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+                g = F.relu(bn(conv(g)))
+            return new_xyz, _GroupMax.apply(g)
+        with torch.no_grad():
+            feats_rows = _to_rows(points) if points is not None else None
+            layers = self._folded.get(self.mlp_convs, self.mlp_bns, in_perm=perm)
+            ld_x = _pad4(D + 3)
+            c_out = layers[-1][3]
+            out_rows = torch.zeros((B, S, c_out), dtype=torch.float32, device=xyz.device)
+            x = torch.empty((B * S * K, ld_x), dtype=torch.float32, device=xyz.device)
+            _capi.group_gather(xyz, strides, feats_rows, D, centres_rows, ball, 0, B, N, S, K, x, ld_x)
+            _mlp_rows(x, B * S * K, ld_x, layers, K, out_rows, c_out, 0)
+            return new_xyz, _rows_to_cf(out_rows)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """Decoder block (reference :265-315).  Outside the accelerated hot path (SURVEY.md
+    section 8f, row N1): plain PyTorch, kept so the model file can import the name."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        last = in_channel
+        for w in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, w, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(w))
+            last = w
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        p1 = xyz1.transpose(1, 2)
+        p2 = xyz2.transpose(1, 2)
+        f2 = points2.transpose(1, 2)
+        B, N, _ = p1.shape
+        S = p2.shape[1]
+        if S == 1:
+            up = f2.expand(B, N, f2.shape[-1])
+        else:
+            d = -2 * torch.matmul(p1, p2.transpose(1, 2))
+            d = d + (p1 * p1).sum(-1, keepdim=True) + (p2 * p2).sum(-1).unsqueeze(1)
+            d3, i3 = d.sort(dim=-1)
+            d3, i3 = d3[..., :3], i3[..., :3]
+            w = 1.0 / (d3 + 1e-8)
+            w = w / w.sum(dim=2, keepdim=True)
+            nb = torch.gather(f2.unsqueeze(1).expand(B, N, S, f2.shape[-1]), 2,
+                              i3.unsqueeze(-1).expand(B, N, 3, f2.shape[-1]))
+            up = (nb * w.unsqueeze(-1)).sum(dim=2)
+        h = up if points1 is None else torch.cat([points1.transpose(1, 2), up], dim=-1)
+        h = h.transpose(1, 2)
+        for conv, bn in zip(self.mlp_convs, self.mlp_bns):
+            h = F.relu(bn(conv(h)))
+        return h

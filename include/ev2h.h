@@ -1,0 +1,174 @@
+/*
+ * ev2h.h - C ABI of libev2h.so: the Ev2Hands set-abstraction encoder hot path
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI for this path: it is pure PyTorch in
+ * src/Ev2Hands/model/pointnet2_utils.py and the drop-in boundary is that
+ * module's Python namespace (imported at src/Ev2Hands/model/TEHNet.py:6).
+ * Each entry point below names the reference function it replaces; the Python
+ * side (ev2hands_b200/pointnet2_utils.py) re-creates the reference's classes on
+ * top of these calls, and INTEGRATION.md shows the one-line change that makes
+ * TEHNet.py use them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  Every pointer is DEVICE
+ *     memory unless the name ends in _host.
+ *   - the caller owns every buffer, including scratch; the library allocates
+ *     nothing on the device and keeps no mutable global state, so it may be
+ *     called from one host thread per GPU (nn.DataParallel, train.py:68).
+ *   - kernels are enqueued on `stream` (a cudaStream_t) of the current device
+ *     and the call returns without synchronising.
+ *   - return value: 0 on success, otherwise an ev2h_status; the message for the
+ *     calling thread is available from ev2h_last_error().  Nothing throws.
+ *   - index outputs are int32 (the reference uses int64; the Python wrappers
+ *     widen them where the reference API hands indices to the user).
+ *   - "cf" = channel-first  [B, C, N]  (how the model passes tensors around),
+ *     "rows" = point-major  [B, N, C]  (how the kernels gather).
+ */
+#ifndef EV2H_H
+#define EV2H_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *ev2h_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define EV2H_API __attribute__((visibility("default")))
+#else
+#define EV2H_API
+#endif
+
+typedef enum {
+    EV2H_OK = 0,
+    EV2H_ERR_BAD_ARGUMENT = 1,  /* null pointer, non-positive size, misaligned buffer */
+    EV2H_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels are built for */
+    EV2H_ERR_CUDA = 3,          /* a CUDA runtime call or launch failed */
+    EV2H_ERR_WORKSPACE = 4      /* scratch buffer too small */
+} ev2h_status;
+
+/* Library version, and the message attached to the last non-zero status
+ * returned on the calling thread ("" if none). */
+EV2H_API int ev2h_version(void);
+EV2H_API const char *ev2h_last_error(void);
+
+/* ---- farthest point sampling -------------------------------------------------
+ * Replaces farthest_point_sample (pointnet2_utils.py:63-84) followed by
+ * index_points(xyz, fps_idx) (pointnet2_utils.py:239).
+ * xyz is read in place from a channel-first tensor through element strides, so
+ * the non-contiguous view xyz[:, :3, :] of TEHNet.py:174 needs no copy:
+ *   x_c(b, n) = xyz[b*stride_b + c*stride_c + n*stride_n],  c = 0..2.
+ * start_idx[b] is the first sample (the reference draws it with torch.randint on
+ * the CPU generator, pointnet2_utils.py:75; the caller draws it the same way).
+ * Outputs (any may be NULL): idx int32 [B,S]; centres as rows [B,S,3] and as
+ * channel-first [B,3,S].  Bit-exact with the reference: distances are
+ * (dx*dx + dy*dy) + dz*dz with every product and sum rounded separately, and
+ * ties go to the lowest index.  Limits: 1 <= S, 1 <= N <= 16384. */
+EV2H_API int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                 const int64_t *start_idx, int B, int N, int S,
+                 int32_t *out_idx, float *out_centres_rows, float *out_centres_cf,
+                 ev2h_stream_t stream);
+
+/* ---- multi-radius ball query --------------------------------------------------
+ * Replaces query_ball_point (pointnet2_utils.py:87-107) for every radius of a
+ * multi-scale layer in one pass over the points, and with it square_distance
+ * (pointnet2_utils.py:19-40): the distance is evaluated in the reference's
+ * expanded form -2*(q.p) + |q|^2 + |p|^2 with its roundings (dot product as an
+ * FMA chain x,y,z; norms as (x*x + y*y) + z*z; the two adds one after the
+ * other), and a point is kept when NOT (d > radius_sq[i]).
+ * radius_sq_host[i] = (float)(radius_i * radius_i evaluated in double), which is
+ * what aten compares against.  nsample_host[i] = K_i.
+ * out_idx int32 [B, S, sum_i K_i]: for centre s the K_0 slots of scale 0, then
+ * the K_1 slots of scale 1, ...; each block holds the first K_i in-radius point
+ * indices in ascending order, padded with the first one; if no point is in
+ * radius every slot holds N (the reference's sentinel).
+ * Limits: n_scales <= 4, N <= 65536. */
+EV2H_API int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                        const float *centres_rows, int B, int N, int S,
+                        int n_scales, const float *radius_sq_host, const int32_t *nsample_host,
+                        int32_t *out_idx, ev2h_stream_t stream);
+
+/* square_distance as a standalone op (pointnet2_utils.py:19-40), same arithmetic as
+ * inside the ball query: src_rows [B,S,3], dst_rows [B,N,3] -> out [B,S,N]. */
+EV2H_API int ev2h_square_distance_f32(const float *src_rows, const float *dst_rows, int B, int S, int N,
+                             float *out, ev2h_stream_t stream);
+
+/* index_points (pointnet2_utils.py:43-60): out[b,m,:] = table_rows[b, idx[b,m], :],
+ * table_rows [B,N,C], idx int32 [B,M] (any trailing shape flattened into M). */
+EV2H_API int ev2h_index_rows_f32(const float *table_rows, const int32_t *idx, int B, int N, int M, int C,
+                        float *out, ev2h_stream_t stream);
+
+/* ---- grouping (materialising gather) -------------------------------------------
+ * Replaces the index_points / subtract / cat sequence of
+ * PointNetSetAbstractionMsg.forward (pointnet2_utils.py:244-248):
+ *   row (b, s, j) = [ feats_rows[b, p, 0..D) , xyz(b, p) - centre(b, s) , 0-pad ]
+ * with p = idx[b, s, k_off + j], j < K.  feats_rows may be NULL (D = 0).
+ * out is [B*S*K, ld_out] f32 with ld_out >= D + 3; columns past D+3 are zeroed.
+ * idx has row length idx_ld (= sum K_i) so one scale is selected by k_off. */
+EV2H_API int ev2h_group_gather_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                          const float *feats_rows, int D, const float *centres_rows,
+                          const int32_t *idx, int idx_ld, int k_off,
+                          int B, int N, int S, int K, float *out, int ld_out,
+                          ev2h_stream_t stream);
+
+/* Backward of the feature part of the gather (autograd of index_points,
+ * pointnet2_utils.py:43-60): grad_feats_rows[b, p, :] += grad_rows[(b,s,j), 0..D)
+ * for p = idx[b,s,k_off+j].  grad_feats_rows [B,N,D] must be zeroed by the
+ * caller (or hold the sum so far, e.g. from another scale). */
+EV2H_API int ev2h_group_gather_bwd_f32(const float *grad_rows, int ld_grad, const int32_t *idx, int idx_ld,
+                              int k_off, int B, int N, int S, int K, int D,
+                              float *grad_feats_rows, ev2h_stream_t stream);
+
+/* ---- batched transpose between the two layouts ----------------------------------
+ * dst[b*dst_stride_b + c*dst_ld + dst_col_off + r] = src[b*src_stride_b + r*src_stride_r + c*src_stride_c]
+ * for r < R, c < C.  Used for cf -> rows (permute(0,2,1).contiguous(),
+ * pointnet2_utils.py:233-235) and rows -> cf on the way out, and to lay xyz and
+ * features side by side for sample_and_group_all (pointnet2_utils.py:141-158). */
+EV2H_API int ev2h_transpose_f32(const float *src, int64_t src_stride_b, int64_t src_stride_r, int64_t src_stride_c,
+                       int B, int R, int C, float *dst, int64_t dst_stride_b, int64_t dst_ld,
+                       int64_t dst_col_off, ev2h_stream_t stream);
+
+/* ---- weight preparation -----------------------------------------------------------
+ * Folds a 1x1 convolution's bias and an eval-mode BatchNorm into one affine map
+ * (Conv2d + BatchNorm2d pairs of pointnet2_utils.py:167-173, :210-222):
+ *   scale = gamma / sqrt(var + eps);  W' = scale * W;  b' = scale * (b - mean) + beta
+ * conv_w is [Cout, Cin].  Output layout for the fp32 kernels: wt is
+ * [Cin_pad, Cout_pad] (input channel major, zero padded; Cin_pad = roundup(Cin,16),
+ * Cout_pad = roundup(Cout,128)), bias_out is [Cout_pad]. */
+EV2H_API int ev2h_fold_conv_bn_f32(const float *conv_w, const float *conv_b, const float *bn_gamma,
+                          const float *bn_beta, const float *bn_mean, const float *bn_var, double eps,
+                          int Cin, int Cout, float *wt, float *bias_out,
+                          ev2h_stream_t stream);
+
+/* ---- shared MLP layer on CUDA cores, fp32 ------------------------------------------
+ * One 1x1-conv + folded BN + ReLU layer over M rows (pointnet2_utils.py:253-256):
+ *   y[m, 0..Cout) = relu( x[m, 0..Cin) . W' + b' )
+ * x is [M, ld_x] (ld_x % 4 == 0, 16-byte aligned), wt/bias come from
+ * ev2h_fold_conv_bn_f32.  pool_rows == 0: y is [M, ld_y].  pool_rows = K > 0 fuses
+ * the max over each run of K consecutive rows (torch.max(x, 2)[0],
+ * pointnet2_utils.py:257): y is [M/K, ld_y] written at column y_col_off and MUST be
+ * zero-filled by the caller beforehand (post-ReLU values are >= 0).
+ * argmax (optional, only with pool_rows) is not produced here; see
+ * ev2h_group_max_f32 for the training path. */
+EV2H_API int ev2h_linear_relu_f32(const float *x, int64_t M, int ld_x, int Cin, const float *wt,
+                         const float *bias, int Cout, int pool_rows, float *y, int ld_y,
+                         int y_col_off, ev2h_stream_t stream);
+
+/* ---- max-pool over the neighbour axis, with argmax, and its backward -----------------
+ * Training path (BatchNorm in batch-statistics mode keeps conv/BN/ReLU in
+ * PyTorch).  x is channel-first [B, C, K, S] as the reference's
+ * convolutions produce it (pointnet2_utils.py:252); out [B, C, S]; arg int32
+ * [B, C, S] = first k attaining the max (torch.max's tie-break on CUDA and CPU).
+ * Backward routes grad_out to x[b, c, arg, s] and writes zeros elsewhere. */
+EV2H_API int ev2h_group_max_f32(const float *x, int B, int C, int K, int S, float *out, int32_t *arg,
+                       ev2h_stream_t stream);
+EV2H_API int ev2h_group_max_bwd_f32(const float *grad_out, const int32_t *arg, int B, int C, int K, int S,
+                           float *grad_x, ev2h_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EV2H_H */

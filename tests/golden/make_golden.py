@@ -168,5 +168,24 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+
+
+def dump_state_dict_layout():
+    """Names and shapes of the reference modules' state_dicts (the checkpoint contract,
+    demo.py:84 loads with strict=True) -> tests/golden/state_dict_layout.json."""
+    import json
+    _, th = load_reference()
+    net = th.TEHNet(n_pose_params=6)
+    out = {}
+    for name in ("sa1", "sa2", "sa3"):
+        out["encoder." + name] = {k: list(v.shape) for k, v in getattr(net, name).state_dict().items()}
+    for name in ("sa1", "sa2"):
+        out["regressor." + name] = {k: list(v.shape) for k, v in getattr(net.left_mano_regressor, name).state_dict().items()}
+    out["fp1"] = {k: list(v.shape) for k, v in net.fp1.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_layout.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     main()
+    dump_state_dict_layout()
