@@ -100,7 +100,7 @@ static int launch_fps(const float *xyz, int64_t sb, int64_t sc, int64_t sn, cons
                       int B, int N, int S, int32_t *oi, float *orows, float *ocf, cudaStream_t st) {
     const size_t smem = (size_t)3 * T * P * sizeof(float);
     auto k = fps_kernel<T, P, R>;
-    if (smem > 48 * 1024) {
+    if (smem + 1024 > 48 * 1024) {   // static slots count against the 48 KB default limit
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "fps: smem attribute: %s", cudaGetErrorString(e));
     }
