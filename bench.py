@@ -189,6 +189,8 @@ def run_ours(args):
         print("bench.py: --gpus %d but WORLD_SIZE=%d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
     B = args.windows_per_gpu
+    import ev2hands_b200 as e2h
+    e2h.set_mlp_precision(args.mlp)
     enc = build_encoder(device)
     # Every rank owns its shard of the global batch; starts are generated for the global batch
     # and sharded with the data so results do not depend on the shard count.
@@ -276,7 +278,10 @@ def run_ours(args):
     peaks, peak_kind = load_peaks()
     windows = B * world * args.steps
     value = windows / (total_ms / 1e3)
-    mlp_n, mlp_ms = kern.get("ev2h_linear_relu_f32", (0, 0.0))
+    mlp_n, mlp_ms = 0, 0.0
+    for kname in ("ev2h_linear_relu_f32", "ev2h_linear_relu_tc", "ev2h_linear_f32", "ev2h_sa_msg_fused_tc"):
+        n_, ms_ = kern.get(kname, (0, 0.0))
+        mlp_n, mlp_ms = mlp_n + n_, mlp_ms + ms_
     mlp_flops_per_step = 2.0 * MLP_MAC_PER_WINDOW * B
     achieved_tflops = (mlp_flops_per_step * args.steps) / (mlp_ms / 1e3) / 1e12 if mlp_ms > 0 else None
     # the bench's timed region is a few ms long: burst peak applies (kernel timed in isolation)
@@ -291,14 +296,16 @@ def run_ours(args):
     line = {
         "metric": "encoder event-windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xtf32)", "bf16": "bf16"}[args.mlp], "data": "synthetic",
         "config": {"workload": "encoder forward sa1->sa2->sa3 (TEHNet.py:172-181), %d windows per GPU, "
                                "N=2048 points/window, 5 channels, random-init weights, eval mode" % B,
-                   "windows_per_gpu": B, "global_windows": B * world, "mlp_path": "fp32 FFMA",
+                   "windows_per_gpu": B, "global_windows": B * world,
+                   "mlp_path": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 kind::tf32, 3-product split (fp32-level accuracy)",
+                                "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate"}[args.mlp],
                    "l2": "256 MiB buffer written between timed steps (L2 flush)"},
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": (achieved_tflops / peak_tflops) if achieved_tflops else None, "traffic": traffic,
-                     "kernel": "linear_relu_kernel (shared MLP layers, %d launches/step)" % (mlp_n // max(args.steps, 1)),
+                     "kernel": "%s (shared MLP, %d launches/step)" % ("linear_relu_kernel" if args.mlp == "fp32" else "sa_fused_tc_kernel + linear_tc_kernel", mlp_n // max(args.steps, 1)),
                      "peak_source": "%s bf16 dense (burst)" % peak_kind,
                      "algorithmic_flops_per_launch_set": mlp_flops_per_step,
                      "hbm_view": {"algorithmic_bytes_per_step": ALGO_BYTES_PER_WINDOW * B,
@@ -329,6 +336,9 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mlp", choices=["fp32", "tf32x3", "bf16"], default=os.environ.get("EV2H_MLP", "fp32"),
+                    help="arithmetic of the shared MLP: fp32 = CUDA-core FFMA, tf32x3 = tensor cores with fp32-level "
+                         "accuracy (bar 1e-5), bf16 = tensor cores, bf16 operands (bar 1e-2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

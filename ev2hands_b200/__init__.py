@@ -5,6 +5,8 @@ from .pointnet2_utils import (  # noqa: F401
     PointNetSetAbstraction,
     PointNetSetAbstractionMsg,
     farthest_point_sample,
+    get_mlp_precision,
+    set_mlp_precision,
     index_points,
     query_ball_point,
     sample_and_group,

@@ -30,6 +30,15 @@ _SIGNATURES = {
     "ev2h_transpose_f32": [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_vp],
     "ev2h_fold_conv_bn_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_linear_relu_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
+    "ev2h_tc_pack_weights": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_linear_relu_tc": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
+    "ev2h_tc_set_debug": [c_int],
+    "ev2h_linear_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp],
+    "ev2h_sa_msg_fused_tc": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
+                             c_vp, c_int,
+                             c_vp, c_int, c_int, c_vp, c_int, c_int,
+                             c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                             ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_group_max_bwd_f32": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
 }
@@ -53,6 +62,8 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         L.ev2h_version.restype = c_int
         L.ev2h_last_error.restype = ctypes.c_char_p
+        L.ev2h_tc_packed_bytes.argtypes = [c_int, c_int, c_int]
+        L.ev2h_tc_packed_bytes.restype = c_i64
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -246,6 +257,70 @@ def linear_relu(x, M, ld_x, Cin, wt, bias, Cout, pool_rows, y, ld_y, y_col_off=0
         with _timed("ev2h_linear_relu_f32"):
             _check(lib().ev2h_linear_relu_f32(_p(x), M, ld_x, Cin, _p(wt), _p(bias), Cout, pool_rows, _p(y), ld_y,
                                           y_col_off, _stream(x)), "ev2h_linear_relu_f32")
+
+
+TC_BF16, TC_TF32X3 = 0, 1
+
+
+def tc_supported(Cout: int, pool_rows: int) -> bool:
+    """Shapes the tensor-core layer kernel covers (others go through the fp32 FFMA kernel)."""
+    return (Cout <= 256 or Cout % 256 == 0) and (pool_rows in (0, 32, 64) or pool_rows % 128 == 0)
+
+
+def tc_pack(wt: torch.Tensor, Cin: int, Cout: int, mode: int) -> torch.Tensor:
+    """folded wt [Cin_pad, Cout_pad] -> packed shared-memory images (uint8 buffer) for `mode`."""
+    n = lib().ev2h_tc_packed_bytes(Cin, Cout, mode)
+    if n <= 0:
+        raise RuntimeError("ev2h_tc_packed_bytes(%d, %d, %d) failed" % (Cin, Cout, mode))
+    packed = torch.empty((n,), dtype=torch.uint8, device=wt.device)
+    with torch.cuda.device(wt.device):
+        with _timed("ev2h_tc_pack_weights"):
+            _check(lib().ev2h_tc_pack_weights(_p(wt), wt.shape[1], Cin, Cout, mode, _p(packed), _stream(wt)),
+                   "ev2h_tc_pack_weights")
+    return packed
+
+
+def linear_relu_tc(x, M, ld_x, Cin, packed, bias, Cout, pool_rows, y, ld_y, y_col_off, mode):
+    with torch.cuda.device(x.device):
+        with _timed("ev2h_linear_relu_tc"):
+            _check(lib().ev2h_linear_relu_tc(_p(x), M, ld_x, Cin, _p(packed), _p(bias), Cout, pool_rows, _p(y), ld_y,
+                                             y_col_off, mode, _stream(x)), "ev2h_linear_relu_tc")
+
+
+def linear_no_relu(x, M, ld_x, Cin, wt, bias, Cout, y, ld_y, y_col_off=0):
+    with torch.cuda.device(x.device):
+        with _timed("ev2h_linear_f32"):
+            _check(lib().ev2h_linear_f32(_p(x), M, ld_x, Cin, _p(wt), _p(bias), Cout, _p(y), ld_y, y_col_off, _stream(x)),
+                   "ev2h_linear_f32")
+
+
+def fused_supported(K: int, widths, first_in: int, per_point: bool) -> bool:
+    """Shapes ev2h_sa_msg_fused_tc covers (see include/ev2h.h)."""
+    if K not in (32, 64, 128) or any(w > 256 for w in widths):
+        return False
+    n = [(w + 15) // 16 * 16 for w in widths]
+    if per_point:
+        n = n[1:]
+        if len(n) != 2 or widths[0] % 32 != 0:
+            return False
+    elif len(n) != 3 or first_in > 8:
+        return False
+    return sum(n[:-1]) + (n[-1] + 31) // 32 * 32 <= 512
+
+
+def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, P, ld_p, p_col, C, ld_c, c_col,
+                 cins, couts, packed, biases, out_rows, ld_out, out_col, mode):
+    L = len(cins)
+    a_cin = (ctypes.c_int32 * L)(*cins)
+    a_cout = (ctypes.c_int32 * L)(*couts)
+    a_w = (c_vp * L)(*[t.data_ptr() for t in packed])
+    a_b = (c_vp * L)(*[t.data_ptr() for t in biases])
+    with torch.cuda.device(out_rows.device):
+        with _timed("ev2h_sa_msg_fused_tc"):
+            _check(lib().ev2h_sa_msg_fused_tc(_p(idx), idx.shape[-1], k_off, _p(centres_rows), B, N, S, K,
+                                              _p(pts8), D, _p(P), ld_p, p_col, _p(C), ld_c, c_col,
+                                              L, a_cin, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode,
+                                              _stream(out_rows)), "ev2h_sa_msg_fused_tc")
 
 
 def group_max(x: torch.Tensor, want_arg: bool = True):

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(LIN_THREADS, 2)
 linear_relu_kernel(const float *__restrict__ x, int64_t M, int ld_x, int Cin,
                    const float *__restrict__ wt, int ld_w, const float *__restrict__ bias,
                    int n_store, int pool_rows, float *__restrict__ y, int ld_y, int y_col_off,
-                   int n_col_blocks) {
+                   int n_col_blocks, int relu) {
     __shared__ __align__(16) float Xs[2][BK][BM];
     __shared__ __align__(16) float Ws[2][BK][BN];
 
@@ -99,7 +99,7 @@ linear_relu_kernel(const float *__restrict__ x, int64_t M, int ld_x, int Cin,
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j] + bj[j], 0.f);
+        for (int j = 0; j < 8; ++j) acc[i][j] = relu ? fmaxf(acc[i][j] + bj[j], 0.f) : acc[i][j] + bj[j];
 
     if (pool_rows == 0) {
 #pragma unroll
@@ -173,9 +173,22 @@ linear_relu_kernel(const float *__restrict__ x, int64_t M, int ld_x, int Cin,
 
 }  // namespace ev2h
 
+static int linear_f32_impl(const float *x, int64_t M, int ld_x, int Cin, const float *wt, const float *bias, int Cout,
+                           int pool_rows, float *y, int ld_y, int y_col_off, int relu, ev2h_stream_t stream);
+
 extern "C" int ev2h_linear_relu_f32(const float *x, int64_t M, int ld_x, int Cin, const float *wt,
                                     const float *bias, int Cout, int pool_rows, float *y, int ld_y,
                                     int y_col_off, ev2h_stream_t stream) {
+    return linear_f32_impl(x, M, ld_x, Cin, wt, bias, Cout, pool_rows, y, ld_y, y_col_off, 1, stream);
+}
+
+extern "C" int ev2h_linear_f32(const float *x, int64_t M, int ld_x, int Cin, const float *wt, const float *bias,
+                               int Cout, float *y, int ld_y, int y_col_off, ev2h_stream_t stream) {
+    return linear_f32_impl(x, M, ld_x, Cin, wt, bias, Cout, 0, y, ld_y, y_col_off, 0, stream);
+}
+
+static int linear_f32_impl(const float *x, int64_t M, int ld_x, int Cin, const float *wt, const float *bias, int Cout,
+                           int pool_rows, float *y, int ld_y, int y_col_off, int relu, ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(x && wt && bias && y, "ev2h_linear_relu_f32: null argument");
     EV2H_REQUIRE(M > 0 && Cin > 0 && Cout > 0, "ev2h_linear_relu_f32: bad sizes");
@@ -194,6 +207,6 @@ extern "C" int ev2h_linear_relu_f32(const float *x, int64_t M, int ld_x, int Cin
         return fail(EV2H_ERR_UNSUPPORTED, "ev2h_linear_relu_f32: M=%lld is too large for one launch; split the call", (long long)M);
     dim3 grid((unsigned)(tiles_m * n_col_blocks));
     linear_relu_kernel<<<grid, LIN_THREADS, 0, as_stream(stream)>>>(x, M, ld_x, Cin, wt, cout_pad, bias, n_store,
-                                                                    pool_rows, y, ld_y, y_col_off, n_col_blocks);
+                                                                    pool_rows, y, ld_y, y_col_off, n_col_blocks, relu);
     return check_launch("ev2h_linear_relu_f32");
 }

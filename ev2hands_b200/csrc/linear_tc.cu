@@ -1,0 +1,441 @@
+// Shared-MLP layer on the 5th-generation tensor cores (tcgen05 / TMEM):
+//     y = relu(x W' + b'), optionally max-pooled over runs of K consecutive rows.
+//
+// Replaces one Conv2d(1x1) + BatchNorm2d(eval) + ReLU step of the reference MLP
+// (src/Ev2Hands/model/pointnet2_utils.py:253-256 / :193-197) and, when pooling, the
+// torch.max over the neighbour axis (:257 / :199) - same contract as linear_ffma.cu.
+//
+// Two arithmetic modes over fp32 activations in HBM:
+//   TF32X3  fp32-accurate: x = x_hi + x_lo, w = w_hi + w_lo (hi exactly tf32), three
+//           kind::tf32 UMMAs per K step: x_lo*w_hi + x_hi*w_lo + x_hi*w_hi, fp32 accumulate.
+//   BF16    one kind::f16 UMMA per K step on bf16-rounded operands, fp32 accumulate.
+//
+// Persistent, warp-specialised CTA (one per SM), 128-row tiles:
+//   warps 5+   loaders : groups of 4 warps take K chunks (32 input channels x 128 rows) round-robin:
+//                        fp32 LDG.128, split / convert, write the UMMA operand image to shared memory
+//                        (K-major, no swizzle: 16-byte chunks, consecutive rows contiguous);
+//                        weights arrive pre-packed in the same image by ONE bulk async copy/stage
+//   warp 4     issuer  : one thread issues tcgen05.mma into one of two TMEM accumulators and
+//                        commits to the stage's "empty" barrier / the accumulator's "full" barrier
+//   warps 0-3  epilogue: tcgen05.ld their 32 TMEM lanes, bias + ReLU, then either store the
+//                        row or reduce the max over the group with warp REDUX (+ shared memory
+//                        across warps) - overlapped with the next tile's UMMAs.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_bf16.h>
+
+namespace ev2h {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_KC = 32;              // input channels per pipeline stage
+constexpr int TC_MAX_N = 256;          // accumulator width per tile (two of them fill TMEM's 512 columns)
+constexpr int TC_LOADER_GROUPS = 2;    // groups of 4 loader warps working on different stages
+constexpr int TC_THREADS = 32 * (5 + 4 * TC_LOADER_GROUPS);   // 4 epilogue + 1 issuer + loader warps
+constexpr int TC_MAX_STAGES = 8;
+
+enum { TC_MODE_BF16 = 0, TC_MODE_TF32X3 = 1 };
+
+__host__ __device__ constexpr int tc_elem_bytes(int mode) { return mode == TC_MODE_BF16 ? 2 : 4; }
+// bytes of one operand image holding `rows` rows x TC_KC channels (one precision part)
+__host__ __device__ constexpr int tc_part_bytes(int mode, int rows) { return rows * TC_KC * tc_elem_bytes(mode); }
+__host__ __device__ constexpr int tc_parts(int mode) { return mode == TC_MODE_BF16 ? 1 : 2; }
+__host__ __device__ constexpr int tc_stage_bytes(int mode, int n_blk) {
+    return tc_parts(mode) * (tc_part_bytes(mode, TC_BLOCK_M) + tc_part_bytes(mode, n_blk));
+}
+
+struct TcParams {
+    const float *x; int64_t M; int ld_x; int Cin;
+    const uint8_t *w_packed; const float *bias;
+    int n_blk;          // accumulator width (multiple of 16, <= 256)
+    int n_blocks;       // ceil(Cout_pad / n_blk)
+    int n_kc;           // ceil(Cin / 32)
+    int Cout; int pool_rows;
+    float *y; int ld_y; int y_col_off;
+    int n_store_total;  // columns of y that may be written (>= Cout when zero padding exists)
+    int stages;
+    int debug;
+};
+
+// ---- weight packing: folded [Cin_pad16, ld_w] fp32 (input-channel major) -> per (n-block, stage)
+// shared-memory images so a stage is one contiguous bulk copy.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+tc_pack_kernel(const float *__restrict__ wt, int ld_w, int cin_rows, int cout_cols, int n_blk, int n_blocks,
+               int n_kc, uint8_t *__restrict__ out) {
+    const int64_t total = (int64_t)n_blocks * n_kc * n_blk * TC_KC;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int kk = (int)(e % TC_KC);
+    int64_t t = e / TC_KC;
+    const int n = (int)(t % n_blk);
+    t /= n_blk;
+    const int kc = (int)(t % n_kc);
+    const int nb = (int)(t / n_kc);
+    const int k = kc * TC_KC + kk, col = nb * n_blk + n;
+    const float w = (k < cin_rows && col < cout_cols) ? wt[(int64_t)k * ld_w + col] : 0.f;
+    constexpr int EB = tc_elem_bytes(MODE);
+    constexpr int CH = 16 / EB;                         // elements per 16-byte chunk
+    const size_t part = (size_t)tc_part_bytes(MODE, n_blk);
+    uint8_t *stage = out + ((size_t)nb * n_kc + kc) * (tc_parts(MODE) * part);
+    const size_t off = (size_t)(kk / CH) * ((size_t)n_blk * 16) + (size_t)n * 16 + (size_t)(kk % CH) * EB;
+    if (MODE == TC_MODE_BF16) {
+        *reinterpret_cast<__nv_bfloat16 *>(stage + off) = __float2bfloat16_rn(w);
+    } else {
+        float hi, lo;
+        tc::split_tf32(w, hi, lo);
+        *reinterpret_cast<float *>(stage + off) = hi;
+        *reinterpret_cast<float *>(stage + part + off) = lo;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+linear_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(128) uint8_t tc_smem[];
+    constexpr int EB = tc_elem_bytes(MODE);
+    constexpr int PARTS = tc_parts(MODE);
+    constexpr int A_PART = tc_part_bytes(MODE, TC_BLOCK_M);
+    constexpr int CH = 16 / EB;                 // elements per 16-byte chunk: 4 (tf32) / 8 (bf16)
+    constexpr int UMMA_K = 32 / EB;             // 8 (tf32) / 16 (bf16)
+    constexpr int K_STEPS = TC_KC / UMMA_K;     // 4 / 2
+    const int n_blk = p.n_blk;
+    const int b_part = tc_part_bytes(MODE, n_blk);
+    const int stage_bytes = PARTS * (A_PART + b_part);
+    const int stages = p.stages;
+
+    uint8_t *ring = tc_smem;
+    uint8_t *tail = tc_smem + (size_t)stages * stage_bytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(tail);           // [stages]
+    uint64_t *empty_bar = full_bar + TC_MAX_STAGES;                    // [stages]
+    uint64_t *acc_full = empty_bar + TC_MAX_STAGES;                    // [2]
+    uint64_t *acc_empty = acc_full + 2;                                // [2]
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    float *bias_s = reinterpret_cast<float *>(tmem_base_slot + 4);     // [n_blocks * n_blk]
+    float *red = bias_s + p.n_blocks * n_blk;                          // [2][4][n_blk]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    const int64_t n_tiles = m_tiles * p.n_blocks;
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            tc::mbar_init(full_bar + s, 128 + 1);     // 128 loader arrivals + the weight copy's expect_tx arrival
+            tc::mbar_init(empty_bar + s, 1);          // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(acc_full + a, 1);
+            tc::mbar_init(acc_empty + a, 128);
+        }
+        tc::fence_mbar_init();
+    }
+    for (int i = tid; i < p.n_blocks * n_blk; i += TC_THREADS) bias_s[i] = p.bias[i];
+    if (warp == 4) tc::tmem_alloc(tmem_base_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp >= 5) {
+        // ================================ loaders ================================
+        // TC_LOADER_GROUPS groups of 4 warps take the K chunks round-robin, so several stages are
+        // being fetched at once.  Inside a group, warp wq owns rows [32 wq, 32 wq + 32) of the tile.
+        // Lane mapping: 8 consecutive lanes = 8 consecutive rows of ONE 16-byte operand chunk (a
+        // conflict-free 128-byte shared-memory store), the 4 lane octets = 4 adjacent chunks, so a
+        // warp-wide load covers 8 rows x 64 contiguous bytes (full 32-byte sectors).
+        const int lw = warp - 5, grp = lw >> 2, wq = lw & 3;
+        const int l8 = lane & 7, oct = lane >> 3;
+        int stage = 0;
+        uint32_t phase = 0, n = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t m0 = (tile / p.n_blocks) * TC_BLOCK_M;
+            const int nb = (int)(tile % p.n_blocks);
+            for (int kc = 0; kc < p.n_kc; ++kc, ++n) {
+                if ((int)(n % TC_LOADER_GROUPS) == grp) {
+                    float4 v[8];
+                    if (MODE == TC_MODE_TF32X3) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 32 * wq + (i >> 1) * 8 + l8;
+                            const int k = kc * TC_KC + 4 * (oct + 4 * (i & 1));
+                            v[i] = ((m0 + row) < p.M && k < p.ld_x)
+                                       ? __ldg(reinterpret_cast<const float4 *>(p.x + (m0 + row) * (int64_t)p.ld_x + k))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = 32 * wq + i * 8 + l8;
+                            const int k = kc * TC_KC + 8 * oct;
+                            const float *src = p.x + (m0 + row) * (int64_t)p.ld_x + k;
+                            const bool ok = (m0 + row) < p.M;
+                            v[2 * i] = (ok && k < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[2 * i + 1] = (ok && k + 4 < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    tc::mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t *st = ring + (size_t)stage * stage_bytes;
+                    if (wq == 0 && lane == 0) {
+                        const uint32_t wbytes = (uint32_t)(PARTS * b_part);
+                        tc::mbar_arrive_expect_tx(full_bar + stage, wbytes);
+                        tc::bulk_g2s(st + PARTS * A_PART, p.w_packed + ((size_t)nb * p.n_kc + kc) * wbytes, wbytes,
+                                     full_bar + stage);
+                    }
+                    if (MODE == TC_MODE_TF32X3) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 32 * wq + (i >> 1) * 8 + l8;
+                            const int c = oct + 4 * (i & 1);
+                            float4 hi, lo;
+                            tc::split_tf32(v[i].x, hi.x, lo.x); tc::split_tf32(v[i].y, hi.y, lo.y);
+                            tc::split_tf32(v[i].z, hi.z, lo.z); tc::split_tf32(v[i].w, hi.w, lo.w);
+                            *reinterpret_cast<float4 *>(st + c * (TC_BLOCK_M * 16) + row * 16) = hi;
+                            *reinterpret_cast<float4 *>(st + A_PART + c * (TC_BLOCK_M * 16) + row * 16) = lo;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = 32 * wq + i * 8 + l8;
+                            __nv_bfloat162 q0 = __floats2bfloat162_rn(v[2 * i].x, v[2 * i].y);
+                            __nv_bfloat162 q1 = __floats2bfloat162_rn(v[2 * i].z, v[2 * i].w);
+                            __nv_bfloat162 q2 = __floats2bfloat162_rn(v[2 * i + 1].x, v[2 * i + 1].y);
+                            __nv_bfloat162 q3 = __floats2bfloat162_rn(v[2 * i + 1].z, v[2 * i + 1].w);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
+                            pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
+                            *reinterpret_cast<uint4 *>(st + oct * (TC_BLOCK_M * 16) + row * 16) = pk;
+                        }
+                    }
+                    tc::fence_proxy_async();
+                    tc::mbar_arrive(full_bar + stage);
+                } else {
+                    // walk the other group's chunks too: a parity wait is only meaningful while the
+                    // waiter is at most one phase ahead of the barrier
+                    tc::mbar_wait(empty_bar + stage, phase ^ 1);
+                }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 4) {
+        // ================================ UMMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = tc::instr_desc(MODE == TC_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_BLOCK_M, (uint32_t)n_blk);
+            const uint32_t a_lbo = TC_BLOCK_M * 16, b_lbo = (uint32_t)n_blk * 16, sbo = 128;
+            const bool swap = p.debug & 1;       // debug: exchange the roles of the two descriptor offsets
+            auto desc = [&](uint32_t addr, uint32_t lbo) {
+                return swap ? tc::smem_desc_kmajor(addr, sbo, lbo) : tc::smem_desc_kmajor(addr, lbo, sbo);
+            };
+            int stage = 0;
+            uint32_t phase = 0, it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+                tc::mbar_wait(acc_empty + acc, acc_phase ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_MAX_N;
+                for (int kc = 0; kc < p.n_kc; ++kc) {
+                    tc::mbar_wait(full_bar + stage, phase);
+                    tc::tc_fence_after();
+                    const uint32_t a0 = tc::smem_u32(ring + (size_t)stage * stage_bytes);
+                    const uint32_t b0 = a0 + PARTS * A_PART;
+#pragma unroll
+                    for (int j = 0; j < K_STEPS; ++j) {
+                        const uint32_t a_off = (uint32_t)j * 2 * a_lbo, b_off = (uint32_t)j * 2 * b_lbo;
+                        const uint32_t first = (kc > 0 || j > 0) ? 1u : 0u;
+                        if (MODE == TC_MODE_TF32X3) {
+                            const uint64_t a_hi = desc(a0 + a_off, a_lbo);
+                            const uint64_t a_lo = desc(a0 + A_PART + a_off, a_lbo);
+                            const uint64_t b_hi = desc(b0 + b_off, b_lbo);
+                            const uint64_t b_lo = desc(b0 + b_part + b_off, b_lbo);
+                            tc::umma_tf32(d_tmem, a_lo, b_hi, idesc, first);     // small terms first
+                            tc::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                            tc::umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                        } else {
+                            tc::umma_f16(d_tmem, desc(a0 + a_off, a_lbo), desc(b0 + b_off, b_lbo), idesc, first);
+                        }
+                    }
+                    tc::umma_commit(empty_bar + stage);             // stage reusable once these UMMAs retire
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(acc_full + acc);                    // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp;                            // TMEM lane quadrant of this warp
+        const int r = q * 32 + lane;                   // row of the tile
+        const int K = p.pool_rows;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int64_t m0 = (tile / p.n_blocks) * TC_BLOCK_M;
+            const int nb = (int)(tile % p.n_blocks);
+            const int col0 = nb * n_blk;
+            const int n_store = min(n_blk, p.n_store_total - col0);      // may be <= 0 for an all-padding block
+            const bool row_ok = (m0 + r) < p.M;
+            tc::mbar_wait(acc_full + acc, acc_phase);
+            tc::tc_fence_after();
+            const uint32_t t_addr = tmem_base + acc * TC_MAX_N + ((uint32_t)(q * 32) << 16);
+            float *red_w = red + ((size_t)acc * 4 + q) * n_blk;
+            for (int c0 = 0; c0 < n_blk; c0 += 32) {
+                uint32_t raw[32];
+                tc::tmem_ld32(t_addr + c0, raw);
+                tc::tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + bias_s[col0 + c0 + j], 0.f);
+                if (K == 0) {
+                    if (row_ok) {
+                        float *yr = p.y + (m0 + r) * (int64_t)p.ld_y + p.y_col_off + col0 + c0;
+                        const bool vec = (((p.ld_y | p.y_col_off) & 3) == 0);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (vec && c0 + j + 3 < n_store) {
+                                *reinterpret_cast<float4 *>(yr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    if (c0 + j + u < n_store) yr[j + u] = v[j + u];
+                            }
+                        }
+                    }
+                } else {
+                    // max over the 32 rows of this warp, column j ends up in lane j
+                    float mine = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const unsigned m = __reduce_max_sync(0xffffffffu, row_ok ? __float_as_uint(v[j]) : 0u);
+                        if (lane == j) mine = __uint_as_float(m);
+                    }
+                    if (K == 32) {
+                        const int64_t g = (m0 + q * 32) / 32;
+                        if ((m0 + q * 32) < p.M && c0 + lane < n_store)
+                            p.y[g * (int64_t)p.ld_y + p.y_col_off + col0 + c0 + lane] = mine;
+                    } else {
+                        if (c0 + lane < n_blk) red_w[c0 + lane] = mine;
+                    }
+                }
+            }
+            // accumulator drained: hand it back to the issuer
+            tc::tc_fence_before();
+            tc::mbar_arrive(acc_empty + acc);
+            if (K > 32) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");            // the 4 epilogue warps only
+                const float *ra = red + (size_t)acc * 4 * n_blk;
+                if (K == 64) {
+                    for (int i = tid; i < 2 * n_blk; i += 128) {
+                        const int g = i / n_blk, c = i % n_blk;
+                        const int64_t row0 = m0 + g * 64;
+                        if (row0 < p.M && c < n_store)
+                            p.y[(row0 / 64) * (int64_t)p.ld_y + p.y_col_off + col0 + c] =
+                                fmaxf(ra[(2 * g) * n_blk + c], ra[(2 * g + 1) * n_blk + c]);
+                    }
+                } else {   // K is a multiple of 128: one group per tile (or a group spanning several tiles)
+                    for (int c = tid; c < n_blk; c += 128) {
+                        if (c >= n_store) continue;
+                        const float m = fmaxf(fmaxf(ra[c], ra[n_blk + c]), fmaxf(ra[2 * n_blk + c], ra[3 * n_blk + c]));
+                        float *dst = p.y + (m0 / K) * (int64_t)p.ld_y + p.y_col_off + col0 + c;
+                        if (K == 128) *dst = m;
+                        else atomicMax(reinterpret_cast<int *>(dst), __float_as_int(m));   // values are >= 0
+                    }
+                }
+            }
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int tc_n_blk(int Cout) { return Cout >= TC_MAX_N ? TC_MAX_N : round_up(Cout, 16); }
+static int tc_n_blocks(int Cout) { return (Cout + tc_n_blk(Cout) - 1) / tc_n_blk(Cout); }
+static int tc_n_kc(int Cin) { return (Cin + TC_KC - 1) / TC_KC; }
+
+static int g_tc_debug = 0;
+static bool tc_pool_supported(int K) { return K == 0 || K == 32 || K == 64 || (K % 128 == 0); }
+
+}  // namespace ev2h
+
+extern "C" int ev2h_tc_set_debug(int flags) { ev2h::g_tc_debug = flags; return 0; }
+
+extern "C" int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode) {
+    using namespace ev2h;
+    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3)) return -1;
+    const int n_blk = tc_n_blk(Cout);
+    return (int64_t)tc_n_blocks(Cout) * tc_n_kc(Cin) * tc_parts(mode) * tc_part_bytes(mode, n_blk);
+}
+
+extern "C" int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
+                                    ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(wt && packed, "ev2h_tc_pack_weights: null argument");
+    EV2H_REQUIRE(Cin > 0 && Cout > 0 && ld_w >= Cout, "ev2h_tc_pack_weights: bad sizes");
+    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3, "ev2h_tc_pack_weights: unknown mode %d", mode);
+    const int n_blk = tc_n_blk(Cout), n_blocks = tc_n_blocks(Cout), n_kc = tc_n_kc(Cin);
+    const int64_t total = (int64_t)n_blocks * n_kc * n_blk * TC_KC;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    // wt comes from ev2h_fold_conv_bn_f32: round_up(Cin,16) rows of ld_w columns, zero padded
+    const int cin_rows = round_up(Cin, 16);
+    const int cout_cols = ld_w;
+    if (mode == TC_MODE_BF16)
+        tc_pack_kernel<TC_MODE_BF16><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, (uint8_t *)packed);
+    else
+        tc_pack_kernel<TC_MODE_TF32X3><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, (uint8_t *)packed);
+    return check_launch("ev2h_tc_pack_weights");
+}
+
+extern "C" int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
+                                   const float *bias, int Cout, int pool_rows, float *y, int ld_y, int y_col_off,
+                                   int mode, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(x && w_packed && bias && y, "ev2h_linear_relu_tc: null argument");
+    EV2H_REQUIRE(M > 0 && Cin > 0 && Cout > 0, "ev2h_linear_relu_tc: bad sizes");
+    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3, "ev2h_linear_relu_tc: unknown mode %d", mode);
+    EV2H_REQUIRE(ld_x % 4 == 0 && ld_x >= Cin, "ev2h_linear_relu_tc: ld_x=%d must be a multiple of 4 and >= Cin=%d", ld_x, Cin);
+    EV2H_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "ev2h_linear_relu_tc: x and w_packed must be 16-byte aligned");
+    EV2H_REQUIRE(pool_rows >= 0 && (pool_rows == 0 || M % pool_rows == 0), "ev2h_linear_relu_tc: M must be a multiple of pool_rows");
+    EV2H_REQUIRE(y_col_off >= 0 && ld_y >= y_col_off + Cout, "ev2h_linear_relu_tc: ld_y too small");
+    if (!tc_pool_supported(pool_rows))
+        return fail(EV2H_ERR_UNSUPPORTED, "ev2h_linear_relu_tc: pool_rows=%d (supported: 0, 32, 64, multiples of 128)", pool_rows);
+
+    TcParams p;
+    p.x = x; p.M = M; p.ld_x = ld_x; p.Cin = Cin;
+    p.w_packed = (const uint8_t *)w_packed; p.bias = bias;
+    p.n_blk = tc_n_blk(Cout); p.n_blocks = tc_n_blocks(Cout); p.n_kc = tc_n_kc(Cin);
+    p.Cout = Cout; p.pool_rows = pool_rows; p.y = y; p.ld_y = ld_y; p.y_col_off = y_col_off;
+    // bias comes from ev2h_fold_conv_bn_f32 (round_up(Cout,128) entries, zero padded) and must cover n_blocks*n_blk
+    if (p.n_blocks * p.n_blk > round_up(Cout, 128))
+        return fail(EV2H_ERR_UNSUPPORTED, "ev2h_linear_relu_tc: Cout=%d needs bias padding beyond round_up(Cout,128)", Cout);
+    p.n_store_total = Cout;
+    if (pool_rows == 0) {
+        const int room = ld_y - y_col_off, padded = p.n_blocks * p.n_blk;
+        p.n_store_total = room < padded ? room : padded;     // also write the exact-zero padding columns
+    }
+    const int stage_bytes = tc_stage_bytes(mode, p.n_blk);
+    const int tail_bytes = (2 * TC_MAX_STAGES + 4) * 8 + 16 + (p.n_blocks * p.n_blk + 2 * 4 * p.n_blk) * 4;
+    int stages = (227 * 1024 - tail_bytes - 1024) / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_linear_relu_tc: stage of %d bytes does not fit twice", stage_bytes);
+    p.stages = stages;
+    p.debug = g_tc_debug;
+    const size_t smem = (size_t)stages * stage_bytes + tail_bytes;
+
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n_tiles = ((M + TC_BLOCK_M - 1) / TC_BLOCK_M) * p.n_blocks;
+    const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    cudaError_t e;
+    if (mode == TC_MODE_BF16) {
+        e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) linear_tc_kernel<TC_MODE_BF16><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) linear_tc_kernel<TC_MODE_TF32X3><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);
+    }
+    if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_linear_relu_tc: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
+    return check_launch("ev2h_linear_relu_tc");
+}

@@ -33,6 +33,34 @@ from . import _capi
 
 _WORKSPACE_BYTES = int(os.environ.get("EV2H_WORKSPACE_MB", "4096")) << 20
 
+# Arithmetic of the shared MLP in the inference path:
+#   "fp32"   CUDA-core FFMA, exact fp32 (parity anchor)
+#   "tf32x3" tensor cores, error-compensated 3xTF32: fp32-level accuracy (bar 1e-5)
+#   "bf16"   tensor cores, bf16 operands / fp32 accumulate (bar 1e-2)
+_MLP_PRECISIONS = ("fp32", "tf32x3", "bf16")
+_mlp_precision = os.environ.get("EV2H_MLP", "fp32")
+
+
+# The fused grouping + MLP + max-pool kernel (sa_fused_tc.cu) is used for every scale it
+# covers when a tensor-core precision is selected; EV2H_FUSED=0 forces the layer-by-layer path.
+_FUSED_ENABLED = os.environ.get("EV2H_FUSED", "1") != "0"
+
+
+def set_fused(enabled: bool) -> None:
+    global _FUSED_ENABLED
+    _FUSED_ENABLED = bool(enabled)
+
+
+def set_mlp_precision(name: str) -> None:
+    global _mlp_precision
+    if name not in _MLP_PRECISIONS:
+        raise ValueError("mlp precision must be one of %s" % (_MLP_PRECISIONS,))
+    _mlp_precision = name
+
+
+def get_mlp_precision() -> str:
+    return _mlp_precision
+
 
 def _pad4(c: int) -> int:
     return (c + 3) // 4 * 4
@@ -169,7 +197,7 @@ class _FoldedMLP:
                 if j == 0 and in_perm is not None:
                     w = w[:, in_perm]
                 wt, bias = _capi.fold_conv_bn(w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-                layers.append((wt, bias, conv.in_channels, conv.out_channels))
+                layers.append({"wt": wt, "bias": bias, "cin": conv.in_channels, "cout": conv.out_channels, "packed": {}})
             self.by_device[dev] = (key, layers)
             return layers
         return hit[1]
@@ -179,15 +207,24 @@ def _mlp_rows(x, M, ld_x, layers, pool_rows, out, ld_out, out_col):
     """Run the folded MLP over M rows of x; the last layer max-pools runs of pool_rows rows
     into out[:, out_col : out_col + C_last]."""
     cur, ld = x, ld_x
-    for j, (wt, bias, cin, cout) in enumerate(layers):
+    mode = {"tf32x3": _capi.TC_TF32X3, "bf16": _capi.TC_BF16}.get(_mlp_precision)
+    for j, L in enumerate(layers):
         last = j == len(layers) - 1
+        cin, cout = L["cin"], L["cout"]
+        pool = pool_rows if last else 0
         if last:
-            _capi.linear_relu(cur, M, ld, cin, wt, bias, cout, pool_rows, out, ld_out, out_col)
+            y, ld_y, col = out, ld_out, out_col
         else:
-            ld_y = _pad4(cout)
+            ld_y, col = _pad4(cout), 0
             y = torch.empty((M, ld_y), dtype=torch.float32, device=x.device)
-            _capi.linear_relu(cur, M, ld, cin, wt, bias, cout, 0, y, ld_y, 0)
-            cur, ld = y, ld_y
+        if mode is not None and _capi.tc_supported(cout, pool):
+            packed = L["packed"].get(mode)
+            if packed is None:
+                packed = L["packed"][mode] = _capi.tc_pack(L["wt"], cin, cout, mode)
+            _capi.linear_relu_tc(cur, M, ld, cin, packed, L["bias"], cout, pool, y, ld_y, col, mode)
+        else:
+            _capi.linear_relu(cur, M, ld, cin, L["wt"], L["bias"], cout, pool, y, ld_y, col)
+        cur, ld = y, ld_y
 
 
 def _check_inputs(xyz, points):
@@ -275,24 +312,83 @@ class PointNetSetAbstractionMsg(nn.Module):
         B, _, N = xyz.shape
         S = self.npoint
         D = 0 if points is None else points.shape[1]
-        feats_rows = _to_rows(points) if points is not None else None
         c_total = sum(convs[-1].out_channels for convs in self.conv_blocks)
         out_rows = torch.zeros((B, S, c_total), dtype=torch.float32, device=xyz.device)
+        mode = {"tf32x3": _capi.TC_TF32X3, "bf16": _capi.TC_BF16}.get(_mlp_precision)
+        all_layers = [self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]) for i in range(len(self.nsample_list))]
+        widths = [[L["cout"] for L in layers] for layers in all_layers]
+
+        # Which scales can run in the fused tensor-core kernel, and with which first-layer mode.
+        per_point = D + 3 > 8
+        fused = [mode is not None and _FUSED_ENABLED and _capi.fused_supported(K, w, D + 3, per_point)
+                 for K, w in zip(self.nsample_list, widths)]
+
+        pts8 = P = C = None
+        p_cols = []
+        if any(fused) and not per_point:
+            # [features | xyz | 0] per point, 32 bytes: one sector per gathered neighbour
+            pts8 = torch.zeros((B, N, 8), dtype=torch.float32, device=xyz.device)
+            if points is not None:
+                _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, pts8, N * 8, 8, 0)
+            _capi.transpose(xyz, strides, B, 3, N, pts8, N * 8, 8, D)
+        elif any(fused):
+            # layer 1 once per point: P = W1'[f; xyz] + b1' for every fused scale side by side,
+            # C = W1'_xyz centre per centre (see sa_fused_tc.cu)
+            ld_pts = _pad4(D + 3)
+            x_pts = torch.zeros((B * N, ld_pts), dtype=torch.float32, device=xyz.device)
+            _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, x_pts, N * ld_pts, ld_pts, 0)
+            _capi.transpose(xyz, strides, B, 3, N, x_pts, N * ld_pts, ld_pts, D)
+            c1_total = sum(w[0] for w, f in zip(widths, fused) if f)
+            P = torch.empty((B * N, c1_total), dtype=torch.float32, device=xyz.device)
+            C = torch.empty((B * S, c1_total), dtype=torch.float32, device=xyz.device)
+            ctr4 = torch.zeros((B * S, 4), dtype=torch.float32, device=xyz.device)
+            ctr4[:, :3] = centres_rows.reshape(B * S, 3)
+            col = 0
+            for layers, f in zip(all_layers, fused):
+                if not f:
+                    p_cols.append(None)
+                    continue
+                L0 = layers[0]
+                if "wt_xyz" not in L0:
+                    wx = torch.zeros((16, L0["wt"].shape[1]), dtype=torch.float32, device=xyz.device)
+                    wx[:3] = L0["wt"][D:D + 3]
+                    L0["wt_xyz"], L0["zero_bias"] = wx, torch.zeros_like(L0["bias"])
+                _capi.linear_no_relu(x_pts, B * N, ld_pts, D + 3, L0["wt"], L0["bias"], L0["cout"], P, c1_total, col)
+                _capi.linear_no_relu(ctr4, B * S, 4, 3, L0["wt_xyz"], L0["zero_bias"], L0["cout"], C, c1_total, col)
+                p_cols.append(col)
+                col += L0["cout"]
+
+        feats_rows = None
         ld_x = _pad4(D + 3)
         k_off = col = 0
         for i, K in enumerate(self.nsample_list):
-            layers = self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i])
-            per_window = S * K * 4 * (ld_x + sum(_pad4(l[3]) for l in layers[:-1]))
-            chunk = max(1, min(B, _WORKSPACE_BYTES // per_window))
-            for b0 in range(0, B, chunk):
-                nb = min(chunk, B - b0)
-                M = nb * S * K
-                x = torch.empty((M, ld_x), dtype=torch.float32, device=xyz.device)
-                _capi.group_gather(xyz[b0:b0 + nb], strides, None if feats_rows is None else feats_rows[b0:b0 + nb], D,
-                                   centres_rows[b0:b0 + nb], ball[b0:b0 + nb], k_off, nb, N, S, K, x, ld_x)
-                _mlp_rows(x, M, ld_x, layers, K, out_rows[b0:b0 + nb], c_total, col)
+            layers = all_layers[i]
+            if fused[i]:
+                use = layers[1:] if per_point else layers
+                packed = []
+                for L in use:
+                    if mode not in L["packed"]:
+                        L["packed"][mode] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], mode)
+                    packed.append(L["packed"][mode])
+                _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D,
+                                   P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
+                                   C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
+                                   [L["cin"] for L in use], [L["cout"] for L in use], packed, [L["bias"] for L in use],
+                                   out_rows, c_total, col, mode)
+            else:
+                if feats_rows is None and points is not None:
+                    feats_rows = _to_rows(points)
+                per_window = S * K * 4 * (ld_x + sum(_pad4(l["cout"]) for l in layers[:-1]))
+                chunk = max(1, min(B, _WORKSPACE_BYTES // per_window))
+                for b0 in range(0, B, chunk):
+                    nb = min(chunk, B - b0)
+                    M = nb * S * K
+                    x = torch.empty((M, ld_x), dtype=torch.float32, device=xyz.device)
+                    _capi.group_gather(xyz[b0:b0 + nb], strides, None if feats_rows is None else feats_rows[b0:b0 + nb], D,
+                                       centres_rows[b0:b0 + nb], ball[b0:b0 + nb], k_off, nb, N, S, K, x, ld_x)
+                    _mlp_rows(x, M, ld_x, layers, K, out_rows[b0:b0 + nb], c_total, col)
             k_off += K
-            col += layers[-1][3]
+            col += layers[-1]["cout"]
         return _rows_to_cf(out_rows)
 
     def _forward_autograd(self, xyz, points, strides, centres_rows, ball):
@@ -355,7 +451,7 @@ class PointNetSetAbstraction(nn.Module):
         if points is not None:
             _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, x, N * ld_x, ld_x, 3)
         layers = self._folded.get(self.mlp_convs, self.mlp_bns)
-        c_out = layers[-1][3]
+        c_out = layers[-1]["cout"]
         out = torch.zeros((B, c_out), dtype=torch.float32, device=xyz.device)
         _mlp_rows(x, B * N, ld_x, layers, N, out, c_out, 0)
         return out.view(B, c_out, 1)
@@ -391,7 +487,7 @@ class PointNetSetAbstraction(nn.Module):
             feats_rows = _to_rows(points) if points is not None else None
             layers = self._folded.get(self.mlp_convs, self.mlp_bns, in_perm=perm)
             ld_x = _pad4(D + 3)
-            c_out = layers[-1][3]
+            c_out = layers[-1]["cout"]
             out_rows = torch.zeros((B, S, c_out), dtype=torch.float32, device=xyz.device)
             x = torch.empty((B * S * K, ld_x), dtype=torch.float32, device=xyz.device)
             _capi.group_gather(xyz, strides, feats_rows, D, centres_rows, ball, 0, B, N, S, K, x, ld_x)

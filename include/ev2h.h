@@ -157,6 +157,57 @@ EV2H_API int ev2h_linear_relu_f32(const float *x, int64_t M, int ld_x, int Cin, 
                          const float *bias, int Cout, int pool_rows, float *y, int ld_y,
                          int y_col_off, ev2h_stream_t stream);
 
+/* The same layer without the ReLU: y = x W' + b' (no pooling).  Used to evaluate a layer's
+ * linear part once per point when it commutes with the grouping (see ev2h_sa_msg_fused_tc). */
+EV2H_API int ev2h_linear_f32(const float *x, int64_t M, int ld_x, int Cin, const float *wt, const float *bias,
+                             int Cout, float *y, int ld_y, int y_col_off, ev2h_stream_t stream);
+
+/* ---- shared MLP layer on the tensor cores (tcgen05 / TMEM) ----------------------------
+ * Same contract as ev2h_linear_relu_f32 (x, y fp32 in HBM; bias from ev2h_fold_conv_bn_f32)
+ * with the contraction on the 5th-generation tensor cores.  mode selects the arithmetic:
+ *   EV2H_TC_BF16   (0)  operands rounded to bf16, fp32 accumulate  (feature bar 1e-2)
+ *   EV2H_TC_TF32X3 (1)  error-compensated split x = hi + lo, w = hi + lo, three tf32 products,
+ *                       fp32 accumulate: fp32-level accuracy     (feature bar 1e-5)
+ * Weights must first be packed from the folded layout (wt, ld_w = round_up(Cout,128) as
+ * written by ev2h_fold_conv_bn_f32) into the kernel's shared-memory image:
+ * ev2h_tc_packed_bytes gives the buffer size, ev2h_tc_pack_weights fills it.
+ * pool_rows must be 0, 32, 64 or a multiple of 128; Cout <= 256 or a multiple of 256;
+ * other shapes return EV2H_ERR_UNSUPPORTED (callers use ev2h_linear_relu_f32 for those). */
+#define EV2H_TC_BF16 0
+#define EV2H_TC_TF32X3 1
+EV2H_API int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode);
+EV2H_API int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
+                                  ev2h_stream_t stream);
+EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
+                                 const float *bias, int Cout, int pool_rows, float *y, int ld_y,
+                                 int y_col_off, int mode, ev2h_stream_t stream);
+/* ---- fused grouping + shared MLP + max-pool for ONE radius scale (tensor cores) ------------
+ * Replaces the body of the per-radius loop of PointNetSetAbstractionMsg.forward
+ * (pointnet2_utils.py:243-257): gather of the K neighbours of every centre, the
+ * Conv2d(1x1)+BatchNorm2d(eval)+ReLU stack and the max over K, without materialising the
+ * grouped tensor or any intermediate activation in HBM.
+ *   idx [B,S,idx_ld] int32 from ev2h_ball_query_f32, this scale's K slots start at k_off;
+ *   centres_rows [B,S,3];  K in {32, 64, 128};  every layer width <= 256.
+ * First-layer input, one of:
+ *   gather mode   (P == NULL, n_layers == 3): pts8 [B,N,8] rows = [features(D) | xyz | 0],
+ *                 D + 3 <= 8; rows are [features | xyz - centre] as in the reference.
+ *   per-point mode (P != NULL, n_layers == 2): layer 1 was evaluated per point / per centre:
+ *                 P [B*N, ld_p] = W1' [features; xyz] + b1' (ev2h_linear_f32) at column p_col,
+ *                 C [B*S, ld_c] = W1'_xyz centre at column c_col; the kernel forms
+ *                 relu(P[point] - C[centre]) and runs the remaining two layers.
+ * cin/cout_host[l]: layer widths; w_packed_host[l]: ev2h_tc_pack_weights images; bias_host[l]:
+ * folded biases (device pointers in host arrays).  out_rows [B*S, ld_out]: the pooled features
+ * of this scale are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3. */
+EV2H_API int ev2h_sa_msg_fused_tc(
+    const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
+    const float *pts8, int D,
+    const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
+    int n_layers, const int32_t *cin_host, const int32_t *cout_host, const void *const *w_packed_host,
+    const float *const *bias_host, float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream);
+
+/* Debug only: bit 0 swaps the leading/stride byte offsets of the UMMA shared-memory descriptors. */
+EV2H_API int ev2h_tc_set_debug(int flags);
+
 /* ---- max-pool over the neighbour axis, with argmax, and its backward -----------------
  * Training path (BatchNorm in batch-statistics mode keeps conv/BN/ReLU in
  * PyTorch).  x is channel-first [B, C, K, S] as the reference's
