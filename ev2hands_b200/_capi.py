@@ -31,8 +31,11 @@ _SIGNATURES = {
     "ev2h_fold_conv_bn_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_linear_relu_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_tc_pack_weights": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_tc_pack_weights_kc": [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_sa_msg_fused_kc": [c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32)],
     "ev2h_linear_relu_tc": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_tc_set_debug": [c_int],
+    "ev2h_fused_set_debug_buffer": [c_vp],
     "ev2h_linear_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_sa_msg_fused_tc": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
                              c_vp, c_int,
@@ -64,6 +67,8 @@ def lib() -> ctypes.CDLL:
         L.ev2h_last_error.restype = ctypes.c_char_p
         L.ev2h_tc_packed_bytes.argtypes = [c_int, c_int, c_int]
         L.ev2h_tc_packed_bytes.restype = c_i64
+        L.ev2h_tc_packed_bytes_kc.argtypes = [c_int, c_int, c_int, c_int]
+        L.ev2h_tc_packed_bytes_kc.restype = c_i64
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = args
@@ -267,17 +272,24 @@ def tc_supported(Cout: int, pool_rows: int) -> bool:
     return (Cout <= 256 or Cout % 256 == 0) and (pool_rows in (0, 32, 64) or pool_rows % 128 == 0)
 
 
-def tc_pack(wt: torch.Tensor, Cin: int, Cout: int, mode: int) -> torch.Tensor:
-    """folded wt [Cin_pad, Cout_pad] -> packed shared-memory images (uint8 buffer) for `mode`."""
-    n = lib().ev2h_tc_packed_bytes(Cin, Cout, mode)
+def tc_pack(wt: torch.Tensor, Cin: int, Cout: int, mode: int, kc: int = 32) -> torch.Tensor:
+    """folded wt [Cin_pad, Cout_pad] -> packed shared-memory images (uint8 buffer) for `mode`,
+    `kc` input channels per image."""
+    n = lib().ev2h_tc_packed_bytes_kc(Cin, Cout, mode, kc)
     if n <= 0:
-        raise RuntimeError("ev2h_tc_packed_bytes(%d, %d, %d) failed" % (Cin, Cout, mode))
+        raise RuntimeError("ev2h_tc_packed_bytes_kc(%d, %d, %d, %d) failed" % (Cin, Cout, mode, kc))
     packed = torch.empty((n,), dtype=torch.uint8, device=wt.device)
     with torch.cuda.device(wt.device):
         with _timed("ev2h_tc_pack_weights"):
-            _check(lib().ev2h_tc_pack_weights(_p(wt), wt.shape[1], Cin, Cout, mode, _p(packed), _stream(wt)),
-                   "ev2h_tc_pack_weights")
+            _check(lib().ev2h_tc_pack_weights_kc(_p(wt), wt.shape[1], Cin, Cout, mode, kc, _p(packed), _stream(wt)),
+                   "ev2h_tc_pack_weights_kc")
     return packed
+
+
+def fused_kc(mode: int, per_point: bool, couts) -> int:
+    """K-chunk length the fused kernel wants for this stack (-1: unsupported)."""
+    arr = (ctypes.c_int32 * len(couts))(*couts)
+    return lib().ev2h_sa_msg_fused_kc(mode, 1 if per_point else 0, len(couts), arr)
 
 
 def linear_relu_tc(x, M, ld_x, Cin, packed, bias, Cout, pool_rows, y, ld_y, y_col_off, mode):
@@ -294,18 +306,17 @@ def linear_no_relu(x, M, ld_x, Cin, wt, bias, Cout, y, ld_y, y_col_off=0):
                    "ev2h_linear_f32")
 
 
-def fused_supported(K: int, widths, first_in: int, per_point: bool) -> bool:
+def fused_supported(K: int, widths, first_in: int, per_point: bool, mode: int = TC_TF32X3) -> bool:
     """Shapes ev2h_sa_msg_fused_tc covers (see include/ev2h.h)."""
-    if K not in (32, 64, 128) or any(w > 256 for w in widths):
+    if K not in (32, 64, 128) or any(w > 256 for w in widths) or len(widths) != 3:
         return False
-    n = [(w + 15) // 16 * 16 for w in widths]
     if per_point:
-        n = n[1:]
-        if len(n) != 2 or widths[0] % 32 != 0:
+        if widths[0] % 32 != 0:
             return False
-    elif len(n) != 3 or first_in > 8:
+        return fused_kc(mode, True, widths[1:]) > 0
+    if first_in > 8:
         return False
-    return sum(n[:-1]) + (n[-1] + 31) // 32 * 32 <= 512
+    return fused_kc(mode, False, widths) > 0
 
 
 def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, P, ld_p, p_col, C, ld_c, c_col,

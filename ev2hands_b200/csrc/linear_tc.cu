@@ -61,21 +61,21 @@ struct TcParams {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 tc_pack_kernel(const float *__restrict__ wt, int ld_w, int cin_rows, int cout_cols, int n_blk, int n_blocks,
-               int n_kc, uint8_t *__restrict__ out) {
-    const int64_t total = (int64_t)n_blocks * n_kc * n_blk * TC_KC;
+               int n_kc, int kc_len, uint8_t *__restrict__ out) {
+    const int64_t total = (int64_t)n_blocks * n_kc * n_blk * kc_len;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
-    const int kk = (int)(e % TC_KC);
-    int64_t t = e / TC_KC;
+    const int kk = (int)(e % kc_len);
+    int64_t t = e / kc_len;
     const int n = (int)(t % n_blk);
     t /= n_blk;
     const int kc = (int)(t % n_kc);
     const int nb = (int)(t / n_kc);
-    const int k = kc * TC_KC + kk, col = nb * n_blk + n;
+    const int k = kc * kc_len + kk, col = nb * n_blk + n;
     const float w = (k < cin_rows && col < cout_cols) ? wt[(int64_t)k * ld_w + col] : 0.f;
     constexpr int EB = tc_elem_bytes(MODE);
     constexpr int CH = 16 / EB;                         // elements per 16-byte chunk
-    const size_t part = (size_t)tc_part_bytes(MODE, n_blk);
+    const size_t part = (size_t)n_blk * kc_len * EB;
     uint8_t *stage = out + ((size_t)nb * n_kc + kc) * (tc_parts(MODE) * part);
     const size_t off = (size_t)(kk / CH) * ((size_t)n_blk * 16) + (size_t)n * 16 + (size_t)(kk % CH) * EB;
     if (MODE == TC_MODE_BF16) {
@@ -361,29 +361,38 @@ static bool tc_pool_supported(int K) { return K == 0 || K == 32 || K == 64 || (K
 
 extern "C" int ev2h_tc_set_debug(int flags) { ev2h::g_tc_debug = flags; return 0; }
 
-extern "C" int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode) {
+extern "C" int64_t ev2h_tc_packed_bytes_kc(int Cin, int Cout, int mode, int kc) {
     using namespace ev2h;
-    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3)) return -1;
+    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3) || (kc != 16 && kc != 32)) return -1;
     const int n_blk = tc_n_blk(Cout);
-    return (int64_t)tc_n_blocks(Cout) * tc_n_kc(Cin) * tc_parts(mode) * tc_part_bytes(mode, n_blk);
+    return (int64_t)tc_n_blocks(Cout) * ((Cin + kc - 1) / kc) * tc_parts(mode) * n_blk * kc * tc_elem_bytes(mode);
 }
+extern "C" int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode) { return ev2h_tc_packed_bytes_kc(Cin, Cout, mode, ev2h::TC_KC); }
 
+extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cout, int mode, int kc, void *packed,
+                                       ev2h_stream_t stream);
 extern "C" int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
                                     ev2h_stream_t stream) {
+    return ev2h_tc_pack_weights_kc(wt, ld_w, Cin, Cout, mode, ev2h::TC_KC, packed, stream);
+}
+
+extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cout, int mode, int kc, void *packed,
+                                       ev2h_stream_t stream) {
     using namespace ev2h;
+    EV2H_REQUIRE(kc == 16 || kc == 32, "ev2h_tc_pack_weights: K chunk must be 16 or 32");
     EV2H_REQUIRE(wt && packed, "ev2h_tc_pack_weights: null argument");
     EV2H_REQUIRE(Cin > 0 && Cout > 0 && ld_w >= Cout, "ev2h_tc_pack_weights: bad sizes");
     EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3, "ev2h_tc_pack_weights: unknown mode %d", mode);
-    const int n_blk = tc_n_blk(Cout), n_blocks = tc_n_blocks(Cout), n_kc = tc_n_kc(Cin);
-    const int64_t total = (int64_t)n_blocks * n_kc * n_blk * TC_KC;
+    const int n_blk = tc_n_blk(Cout), n_blocks = tc_n_blocks(Cout), n_kc = (Cin + kc - 1) / kc;
+    const int64_t total = (int64_t)n_blocks * n_kc * n_blk * kc;
     const unsigned grid = (unsigned)((total + 255) / 256);
     // wt comes from ev2h_fold_conv_bn_f32: round_up(Cin,16) rows of ld_w columns, zero padded
     const int cin_rows = round_up(Cin, 16);
     const int cout_cols = ld_w;
     if (mode == TC_MODE_BF16)
-        tc_pack_kernel<TC_MODE_BF16><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, (uint8_t *)packed);
+        tc_pack_kernel<TC_MODE_BF16><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
     else
-        tc_pack_kernel<TC_MODE_TF32X3><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, (uint8_t *)packed);
+        tc_pack_kernel<TC_MODE_TF32X3><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
     return check_launch("ev2h_tc_pack_weights");
 }
 

@@ -35,11 +35,13 @@
 namespace ev2h {
 
 constexpr int FZ_BLOCK_M = 128;
-constexpr int FZ_KC = 32;                 // channels per K chunk
 constexpr int FZ_MAX_GEMMS = 3;
 constexpr int FZ_MAX_RING = 8;
-constexpr int FZ_LOADER_GROUPS = 2;
-constexpr int FZ_THREADS = 32 * (6 + 4 * FZ_LOADER_GROUPS);   // 4 epilogue, issuer, weight streamer, loaders
+// Template parameters of the kernel:
+//   KC  channels per K chunk (32, or 16 to halve the ring footprint so two CTAs share an SM)
+//   LG  loader groups of 4 warps;  threads = 32 * (6 + 4 LG): 4 epilogue, issuer, weight streamer, loaders
+//   OCC CTAs per SM the instance is built for (launch bound and TMEM share: 512 / OCC columns)
+__host__ __device__ constexpr int fz_threads(int lg) { return 32 * (6 + 4 * lg); }
 
 enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1 };
 
@@ -64,8 +66,11 @@ struct FusedParams {
     const float *bias[FZ_MAX_GEMMS];
     // output: pooled features of this scale, rows = centres
     float *out; int ld_out, out_col, c_out;
+    int alias02;                                 // GEMM 2's accumulator reuses GEMM 0's TMEM columns
+    int tmem_cols;                               // TMEM columns to allocate (power of two)
     // rings
     int sa, sb, a_slot_bytes, b_slot_bytes;
+    long long *dbg;     // optional [gridDim.x][8] issuer wait-cycle counters (debug/profiling only)
 };
 
 struct Ring {
@@ -74,15 +79,20 @@ struct Ring {
     __device__ __forceinline__ void advance(int k) { for (int i = 0; i < k; ++i) advance(); }
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(FZ_THREADS, 1)
+template <int MODE, int KC, int LG, int OCC>
+__global__ void __launch_bounds__(fz_threads(LG), OCC)
 sa_fused_tc_kernel(const FusedParams p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
+    constexpr int FZ_KC = KC;
+    constexpr int FZ_THREADS = fz_threads(LG);
+    constexpr int FZ_LOADER_GROUPS = LG;
     constexpr int EB = MODE == FZ_MODE_BF16 ? 2 : 4;
     constexpr int PARTS = MODE == FZ_MODE_BF16 ? 1 : 2;
-    constexpr int A_PART = FZ_BLOCK_M * FZ_KC * EB;      // 16 KB (tf32) / 8 KB (bf16)
+    constexpr int A_PART = FZ_BLOCK_M * FZ_KC * EB;      // per precision part: 16 KB (tf32, KC 32) / 8 KB
+    constexpr int NCH = FZ_KC * EB / 16;                 // 16-byte operand chunks per row per K chunk
     constexpr int UMMA_K = 32 / EB;
     constexpr int K_STEPS = FZ_KC / UMMA_K;
+    static_assert(NCH >= 2 && (MODE == FZ_MODE_TF32X3 || KC == 32), "unsupported chunk geometry");
     constexpr int CHUNK_ROWS_BYTES = FZ_BLOCK_M * 16;    // one 16-byte operand chunk for all 128 rows
 
     uint8_t *a_ring = fz_smem;
@@ -114,7 +124,7 @@ sa_fused_tc_kernel(const FusedParams p) {
     }
     for (int g = 0; g < p.G; ++g)
         for (int i = tid; i < p.n[g]; i += FZ_THREADS) bias_s[p.bias_off[g] + i] = p.bias[g][i];
-    if (warp == 4) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == 4) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -208,11 +218,12 @@ sa_fused_tc_kernel(const FusedParams p) {
                 }
                 for (int kc = 0; kc < p.n_chunks[0]; ++kc, ++ln) {
                     if ((int)(ln % FZ_LOADER_GROUPS) == grp) {
-                        float4 v[8];
+                        constexpr int QP = FZ_KC / 16;          // passes of 4 channel quads per 8-row group
+                        float4 v[4 * QP];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int h = i >> 1;
-                            const int k = kc * FZ_KC + 4 * (oct + 4 * (i & 1));
+                        for (int i = 0; i < 4 * QP; ++i) {
+                            const int h = i / QP;
+                            const int k = kc * FZ_KC + 4 * (oct + 4 * (i % QP));
                             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (p_row[h] >= 0) {
                                 const float4 a = __ldg(reinterpret_cast<const float4 *>(p.P + p_row[h] * p.ld_p + p.p_col + k));
@@ -224,9 +235,9 @@ sa_fused_tc_kernel(const FusedParams p) {
                         uint8_t *st = a_ring + (size_t)ra.slot * p.a_slot_bytes;
                         if (MODE == FZ_MODE_TF32X3) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int row = 32 * wq + (i >> 1) * 8 + l8;
-                                const int c = oct + 4 * (i & 1);
+                            for (int i = 0; i < 4 * QP; ++i) {
+                                const int row = 32 * wq + (i / QP) * 8 + l8;
+                                const int c = oct + 4 * (i % QP);
                                 float4 hi, lo;
                                 tc::split_tf32(v[i].x, hi.x, lo.x); tc::split_tf32(v[i].y, hi.y, lo.y);
                                 tc::split_tf32(v[i].z, hi.z, lo.z); tc::split_tf32(v[i].w, hi.w, lo.w);
@@ -238,9 +249,9 @@ sa_fused_tc_kernel(const FusedParams p) {
                             // lanes oct and oct+... own channel quads (oct + 4*(i&1)); pair them through shuffles:
                             // quad q (0..7) belongs to chunk q/2; lane octet `oct` holds quads oct and oct+4.
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int row = 32 * wq + (i >> 1) * 8 + l8;
-                                const int quad = oct + 4 * (i & 1);
+                            for (int i = 0; i < 4 * QP; ++i) {
+                                const int row = 32 * wq + (i / QP) * 8 + l8;
+                                const int quad = oct + 4 * (i % QP);
                                 __nv_bfloat162 q0 = __floats2bfloat162_rn(v[i].x, v[i].y), q1 = __floats2bfloat162_rn(v[i].z, v[i].w);
                                 uint2 pk;
                                 pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
@@ -279,49 +290,75 @@ sa_fused_tc_kernel(const FusedParams p) {
         __syncwarp();
     } else if (warp == 4) {
         // =============================== UMMA issuer ===============================
-        if (lane == 0) {
-            Ring ra{0, 0, p.sa}, rb{0, 0, p.sb};
-            uint32_t it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                for (int g = 0; g < p.G; ++g) {
-                    const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M, (uint32_t)p.n[g]);
-                    const uint32_t a_lbo = CHUNK_ROWS_BYTES, b_lbo = (uint32_t)p.n[g] * 16, sbo = 128;
-                    const uint32_t b_part = (uint32_t)(p.n[g] * FZ_KC * EB);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)p.tmem_col[g];
-                    tc::mbar_wait(acc_empty + g, (it & 1) ^ 1, 30 + g);       // previous tile's epilogue drained this accumulator
+        // The whole warp walks the chunk sequence (so every value below is warp-uniform and the
+        // descriptor arithmetic stays on the uniform datapath); one elected lane issues.
+        Ring ra{0, 0, p.sa}, rb{0, 0, p.sb};
+        uint32_t it = 0;
+        const bool prof = p.dbg != nullptr;
+        long long w_a[3] = {0, 0, 0}, w_b = 0, w_acc = 0, w_commit = 0, t0 = 0, t1 = 0;
+        const long long t_begin = prof ? clock64() : 0;
+        const uint32_t a_lbo = CHUNK_ROWS_BYTES, sbo = 128;
+        const uint32_t desc_hi = tc::smem_desc_hi(sbo);
+        const uint32_t a_ring_addr = tc::smem_u32(a_ring), b_ring_addr = tc::smem_u32(b_ring);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int g = 0; g < p.G; ++g) {
+                const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M, (uint32_t)p.n[g]);
+                const uint32_t b_lbo = (uint32_t)p.n[g] * 16;
+                const uint32_t b_part = (uint32_t)(p.n[g] * FZ_KC * EB);
+                const uint32_t d_tmem = tmem_base + (uint32_t)p.tmem_col[g];
+                const int n_chunks = p.n_chunks[g];
+                if (prof) t0 = clock64();
+                tc::mbar_wait(acc_empty + g, (it & 1) ^ 1, 30 + g);       // previous tile's epilogue drained this accumulator
+                if (p.alias02) {
+                    // GEMM 0 and GEMM 2 share TMEM columns: GEMM 0 also needs the previous tile's pooled
+                    // epilogue (GEMM 2) done, GEMM 2 needs THIS tile's GEMM 0 activations converted
+                    if (g == 0) tc::mbar_wait(acc_empty + 2, (it & 1) ^ 1, 36);
+                    if (g == 2) tc::mbar_wait(acc_empty + 0, it & 1, 37);
+                }
+                if (prof) w_acc += clock64() - t0;
+                tc::tc_fence_after();
+                for (int c = 0; c < n_chunks; ++c) {
+                    if (prof) t0 = clock64();
+                    tc::mbar_wait(a_full + ra.slot, ra.phase, 40 + g);
+                    if (prof) { t1 = clock64(); w_a[g] += t1 - t0; }
+                    tc::mbar_wait(b_full + rb.slot, rb.phase, 50 + g);
+                    if (prof) w_b += clock64() - t1;
                     tc::tc_fence_after();
-                    for (int c = 0; c < p.n_chunks[g]; ++c) {
-                        tc::mbar_wait(a_full + ra.slot, ra.phase, 40 + g);
-                        tc::mbar_wait(b_full + rb.slot, rb.phase, 50 + g);
-                        tc::tc_fence_after();
-                        const uint32_t a0 = tc::smem_u32(a_ring + (size_t)ra.slot * p.a_slot_bytes);
-                        const uint32_t b0 = tc::smem_u32(b_ring + (size_t)rb.slot * p.b_slot_bytes);
-                        const int ks = (c == p.n_chunks[g] - 1) ? p.k_steps_last[g] : K_STEPS;
+                    const uint32_t a0 = a_ring_addr + (uint32_t)ra.slot * (uint32_t)p.a_slot_bytes;
+                    const uint32_t b0 = b_ring_addr + (uint32_t)rb.slot * (uint32_t)p.b_slot_bytes;
+                    const int ks = (c == n_chunks - 1) ? p.k_steps_last[g] : K_STEPS;
+                    if (tc::elect_one()) {
+                        // descriptor low words; one K step = two 16-byte chunks further along K
+                        uint32_t a_hi = tc::smem_desc_lo(a0, a_lbo), b_hi = tc::smem_desc_lo(b0, b_lbo);
+                        const uint32_t a_step = (2 * a_lbo) >> 4, b_step = (2 * b_lbo) >> 4;
+                        const uint32_t a_lo_off = A_PART >> 4, b_lo_off = b_part >> 4;
+#pragma unroll 1
                         for (int j = 0; j < ks; ++j) {
-                            const uint32_t a_off = (uint32_t)j * 2 * a_lbo, b_off = (uint32_t)j * 2 * b_lbo;
                             const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
                             if (MODE == FZ_MODE_TF32X3) {
-                                const uint64_t a_hi = tc::smem_desc_kmajor(a0 + a_off, a_lbo, sbo);
-                                const uint64_t a_lo = tc::smem_desc_kmajor(a0 + A_PART + a_off, a_lbo, sbo);
-                                const uint64_t b_hi = tc::smem_desc_kmajor(b0 + b_off, b_lbo, sbo);
-                                const uint64_t b_lo = tc::smem_desc_kmajor(b0 + b_part + b_off, b_lbo, sbo);
-                                tc::umma_tf32(d_tmem, a_lo, b_hi, idesc, acc);
-                                tc::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                                tc::umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                                tc::umma_tf32(d_tmem, tc::make_desc(a_hi + a_lo_off, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
+                                tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi + b_lo_off, desc_hi), idesc, 1u);
+                                tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, 1u);
                             } else {
-                                tc::umma_f16(d_tmem, tc::smem_desc_kmajor(a0 + a_off, a_lbo, sbo),
-                                             tc::smem_desc_kmajor(b0 + b_off, b_lbo, sbo), idesc, acc);
+                                tc::umma_f16(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
                             }
+                            a_hi += a_step; b_hi += b_step;
                         }
+                        if (prof) t0 = clock64();
                         tc::umma_commit(a_empty + ra.slot);
                         tc::umma_commit(b_empty + rb.slot);
-                        ra.advance(); rb.advance();
+                        if (c == n_chunks - 1) tc::umma_commit(acc_full + g);
+                        if (prof) w_commit += clock64() - t0;
                     }
-                    tc::umma_commit(acc_full + g);
+                    __syncwarp();
+                    ra.advance(); rb.advance();
                 }
             }
         }
-        __syncwarp();
+        if (prof && lane == 0) {
+            long long *d = p.dbg + (size_t)blockIdx.x * 8;
+            d[0] = w_a[0]; d[1] = w_a[1]; d[2] = w_a[2]; d[3] = w_b; d[4] = w_acc; d[5] = clock64() - t_begin; d[6] = it; d[7] = w_commit;
+        }
     } else {
         // =============================== epilogue warps ===============================
         const int q = warp, r = q * 32 + lane;
@@ -339,20 +376,21 @@ sa_fused_tc_kernel(const FusedParams p) {
                 if (g < p.G - 1) {
                     // ---- activations of layer g -> operand chunks of layer g+1 ----
                     for (int c = 0; c < p.n_chunks[g + 1]; ++c) {
-                        uint32_t raw[32];
-                        tc::tmem_ld32(t_addr + c * 32, raw);
+                        uint32_t raw[FZ_KC];
+                        if constexpr (FZ_KC == 32) tc::tmem_ld32(t_addr + c * 32, raw);
+                        else tc::tmem_ld16(t_addr + c * 16, raw);
                         tc::tmem_ld_wait();
-                        float v[32];
+                        float v[FZ_KC];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = c * 32 + j;
+                        for (int j = 0; j < FZ_KC; ++j) {
+                            const int col = c * FZ_KC + j;
                             v[j] = col < p.n[g] ? fmaxf(__uint_as_float(raw[j]) + bias_g[col], 0.f) : 0.f;
                         }
                         tc::mbar_wait(a_empty + ra.slot, ra.phase ^ 1, 70 + g);
                         uint8_t *st = a_ring + (size_t)ra.slot * p.a_slot_bytes;
                         if (MODE == FZ_MODE_TF32X3) {
 #pragma unroll
-                            for (int cc = 0; cc < 8; ++cc) {
+                            for (int cc = 0; cc < NCH; ++cc) {
                                 float4 hi, lo;
                                 tc::split_tf32(v[4 * cc], hi.x, lo.x); tc::split_tf32(v[4 * cc + 1], hi.y, lo.y);
                                 tc::split_tf32(v[4 * cc + 2], hi.z, lo.z); tc::split_tf32(v[4 * cc + 3], hi.w, lo.w);
@@ -361,7 +399,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                             }
                         } else {
 #pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
+                            for (int cc = 0; cc < NCH; ++cc) {
                                 __nv_bfloat162 q0 = __floats2bfloat162_rn(v[8 * cc], v[8 * cc + 1]);
                                 __nv_bfloat162 q1 = __floats2bfloat162_rn(v[8 * cc + 2], v[8 * cc + 3]);
                                 __nv_bfloat162 q2 = __floats2bfloat162_rn(v[8 * cc + 4], v[8 * cc + 5]);
@@ -432,11 +470,68 @@ sa_fused_tc_kernel(const FusedParams p) {
     __syncthreads();
     if (warp == 4) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, 512);
+        tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
 }  // namespace ev2h
+
+namespace ev2h {
+static long long *g_fused_dbg = nullptr;
+
+// Which kernel instance serves a layer stack: two CTAs per SM (KC 16 for tf32) whenever the
+// accumulators of one tile fit 256 TMEM columns, so one CTA's epilogues overlap the other's UMMAs.
+struct FusedPlan { int kc, occ, lg, alias02, tmem_cols, col[FZ_MAX_GEMMS], n[FZ_MAX_GEMMS]; bool ok; };
+
+static FusedPlan fused_plan(int mode, bool mode_b, int n_layers, const int32_t *cout) {
+    FusedPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    int sum = 0;
+    for (int g = 0; g < n_layers; ++g) { pl.n[g] = round_up(cout[g], 16); sum += pl.n[g]; }
+    auto extent = [&](bool alias) {
+        int c = 0, ext = 0;
+        for (int g = 0; g < n_layers; ++g) {
+            if (alias && g == 2) { pl.col[2] = 0; }
+            else if (alias && g == 0) { pl.col[0] = 0; c = pl.n[0] > pl.n[2] ? pl.n[0] : pl.n[2]; }
+            else { pl.col[g] = c; c += pl.n[g]; }
+            const int e = pl.col[g] + round_up(pl.n[g], 32);
+            if (e > ext) ext = e;
+        }
+        return ext;
+    };
+    int ext = extent(false);
+    pl.alias02 = 0;
+    if (!mode_b && n_layers == 3 && ext > 256 && extent(true) <= 256) { pl.alias02 = 1; ext = extent(true); }
+    else ext = extent(false);
+    pl.ok = ext <= 512;
+    pl.occ = (!mode_b && ext <= 256) ? 2 : 1;
+    pl.kc = (pl.occ == 2 && mode == FZ_MODE_TF32X3) ? 16 : 32;
+    pl.lg = pl.occ == 2 ? 1 : 2;
+    pl.tmem_cols = 32;
+    while (pl.tmem_cols < ext) pl.tmem_cols *= 2;
+    if (pl.occ == 2 && pl.tmem_cols > 256) pl.occ = 1;
+    return pl;
+}
+}  // namespace ev2h
+
+extern "C" int ev2h_fused_set_debug_buffer(void *buf) { ev2h::g_fused_dbg = (long long *)buf; return 0; }
+
+extern "C" int ev2h_sa_msg_fused_kc(int mode, int per_point, int n_layers, const int32_t *cout_host) {
+    using namespace ev2h;
+    if (!cout_host || n_layers < 2 || n_layers > 3) return -1;
+    const FusedPlan pl = fused_plan(mode, per_point != 0, n_layers, cout_host);
+    return pl.ok ? pl.kc : -1;
+}
+
+template <int MODE, int KC, int LG, int OCC>
+static int launch_fused(const ev2h::FusedParams &p, size_t smem, unsigned grid, cudaStream_t st) {
+    using namespace ev2h;
+    auto k = sa_fused_tc_kernel<MODE, KC, LG, OCC>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_sa_msg_fused_tc: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
+    k<<<grid, fz_threads(LG), smem, st>>>(p);
+    return check_launch("ev2h_sa_msg_fused_tc");
+}
 
 extern "C" int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
@@ -464,38 +559,44 @@ extern "C" int ev2h_sa_msg_fused_tc(
         if (cin_host[0] % 32 != 0)
             return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: per-point mode needs a multiple of 32 channels, got %d", cin_host[0]);
     }
+    for (int g = 0; g < n_layers; ++g) {
+        if (cout_host[g] > 256) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: layer width %d > 256", cout_host[g]);
+        if (g > 0 && cin_host[g] != cout_host[g - 1]) return fail(EV2H_ERR_BAD_ARGUMENT, "ev2h_sa_msg_fused_tc: layer %d input width mismatch", g);
+    }
+    const FusedPlan pl = fused_plan(mode, mode_b, n_layers, cout_host);
+    if (!pl.ok) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: accumulators exceed the 512 TMEM columns");
+    const int KC = pl.kc;
     const int EB = mode == FZ_MODE_BF16 ? 2 : 4, PARTS = mode == FZ_MODE_BF16 ? 1 : 2, UMMA_K = 32 / EB;
 
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
     p.mode_b = mode_b ? 1 : 0; p.pts8 = pts8; p.D = D; p.P = P; p.ld_p = ld_p; p.p_col = p_col; p.C = C; p.ld_c = ld_c; p.c_col = c_col;
-    p.G = n_layers;
-    int col = 0, boff = 0, max_n = 0;
+    p.G = n_layers; p.alias02 = pl.alias02; p.tmem_cols = pl.tmem_cols;
+    int boff = 0, max_n = 0;
     for (int g = 0; g < n_layers; ++g) {
-        const int cin = cin_host[g], cout = cout_host[g];
-        if (cout > 256) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: layer width %d > 256", cout);
-        if (g > 0 && cin != cout_host[g - 1]) return fail(EV2H_ERR_BAD_ARGUMENT, "ev2h_sa_msg_fused_tc: layer %d input width mismatch", g);
-        p.n[g] = round_up(cout, 16);
-        p.n_chunks[g] = (cin + FZ_KC - 1) / FZ_KC;
-        const int rem = cin - (p.n_chunks[g] - 1) * FZ_KC;
+        const int cin = cin_host[g];
+        p.n[g] = pl.n[g];
+        p.n_chunks[g] = (cin + KC - 1) / KC;
+        const int rem = cin - (p.n_chunks[g] - 1) * KC;
         p.k_steps_last[g] = (rem + UMMA_K - 1) / UMMA_K;
-        p.tmem_col[g] = col; col += p.n[g];
+        p.tmem_col[g] = pl.col[g];
         p.bias_off[g] = boff; boff += p.n[g];
         p.w[g] = (const uint8_t *)w_packed_host[g]; p.bias[g] = bias_host[g];
         EV2H_REQUIRE(p.w[g] && p.bias[g] && ((uintptr_t)p.w[g] & 15) == 0, "ev2h_sa_msg_fused_tc: layer %d weights null or misaligned", g);
         if (p.n[g] > max_n) max_n = p.n[g];
     }
-    if (col > 512 || p.tmem_col[n_layers - 1] + round_up(p.n[n_layers - 1], 32) > 512)
-        return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: accumulators need %d TMEM columns (> 512)", col);
     p.out = out_rows; p.ld_out = ld_out; p.out_col = out_col; p.c_out = cout_host[n_layers - 1];
     EV2H_REQUIRE(ld_out >= out_col + p.c_out, "ev2h_sa_msg_fused_tc: ld_out too small");
+    p.dbg = g_fused_dbg;
 
-    p.a_slot_bytes = PARTS * FZ_BLOCK_M * FZ_KC * EB;
-    p.b_slot_bytes = PARTS * max_n * FZ_KC * EB;
+    p.a_slot_bytes = PARTS * FZ_BLOCK_M * KC * EB;
+    p.b_slot_bytes = PARTS * max_n * KC * EB;
     const int tail = (4 * FZ_MAX_RING + 2 * FZ_MAX_GEMMS + 1) * 8 + 16 + (boff + 2 * 4 * p.n[n_layers - 1]) * 4;
-    const int budget = 227 * 1024 - tail - 512;
-    // split the budget: at least 2 slots each; weights get the remainder (they are prefetched furthest ahead)
+    int occ = pl.occ;
+    int budget = (occ == 2 ? 113 : 227) * 1024 - tail - 512;
+    if (occ == 2 && budget < 2 * p.a_slot_bytes + 2 * p.b_slot_bytes) { occ = 1; budget = 227 * 1024 - tail - 512; }
+    // at least 2 slots each; a third operand slot when affordable; weights get the rest (prefetched furthest ahead)
     p.sa = 2;
     if (budget - 3 * p.a_slot_bytes >= 3 * p.b_slot_bytes) p.sa = 3;
     p.sb = (budget - p.sa * p.a_slot_bytes) / p.b_slot_bytes;
@@ -507,15 +608,15 @@ extern "C" int ev2h_sa_msg_fused_tc(
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_tiles = ((int64_t)B * S * K + FZ_BLOCK_M - 1) / FZ_BLOCK_M;
-    const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-    cudaError_t e;
-    if (mode == FZ_MODE_BF16) {
-        e = cudaFuncSetAttribute(sa_fused_tc_kernel<FZ_MODE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) sa_fused_tc_kernel<FZ_MODE_BF16><<<grid, FZ_THREADS, smem, as_stream(stream)>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(sa_fused_tc_kernel<FZ_MODE_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) sa_fused_tc_kernel<FZ_MODE_TF32X3><<<grid, FZ_THREADS, smem, as_stream(stream)>>>(p);
+    const int64_t slots = (int64_t)sms * occ;
+    const unsigned grid = (unsigned)(n_tiles < slots ? n_tiles : slots);
+    cudaStream_t st = as_stream(stream);
+    if (mode == FZ_MODE_TF32X3) {
+        if (KC == 16) return occ == 2 ? launch_fused<FZ_MODE_TF32X3, 16, 1, 2>(p, smem, grid, st)
+                                      : launch_fused<FZ_MODE_TF32X3, 16, 1, 1>(p, smem, grid, st);
+        return launch_fused<FZ_MODE_TF32X3, 32, 2, 1>(p, smem, grid, st);
     }
-    if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_sa_msg_fused_tc: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
-    return check_launch("ev2h_sa_msg_fused_tc");
+    if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_BF16, 32, 1, 2>(p, smem, grid, st)
+                                     : launch_fused<FZ_MODE_BF16, 32, 1, 1>(p, smem, grid, st);
+    return launch_fused<FZ_MODE_BF16, 32, 2, 1>(p, smem, grid, st);
 }

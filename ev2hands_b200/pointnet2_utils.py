@@ -320,7 +320,7 @@ class PointNetSetAbstractionMsg(nn.Module):
 
         # Which scales can run in the fused tensor-core kernel, and with which first-layer mode.
         per_point = D + 3 > 8
-        fused = [mode is not None and _FUSED_ENABLED and _capi.fused_supported(K, w, D + 3, per_point)
+        fused = [mode is not None and _FUSED_ENABLED and _capi.fused_supported(K, w, D + 3, per_point, mode)
                  for K, w in zip(self.nsample_list, widths)]
 
         pts8 = P = C = None
@@ -365,11 +365,12 @@ class PointNetSetAbstractionMsg(nn.Module):
             layers = all_layers[i]
             if fused[i]:
                 use = layers[1:] if per_point else layers
+                kc = _capi.fused_kc(mode, per_point, [L["cout"] for L in use])
                 packed = []
                 for L in use:
-                    if mode not in L["packed"]:
-                        L["packed"][mode] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], mode)
-                    packed.append(L["packed"][mode])
+                    if (mode, kc) not in L["packed"]:
+                        L["packed"][(mode, kc)] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], mode, kc)
+                    packed.append(L["packed"][(mode, kc)])
                 _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D,
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
                                    C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,

@@ -178,6 +178,11 @@ EV2H_API int ev2h_linear_f32(const float *x, int64_t M, int ld_x, int Cin, const
 EV2H_API int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode);
 EV2H_API int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
                                   ev2h_stream_t stream);
+/* Same with an explicit K-chunk length (16 or 32 input channels per shared-memory image);
+ * ev2h_sa_msg_fused_kc tells which one the fused kernel wants for a given layer stack. */
+EV2H_API int64_t ev2h_tc_packed_bytes_kc(int Cin, int Cout, int mode, int kc);
+EV2H_API int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cout, int mode, int kc, void *packed,
+                                     ev2h_stream_t stream);
 EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
                                  const float *bias, int Cout, int pool_rows, float *y, int ld_y,
                                  int y_col_off, int mode, ev2h_stream_t stream);
@@ -205,6 +210,14 @@ EV2H_API int ev2h_sa_msg_fused_tc(
     int n_layers, const int32_t *cin_host, const int32_t *cout_host, const void *const *w_packed_host,
     const float *const *bias_host, float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream);
 
+/* K-chunk length (16 or 32) the fused kernel uses for this stack, i.e. the kc to pack its
+ * weights with; -1 if the stack is not supported.  cout_host = widths of the layers the kernel
+ * runs (3 in gather mode, the last 2 in per-point mode). */
+EV2H_API int ev2h_sa_msg_fused_kc(int mode, int per_point, int n_layers, const int32_t *cout_host);
+
+/* Debug/profiling only: device buffer [148][8] int64 receiving the UMMA issuer's wait-cycle counters
+ * of the next fused launches (NULL turns it off). */
+EV2H_API int ev2h_fused_set_debug_buffer(void *buf);
 /* Debug only: bit 0 swaps the leading/stride byte offsets of the UMMA shared-memory descriptors. */
 EV2H_API int ev2h_tc_set_debug(int flags);
 

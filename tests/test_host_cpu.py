@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), "libev2h.so does not export %s" % n
     assert L.ev2h_version() >= 100
     # every declared compute entry has a ctypes signature (the binding covers the whole ABI)
-    assert set(names) - {"ev2h_version", "ev2h_last_error", "ev2h_tc_packed_bytes"} == set(_capi._SIGNATURES)
+    assert set(names) - {"ev2h_version", "ev2h_last_error", "ev2h_tc_packed_bytes", "ev2h_tc_packed_bytes_kc"} == set(_capi._SIGNATURES)
 
 
 def test_bad_arguments_return_status_not_crash():
