@@ -197,10 +197,11 @@ def run_ours(args):
     ev_all = synth.make_windows(B * world, N_POINTS, seed=1234 + 2)
     s1_all = synth.make_start_indices(B * world, N_POINTS, 0)
     s2_all = synth.make_start_indices(B * world, 512, 1)
-    sl = slice(rank * B, (rank + 1) * B)
-    ev_host = torch.from_numpy(ev_all[sl]).pin_memory()
-    s1 = torch.from_numpy(s1_all[sl]).to(device)
-    s2 = torch.from_numpy(s2_all[sl]).to(device)
+    from ev2hands_b200 import sharding
+    ev_sh, s1_sh, s2_sh = sharding.shard((torch.from_numpy(ev_all), torch.from_numpy(s1_all), torch.from_numpy(s2_all)), rank, world)
+    ev_host = ev_sh.contiguous().pin_memory()
+    s1 = s1_sh.to(device)
+    s2 = s2_sh.to(device)
     ev_dev = ev_host.to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
 
@@ -266,10 +267,7 @@ def run_ours(args):
     e2e_ms = float(sum(a.elapsed_time(b) for a, b in e_evs))
 
     # ---- max over ranks
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms = sharding.max_over_ranks([total_ms, e2e_ms], device=device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -336,7 +334,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mlp", choices=["fp32", "tf32x3", "bf16"], default=os.environ.get("EV2H_MLP", "fp32"),
+    ap.add_argument("--mlp", choices=["fp32", "tf32x3", "bf16"], default=os.environ.get("EV2H_MLP", "tf32x3"),
                     help="arithmetic of the shared MLP: fp32 = CUDA-core FFMA, tf32x3 = tensor cores with fp32-level "
                          "accuracy (bar 1e-5), bf16 = tensor cores, bf16 operands (bar 1e-2)")
     args = ap.parse_args()

@@ -38,7 +38,7 @@ _WORKSPACE_BYTES = int(os.environ.get("EV2H_WORKSPACE_MB", "4096")) << 20
 #   "tf32x3" tensor cores, error-compensated 3xTF32: fp32-level accuracy (bar 1e-5)
 #   "bf16"   tensor cores, bf16 operands / fp32 accumulate (bar 1e-2)
 _MLP_PRECISIONS = ("fp32", "tf32x3", "bf16")
-_mlp_precision = os.environ.get("EV2H_MLP", "fp32")
+_mlp_precision = os.environ.get("EV2H_MLP", "tf32x3")
 
 
 # The fused grouping + MLP + max-pool kernel (sa_fused_tc.cu) is used for every scale it

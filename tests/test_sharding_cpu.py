@@ -1,0 +1,77 @@
+"""Host logic of the multi-GPU path on CPU: world_size-2 gloo processes shard a batch and its FPS
+start indices, run the per-window oracle on their shard, and the union must equal the unsharded run;
+timings agree through a max all-reduce; gradients average through one flattened all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ev2hands_b200 import sharding, synth
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 64, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import c_oracle
+    torch.set_num_threads(1)
+    B, N, S = 6, 256, 32
+    ev = synth.make_windows(B, N, seed=9)
+    start = synth.make_start_indices(B, N, seed=4)
+    xyz = np.ascontiguousarray(ev[:, :3].transpose(0, 2, 1))
+    (xs, ss) = sharding.shard((torch.from_numpy(xyz), torch.from_numpy(start)), rank, world)
+    idx = c_oracle.fps(xs.numpy(), S, ss.numpy())
+    np.save(os.path.join(out_dir, "fps_%d.npy" % rank), idx)
+    # timing agreement: slowest rank wins
+    got = sharding.max_over_ranks([1.0 + rank, 5.0 - rank])
+    assert got == [float(world), 5.0]
+    # gradient averaging through one flattened all-reduce
+    lin = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        lin.weight.fill_(0.5)
+        lin.bias.zero_()
+    lin(torch.full((4, 3), float(rank + 1))).sum().backward()
+    n = sharding.allreduce_mean_grads(lin.parameters())
+    assert n == 8
+    want_w = np.mean([4.0 * (r + 1) for r in range(world)])
+    assert torch.allclose(lin.weight.grad, torch.full((2, 3), want_w))
+    assert torch.allclose(lin.bias.grad, torch.full((2,), 4.0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_unsharded(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from oracle import c_oracle
+    B, N, S = 6, 256, 32
+    ev = synth.make_windows(B, N, seed=9)
+    start = synth.make_start_indices(B, N, seed=4)
+    xyz = np.ascontiguousarray(ev[:, :3].transpose(0, 2, 1))
+    whole = c_oracle.fps(xyz, S, start)
+    parts = np.concatenate([np.load(os.path.join(str(tmp_path), "fps_%d.npy" % r)) for r in range(world)])
+    assert np.array_equal(whole, parts)
