@@ -57,7 +57,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.05):
+    def __init__(self, index: int, period_s: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -194,8 +194,8 @@ def run_ours(args):
     enc = build_encoder(device)
     # Every rank owns its shard of the global batch; starts are generated for the global batch
     # and sharded with the data so results do not depend on the shard count.
-    ev_all = synth.make_windows(B * world, N_POINTS, seed=1234 + 2)
-    s1_all = synth.make_start_indices(B * world, N_POINTS, 0)
+    ev_all = synth.make_windows(B * world, args.points, seed=1234 + 2)
+    s1_all = synth.make_start_indices(B * world, args.points, 0)
     s2_all = synth.make_start_indices(B * world, 512, 1)
     from ev2hands_b200 import sharding
     ev_sh, s1_sh, s2_sh = sharding.shard((torch.from_numpy(ev_all), torch.from_numpy(s1_all), torch.from_numpy(s2_all)), rank, world)
@@ -296,7 +296,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xtf32)", "bf16": "bf16"}[args.mlp], "data": "synthetic",
         "config": {"workload": "encoder forward sa1->sa2->sa3 (TEHNet.py:172-181), %d windows per GPU, "
-                               "N=2048 points/window, 5 channels, random-init weights, eval mode" % B,
+                               "N=%d points/window, 5 channels, random-init weights, eval mode" % (B, args.points),
                    "windows_per_gpu": B, "global_windows": B * world,
                    "mlp_path": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 kind::tf32, 3-product split (fp32-level accuracy)",
                                 "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate"}[args.mlp],
@@ -334,6 +334,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--points", type=int, default=N_POINTS, help="events per window (2048 = the model's default; 16384 = config 5)")
     ap.add_argument("--mlp", choices=["fp32", "tf32x3", "bf16"], default=os.environ.get("EV2H_MLP", "tf32x3"),
                     help="arithmetic of the shared MLP: fp32 = CUDA-core FFMA, tf32x3 = tensor cores with fp32-level "
                          "accuracy (bar 1e-5), bf16 = tensor cores, bf16 operands (bar 1e-2)")

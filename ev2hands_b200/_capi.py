@@ -38,7 +38,7 @@ _SIGNATURES = {
     "ev2h_fused_set_debug_buffer": [c_vp],
     "ev2h_linear_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_sa_msg_fused_tc": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
-                             c_vp, c_int,
+                             c_vp, c_int, c_vp, c_int, c_vp,
                              c_vp, c_int, c_int, c_vp, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                              ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_int, c_int, c_int, c_vp],
@@ -316,11 +316,11 @@ def fused_supported(K: int, widths, first_in: int, per_point: bool, mode: int = 
         return fused_kc(mode, True, widths[1:]) > 0
     if first_in > 8:
         return False
-    return fused_kc(mode, False, widths) > 0
+    return fused_kc(mode, False, widths[1:]) > 0      # layer 1 runs in the loaders (exact fp32)
 
 
 def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, P, ld_p, p_col, C, ld_c, c_col,
-                 cins, couts, packed, biases, out_rows, ld_out, out_col, mode):
+                 cins, couts, packed, biases, out_rows, ld_out, out_col, mode, first_wt=None, first_bias=None):
     L = len(cins)
     a_cin = (ctypes.c_int32 * L)(*cins)
     a_cout = (ctypes.c_int32 * L)(*couts)
@@ -329,7 +329,8 @@ def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, P, ld_p, p_col, 
     with torch.cuda.device(out_rows.device):
         with _timed("ev2h_sa_msg_fused_tc"):
             _check(lib().ev2h_sa_msg_fused_tc(_p(idx), idx.shape[-1], k_off, _p(centres_rows), B, N, S, K,
-                                              _p(pts8), D, _p(P), ld_p, p_col, _p(C), ld_c, c_col,
+                                              _p(pts8), D, _p(first_wt), 0 if first_wt is None else first_wt.shape[1],
+                                              _p(first_bias), _p(P), ld_p, p_col, _p(C), ld_c, c_col,
                                               L, a_cin, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode,
                                               _stream(out_rows)), "ev2h_sa_msg_fused_tc")
 

@@ -51,8 +51,11 @@ struct FusedParams {
     const int32_t *idx; int idx_ld, k_off;       // ball-query result [B,S,idx_ld], this scale at k_off
     const float *centres;                        // [B,S,3]
     // first-layer source
-    int mode_b;
-    const float *pts8; int D;                    // mode A: [B,N,8] rows = [features(D) | xyz | 0]
+    int mode_b;                                  // 0 = gather rows, 1 = per-point layer 1 (P - C)
+    int ffma_first;                              // gather mode: loaders evaluate layer 1 (<= 8 -> c1 channels) in fp32 FFMA
+    const float *first_wt; int first_ld, c1;     // folded layer-1 weights, input-channel major [16, first_ld], and width
+    const float *first_bias;
+    const float *pts8; int D;                    // gather modes: [B,N,8] rows = [features(D) | xyz | 0]
     const float *P; int ld_p, p_col;             // mode B: per-point layer-1 pre-activation [B*N, ld_p]
     const float *C; int ld_c, c_col;             // mode B: per-centre offset [B*S, ld_c]
     // the GEMM chain
@@ -105,10 +108,12 @@ sa_fused_tc_kernel(const FusedParams p) {
     uint64_t *acc_full = b_empty + FZ_MAX_RING;          // [3]
     uint64_t *acc_empty = acc_full + FZ_MAX_GEMMS;       // [3]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + FZ_MAX_GEMMS + 1);
-    float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);          // [sum n[g]]
+    float *bias_s = reinterpret_cast<float *>(tmem_slot + 6);          // [sum n[g]], 16-byte aligned (tail offset 336)
     int bias_total = 0;
     for (int g = 0; g < p.G; ++g) bias_total += p.n[g];
     float *red = bias_s + bias_total;                                  // [2][4][n[G-1]]
+    float *w1s = red + 2 * 4 * p.n[p.G - 1];                           // [c1_pad][8] layer-1 weights (ffma_first)
+    float *b1s = w1s + (p.ffma_first ? p.n_chunks[0] * KC * 8 : 0);    // [c1_pad]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t M = (int64_t)p.B * p.S * p.K;
@@ -124,6 +129,14 @@ sa_fused_tc_kernel(const FusedParams p) {
     }
     for (int g = 0; g < p.G; ++g)
         for (int i = tid; i < p.n[g]; i += FZ_THREADS) bias_s[p.bias_off[g] + i] = p.bias[g][i];
+    if (p.ffma_first) {
+        const int c1_pad = p.n_chunks[0] * KC;
+        for (int i = tid; i < c1_pad * 8; i += FZ_THREADS) {
+            const int ch = i >> 3, k = i & 7;
+            w1s[i] = ch < p.c1 ? p.first_wt[(size_t)k * p.first_ld + ch] : 0.f;
+        }
+        for (int i = tid; i < c1_pad; i += FZ_THREADS) b1s[i] = i < p.c1 ? p.first_bias[i] : 0.f;
+    }
     if (warp == 4) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
@@ -137,7 +150,83 @@ sa_fused_tc_kernel(const FusedParams p) {
         uint32_t ln = 0;                          // counts first-layer chunks; groups alternate on it
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t m0 = tile * FZ_BLOCK_M;
-            if (!p.mode_b) {
+            if (p.ffma_first) {
+                // ---- gather + layer 1 in exact fp32 on the CUDA cores; thread = row ------------------------
+                // x = [features | xyz - centre] (8 floats, one 32-byte sector), then for every K chunk of the
+                // SECOND layer's input: relu(W1' x + b1') for KC channels, split, store as operand rows.
+                const int r = wq * 32 + lane;
+                const int64_t R = m0 + r;
+                float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                bool valid = false;
+                if (R < M) {
+                    const int64_t bs = R / p.K;
+                    const int j = (int)(R - bs * p.K);
+                    const int64_t b = bs / p.S;
+                    const int pt = p.idx[bs * p.idx_ld + p.k_off + j];
+                    if (pt >= 0 && pt < p.N) {
+                        valid = true;
+                        const float4 *src = reinterpret_cast<const float4 *>(p.pts8 + (b * p.N + pt) * 8);
+                        const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                        const float *c = p.centres + bs * 3;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const float ca = __ldg(c + a);
+#pragma unroll
+                            for (int ch = 0; ch < 8; ++ch)
+                                if (ch == p.D + a) x[ch] = __fsub_rn(x[ch], ca);   // grouped_xyz -= new_xyz (:245)
+                        }
+                    }
+                }
+                for (int kc = 0; kc < p.n_chunks[0]; ++kc, ++ln) {
+                    if ((int)(ln % FZ_LOADER_GROUPS) == grp) {
+                        float v[FZ_KC];
+#pragma unroll
+                        for (int j = 0; j < FZ_KC; ++j) {
+                            const int ch = kc * FZ_KC + j;
+                            const float4 wa = *reinterpret_cast<const float4 *>(w1s + ch * 8);
+                            const float4 wb = *reinterpret_cast<const float4 *>(w1s + ch * 8 + 4);
+                            float acc = b1s[ch];
+                            acc = fmaf(wa.x, x[0], acc); acc = fmaf(wa.y, x[1], acc); acc = fmaf(wa.z, x[2], acc); acc = fmaf(wa.w, x[3], acc);
+                            acc = fmaf(wb.x, x[4], acc); acc = fmaf(wb.y, x[5], acc); acc = fmaf(wb.z, x[6], acc); acc = fmaf(wb.w, x[7], acc);
+                            v[j] = valid ? fmaxf(acc, 0.f) : 0.f;
+                        }
+                        tc::mbar_wait(a_empty + ra.slot, ra.phase ^ 1, 16);
+                        uint8_t *st = a_ring + (size_t)ra.slot * p.a_slot_bytes;
+                        if (MODE == FZ_MODE_TF32X3) {
+#pragma unroll
+                            for (int cc = 0; cc < NCH; ++cc) {
+                                float4 hi, lo;
+                                tc::split_tf32(v[4 * cc], hi.x, lo.x); tc::split_tf32(v[4 * cc + 1], hi.y, lo.y);
+                                tc::split_tf32(v[4 * cc + 2], hi.z, lo.z); tc::split_tf32(v[4 * cc + 3], hi.w, lo.w);
+                                *reinterpret_cast<float4 *>(st + cc * CHUNK_ROWS_BYTES + r * 16) = hi;
+                                *reinterpret_cast<float4 *>(st + A_PART + cc * CHUNK_ROWS_BYTES + r * 16) = lo;
+                            }
+                        } else {
+#pragma unroll
+                            for (int cc = 0; cc < NCH; ++cc) {
+                                __nv_bfloat162 q0 = __floats2bfloat162_rn(v[8 * cc], v[8 * cc + 1]);
+                                __nv_bfloat162 q1 = __floats2bfloat162_rn(v[8 * cc + 2], v[8 * cc + 3]);
+                                __nv_bfloat162 q2 = __floats2bfloat162_rn(v[8 * cc + 4], v[8 * cc + 5]);
+                                __nv_bfloat162 q3 = __floats2bfloat162_rn(v[8 * cc + 6], v[8 * cc + 7]);
+                                uint4 pk;
+                                pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
+                                pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
+                                *reinterpret_cast<uint4 *>(st + cc * CHUNK_ROWS_BYTES + r * 16) = pk;
+                            }
+                        }
+                        tc::fence_proxy_async();
+                        tc::mbar_arrive(a_full + ra.slot);
+                    } else {
+                        tc::mbar_wait(a_empty + ra.slot, ra.phase ^ 1, 17);      // in-order walk
+                    }
+                    ra.advance();
+                }
+                for (int i = p.n_chunks[0]; i < chunks_per_tile; ++i) {
+                    tc::mbar_wait(a_empty + ra.slot, ra.phase ^ 1, 18);
+                    ra.advance();
+                }
+            } else if (!p.mode_b) {
                 // ---- mode A: one chunk per tile; thread = row -------------------------------------------
                 // Every loader walks EVERY chunk's "slot free" barrier in order, also for chunks other
                 // warps fill: a parity wait is only meaningful when the waiter is at most one phase
@@ -504,7 +593,7 @@ static FusedPlan fused_plan(int mode, bool mode_b, int n_layers, const int32_t *
     if (!mode_b && n_layers == 3 && ext > 256 && extent(true) <= 256) { pl.alias02 = 1; ext = extent(true); }
     else ext = extent(false);
     pl.ok = ext <= 512;
-    pl.occ = (!mode_b && ext <= 256) ? 2 : 1;
+    pl.occ = ext <= 256 ? 2 : 1;
     pl.kc = (pl.occ == 2 && mode == FZ_MODE_TF32X3) ? 16 : 32;
     pl.lg = pl.occ == 2 ? 1 : 2;
     pl.tmem_cols = 32;
@@ -535,7 +624,7 @@ static int launch_fused(const ev2h::FusedParams &p, size_t smem, unsigned grid, 
 
 extern "C" int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
-    const float *pts8, int D,
+    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int n_layers, const int32_t *cin_host, const int32_t *cout_host, const void *const *w_packed_host,
     const float *const *bias_host, float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream) {
@@ -547,12 +636,15 @@ extern "C" int ev2h_sa_msg_fused_tc(
     if (K != 32 && K != 64 && K != 128)
         return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: K=%d (supported: 32, 64, 128)", K);
     const bool mode_b = P != nullptr;
-    if (n_layers < 2 || n_layers > 3 || (mode_b && n_layers != 2) || (!mode_b && n_layers != 3))
-        return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: %d layers in %s mode", n_layers, mode_b ? "per-point" : "gather");
+    const bool ffma_first = !mode_b && first_wt != nullptr;
+    if (n_layers < 2 || n_layers > 3 || ((mode_b || ffma_first) && n_layers != 2) || (!mode_b && !ffma_first && n_layers != 3))
+        return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: %d tensor-core layers in %s mode", n_layers,
+                    mode_b ? "per-point" : (ffma_first ? "gather (layer 1 on CUDA cores)" : "gather"));
     if (!mode_b) {
         EV2H_REQUIRE(pts8 != nullptr, "ev2h_sa_msg_fused_tc: pts8 is null");
-        if (D + 3 > 8 || cin_host[0] != D + 3)
+        if (D + 3 > 8 || (!ffma_first && cin_host[0] != D + 3))
             return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: gather mode needs D+3 <= 8 input channels (D=%d)", D);
+        if (ffma_first) EV2H_REQUIRE(first_bias != nullptr && first_ld >= cin_host[0], "ev2h_sa_msg_fused_tc: first layer weights incomplete");
     } else {
         EV2H_REQUIRE(C != nullptr && ld_p % 4 == 0 && ld_c % 4 == 0 && p_col % 4 == 0 && c_col % 4 == 0,
                      "ev2h_sa_msg_fused_tc: per-point tables must be float4 addressable");
@@ -573,6 +665,7 @@ extern "C" int ev2h_sa_msg_fused_tc(
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
     p.mode_b = mode_b ? 1 : 0; p.pts8 = pts8; p.D = D; p.P = P; p.ld_p = ld_p; p.p_col = p_col; p.C = C; p.ld_c = ld_c; p.c_col = c_col;
     p.G = n_layers; p.alias02 = pl.alias02; p.tmem_cols = pl.tmem_cols;
+    p.ffma_first = ffma_first ? 1 : 0; p.first_wt = first_wt; p.first_ld = first_ld; p.first_bias = first_bias; p.c1 = cin_host[0];
     int boff = 0, max_n = 0;
     for (int g = 0; g < n_layers; ++g) {
         const int cin = cin_host[g];
@@ -592,7 +685,8 @@ extern "C" int ev2h_sa_msg_fused_tc(
 
     p.a_slot_bytes = PARTS * FZ_BLOCK_M * KC * EB;
     p.b_slot_bytes = PARTS * max_n * KC * EB;
-    const int tail = (4 * FZ_MAX_RING + 2 * FZ_MAX_GEMMS + 1) * 8 + 16 + (boff + 2 * 4 * p.n[n_layers - 1]) * 4;
+    const int tail = (4 * FZ_MAX_RING + 2 * FZ_MAX_GEMMS + 1) * 8 + 24 + (boff + 2 * 4 * p.n[n_layers - 1]) * 4 +
+                     (ffma_first ? p.n_chunks[0] * KC * 9 * 4 : 0);
     int occ = pl.occ;
     int budget = (occ == 2 ? 113 : 227) * 1024 - tail - 512;
     if (occ == 2 && budget < 2 * p.a_slot_bytes + 2 * p.b_slot_bytes) { occ = 1; budget = 227 * 1024 - tail - 512; }

@@ -44,6 +44,8 @@ _mlp_precision = os.environ.get("EV2H_MLP", "tf32x3")
 # The fused grouping + MLP + max-pool kernel (sa_fused_tc.cu) is used for every scale it
 # covers when a tensor-core precision is selected; EV2H_FUSED=0 forces the layer-by-layer path.
 _FUSED_ENABLED = os.environ.get("EV2H_FUSED", "1") != "0"
+# Evaluate layer 1 per point (instead of per gathered row) also for narrow inputs; experiment switch.
+_PER_POINT_ALWAYS = os.environ.get("EV2H_PER_POINT", "0") == "1"
 
 
 def set_fused(enabled: bool) -> None:
@@ -319,7 +321,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         widths = [[L["cout"] for L in layers] for layers in all_layers]
 
         # Which scales can run in the fused tensor-core kernel, and with which first-layer mode.
-        per_point = D + 3 > 8
+        per_point = D + 3 > 8 or _PER_POINT_ALWAYS
         fused = [mode is not None and _FUSED_ENABLED and _capi.fused_supported(K, w, D + 3, per_point, mode)
                  for K, w in zip(self.nsample_list, widths)]
 
@@ -364,7 +366,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         for i, K in enumerate(self.nsample_list):
             layers = all_layers[i]
             if fused[i]:
-                use = layers[1:] if per_point else layers
+                use = layers[1:]      # layer 1: per point (wide inputs) or in the loader warps (<= 8 channels)
                 kc = _capi.fused_kc(mode, per_point, [L["cout"] for L in use])
                 packed = []
                 for L in use:
@@ -375,7 +377,9 @@ class PointNetSetAbstractionMsg(nn.Module):
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
                                    C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
                                    [L["cin"] for L in use], [L["cout"] for L in use], packed, [L["bias"] for L in use],
-                                   out_rows, c_total, col, mode)
+                                   out_rows, c_total, col, mode,
+                                   first_wt=None if per_point else layers[0]["wt"],
+                                   first_bias=None if per_point else layers[0]["bias"])
             else:
                 if feats_rows is None and points is not None:
                     feats_rows = _to_rows(points)

@@ -410,3 +410,36 @@ def test_train_mode_forward_backward_matches_torch_autograd():
         assert rel_err(got[n], p.grad) <= 1e-4, n
     assert rel_err(got_in, feats2.grad) <= 1e-4
     assert rel_err(got_rm, ref.bn_blocks[0][0].running_mean) <= 1e-5
+
+
+# ------------------------------------------------------------------ long windows (config 5) ------
+def test_long_window_16k_fp32_vs_bf16_and_oracle_indices():
+    """BASELINE config 5 shape (16384-event windows, small batch here): indices bit-exact against the
+    C oracle, 3xTF32 features within 1e-5 of the exact-fp32 CUDA path, bf16 variant within 1e-2."""
+    B, N = 3, 16384
+    enc = _encoder_with((11, 12, 13))
+    ev_np = synth.make_windows(B, N, seed=555)
+    ev = dev(ev_np)
+    s1 = torch.from_numpy(synth.make_start_indices(B, N, 2))
+    s2 = torch.from_numpy(synth.make_start_indices(B, 512, 3))
+    outs = {}
+    old = e2h.get_mlp_precision()
+    try:
+        for prec in ("fp32", "tf32x3", "bf16"):
+            e2h.set_mlp_precision(prec)
+            with torch.no_grad():
+                outs[prec] = enc(ev, fps_starts=(s1, s2))
+            if prec == "fp32":
+                xyz = np.ascontiguousarray(ev_np[:, :3].transpose(0, 2, 1))
+                fidx = c_oracle.fps(xyz, 512, s1.numpy())
+                assert np.array_equal(enc.sa1.last_fps_idx.cpu().numpy(), fidx)
+                centres = np.stack([xyz[b, fidx[b]] for b in range(B)])
+                ball = enc.sa1.last_ball_idx.cpu().numpy()
+                off = 0
+                for r, k in zip([0.1, 0.2, 0.4], [32, 64, 128]):
+                    assert np.array_equal(ball[:, :, off:off + k], c_oracle.ball_query(r, k, xyz, centres)), r
+                    off += k
+    finally:
+        e2h.set_mlp_precision(old)
+    assert rel_err(outs["tf32x3"], outs["fp32"]) <= 1e-5
+    assert rel_err(outs["bf16"], outs["fp32"]) <= 1e-2

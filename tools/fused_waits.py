@@ -17,7 +17,7 @@ with torch.no_grad():
 torch.cuda.synchronize()
 # patch sa_msg_fused to capture per-launch counters
 orig = _capi.sa_msg_fused
-buf = torch.zeros(148, 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(512, 8, dtype=torch.int64, device=dev)
 def wrapped(*a, **k):
     buf.zero_(); _capi.lib().ev2h_fused_set_debug_buffer(buf.data_ptr())
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
