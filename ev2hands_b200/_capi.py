@@ -32,7 +32,7 @@ _SIGNATURES = {
     "ev2h_linear_relu_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_tc_pack_weights": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "ev2h_tc_pack_weights_kc": [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
-    "ev2h_sa_msg_fused_kc": [c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32)],
+    "ev2h_sa_msg_fused_kc": [c_int, ctypes.POINTER(ctypes.c_int32)],
     "ev2h_linear_relu_tc": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_tc_set_debug": [c_int],
     "ev2h_fused_set_debug_buffer": [c_vp],
@@ -40,8 +40,8 @@ _SIGNATURES = {
     "ev2h_sa_msg_fused_tc": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
                              c_vp, c_int, c_vp, c_int, c_vp,
                              c_vp, c_int, c_int, c_vp, c_int, c_int,
-                             c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
-                             ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_int, c_int, c_int, c_vp],
+                             c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                             c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_group_max_bwd_f32": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
 }
@@ -286,10 +286,10 @@ def tc_pack(wt: torch.Tensor, Cin: int, Cout: int, mode: int, kc: int = 32) -> t
     return packed
 
 
-def fused_kc(mode: int, per_point: bool, couts) -> int:
-    """K-chunk length the fused kernel wants for this stack (-1: unsupported)."""
-    arr = (ctypes.c_int32 * len(couts))(*couts)
-    return lib().ev2h_sa_msg_fused_kc(mode, 1 if per_point else 0, len(couts), arr)
+def fused_kc(mode: int, couts) -> int:
+    """K-chunk length the fused kernel wants for tensor-core layers of widths `couts` (-1: unsupported)."""
+    arr = (ctypes.c_int32 * 2)(*couts)
+    return lib().ev2h_sa_msg_fused_kc(mode, arr)
 
 
 def linear_relu_tc(x, M, ld_x, Cin, packed, bias, Cout, pool_rows, y, ld_y, y_col_off, mode):
@@ -307,31 +307,28 @@ def linear_no_relu(x, M, ld_x, Cin, wt, bias, Cout, y, ld_y, y_col_off=0):
 
 
 def fused_supported(K: int, widths, first_in: int, per_point: bool, mode: int = TC_TF32X3) -> bool:
-    """Shapes ev2h_sa_msg_fused_tc covers (see include/ev2h.h)."""
-    if K not in (32, 64, 128) or any(w > 256 for w in widths) or len(widths) != 3:
+    """Shapes ev2h_sa_msg_fused_tc covers (see include/ev2h.h): three layers, layer 1 either per point
+    (wide inputs, width a multiple of 32) or in the loader warps (<= 8 input channels)."""
+    if K not in (32, 64, 128) or len(widths) != 3 or any(w > 256 for w in widths):
         return False
-    if per_point:
-        if widths[0] % 32 != 0:
-            return False
-        return fused_kc(mode, True, widths[1:]) > 0
-    if first_in > 8:
+    if per_point and widths[0] % 32 != 0:
         return False
-    return fused_kc(mode, False, widths[1:]) > 0      # layer 1 runs in the loaders (exact fp32)
+    if not per_point and first_in > 8:
+        return False
+    return fused_kc(mode, widths[1:]) > 0
 
 
-def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, P, ld_p, p_col, C, ld_c, c_col,
-                 cins, couts, packed, biases, out_rows, ld_out, out_col, mode, first_wt=None, first_bias=None):
-    L = len(cins)
-    a_cin = (ctypes.c_int32 * L)(*cins)
-    a_cout = (ctypes.c_int32 * L)(*couts)
-    a_w = (c_vp * L)(*[t.data_ptr() for t in packed])
-    a_b = (c_vp * L)(*[t.data_ptr() for t in biases])
+def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, first_wt, first_bias, P, ld_p, p_col, C, ld_c, c_col,
+                 c1, couts, packed, biases, out_rows, ld_out, out_col, mode):
+    a_cout = (ctypes.c_int32 * 2)(*couts)
+    a_w = (c_vp * 2)(*[t.data_ptr() for t in packed])
+    a_b = (c_vp * 2)(*[t.data_ptr() for t in biases])
     with torch.cuda.device(out_rows.device):
         with _timed("ev2h_sa_msg_fused_tc"):
             _check(lib().ev2h_sa_msg_fused_tc(_p(idx), idx.shape[-1], k_off, _p(centres_rows), B, N, S, K,
                                               _p(pts8), D, _p(first_wt), 0 if first_wt is None else first_wt.shape[1],
                                               _p(first_bias), _p(P), ld_p, p_col, _p(C), ld_c, c_col,
-                                              L, a_cin, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode,
+                                              c1, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode,
                                               _stream(out_rows)), "ev2h_sa_msg_fused_tc")
 
 

@@ -367,19 +367,18 @@ class PointNetSetAbstractionMsg(nn.Module):
             layers = all_layers[i]
             if fused[i]:
                 use = layers[1:]      # layer 1: per point (wide inputs) or in the loader warps (<= 8 channels)
-                kc = _capi.fused_kc(mode, per_point, [L["cout"] for L in use])
+                kc = _capi.fused_kc(mode, [L["cout"] for L in use])
                 packed = []
                 for L in use:
                     if (mode, kc) not in L["packed"]:
                         L["packed"][(mode, kc)] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], mode, kc)
                     packed.append(L["packed"][(mode, kc)])
                 _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D,
+                                   None if per_point else layers[0]["wt"], None if per_point else layers[0]["bias"],
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
                                    C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
-                                   [L["cin"] for L in use], [L["cout"] for L in use], packed, [L["bias"] for L in use],
-                                   out_rows, c_total, col, mode,
-                                   first_wt=None if per_point else layers[0]["wt"],
-                                   first_bias=None if per_point else layers[0]["bias"])
+                                   layers[0]["cout"], [L["cout"] for L in use], packed, [L["bias"] for L in use],
+                                   out_rows, c_total, col, mode)
             else:
                 if feats_rows is None and points is not None:
                     feats_rows = _to_rows(points)

@@ -188,36 +188,34 @@ EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, c
                                  int y_col_off, int mode, ev2h_stream_t stream);
 /* ---- fused grouping + shared MLP + max-pool for ONE radius scale (tensor cores) ------------
  * Replaces the body of the per-radius loop of PointNetSetAbstractionMsg.forward
- * (pointnet2_utils.py:243-257): gather of the K neighbours of every centre, the
- * Conv2d(1x1)+BatchNorm2d(eval)+ReLU stack and the max over K, without materialising the
+ * (pointnet2_utils.py:243-257): gather of the K neighbours of every centre, the three
+ * Conv2d(1x1)+BatchNorm2d(eval)+ReLU layers and the max over K, without materialising the
  * grouped tensor or any intermediate activation in HBM.
  *   idx [B,S,idx_ld] int32 from ev2h_ball_query_f32, this scale's K slots start at k_off;
  *   centres_rows [B,S,3];  K in {32, 64, 128};  every layer width <= 256.
- * First-layer input, one of:
- *   gather mode   (P == NULL): pts8 [B,N,8] rows = [features(D) | xyz | 0], D + 3 <= 8; rows are
- *                 [features | xyz - centre] as in the reference.  With first_wt == NULL all three
- *                 layers run on the tensor cores (n_layers == 3).  With first_wt / first_bias (the
- *                 folded layer-1 map from ev2h_fold_conv_bn_f32, ld = first_ld) the loader warps
- *                 evaluate layer 1 in exact fp32 on the CUDA cores while gathering, and
- *                 cin/cout/w_packed/bias describe only the two remaining layers (n_layers == 2).
- *   per-point mode (P != NULL, n_layers == 2): layer 1 was evaluated per point / per centre:
- *                 P [B*N, ld_p] = W1' [features; xyz] + b1' (ev2h_linear_f32) at column p_col,
- *                 C [B*S, ld_c] = W1'_xyz centre at column c_col; the kernel forms
- *                 relu(P[point] - C[centre]) and runs the remaining two layers.
- * cin/cout_host[l]: layer widths; w_packed_host[l]: ev2h_tc_pack_weights images; bias_host[l]:
- * folded biases (device pointers in host arrays).  out_rows [B*S, ld_out]: the pooled features
- * of this scale are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3. */
+ * Layer 1 (width c1), one of:
+ *   gather mode    (P == NULL): pts8 [B,N,8] rows = [features(D) | xyz | 0], D + 3 <= 8; the kernel
+ *                  forms [features | xyz - centre] as the reference does and evaluates layer 1 in
+ *                  exact fp32 on the CUDA cores from first_wt / first_bias (the folded map written
+ *                  by ev2h_fold_conv_bn_f32, row length first_ld).
+ *   per-point mode (P != NULL): layer 1 was evaluated per point / per centre:
+ *                  P [B*N, ld_p] = W1' [features; xyz] + b1' (ev2h_linear_f32) at column p_col,
+ *                  C [B*S, ld_c] = W1'_xyz centre at column c_col; the kernel forms
+ *                  relu(P[point] - C[centre]); c1 must be a multiple of 32.
+ * Layers 2 and 3 run on the tensor cores: cout_host[2] their widths, w_packed_host[2] their
+ * ev2h_tc_pack_weights_kc images (kc from ev2h_sa_msg_fused_kc), bias_host[2] their folded biases
+ * (device pointers in host arrays).  out_rows [B*S, ld_out]: the pooled features of this scale
+ * are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3. */
 EV2H_API int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
     const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
-    int n_layers, const int32_t *cin_host, const int32_t *cout_host, const void *const *w_packed_host,
-    const float *const *bias_host, float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream);
+    int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
+    float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream);
 
-/* K-chunk length (16 or 32) the fused kernel uses for this stack, i.e. the kc to pack its
- * weights with; -1 if the stack is not supported.  cout_host = widths of the layers the kernel
- * runs (3 in gather mode, the last 2 in per-point mode). */
-EV2H_API int ev2h_sa_msg_fused_kc(int mode, int per_point, int n_layers, const int32_t *cout_host);
+/* K-chunk length (16 or 32) the fused kernel uses for layers of widths cout_host[2], i.e. the kc
+ * to pack their weights with; -1 if the pair is not supported. */
+EV2H_API int ev2h_sa_msg_fused_kc(int mode, const int32_t *cout_host);
 
 /* Debug/profiling only: device buffer [512][8] int64 (one row per CTA) receiving the UMMA issuer's wait-cycle counters
  * of the next fused launches (NULL turns it off). */

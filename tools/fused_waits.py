@@ -27,7 +27,7 @@ def wrapped(*a, **k):
     act = d[d[:, 5] > 0]
     m = act.mean(0)
     print("%s K=%d widths=%s: %.3f ms | issuer cycles/CTA total=%.0f tiles=%.1f | wait a_full g0=%.1f%% g1=%.1f%% g2=%.1f%% b_full=%.1f%% acc_empty=%.1f%% | commit=%.1f%% issue+other=%.1f%% | cycles/tile=%.0f" % (
-        prec, a[6], a[16], t0.elapsed_time(t1), m[5], m[6], 100*m[0]/m[5], 100*m[1]/m[5], 100*m[2]/m[5], 100*m[3]/m[5], 100*m[4]/m[5],
+        prec, a[6], a[18], t0.elapsed_time(t1), m[5], m[6], 100*m[0]/m[5], 100*m[1]/m[5], 100*m[2]/m[5], 100*m[3]/m[5], 100*m[4]/m[5],
         100*m[7]/m[5], 100*(m[5]-m[:5].sum()-m[7])/m[5], m[5]/max(m[6],1)), flush=True)
 _capi.sa_msg_fused = wrapped
 import ev2hands_b200.pointnet2_utils as pu
