@@ -420,7 +420,7 @@ sa_fused_tc_kernel(const FusedParams p) {
             }
         }
         if (prof && lane == 0) {
-            long long *d = p.dbg + (size_t)blockIdx.x * 8;
+            long long *d = p.dbg + (size_t)blockIdx.x * 16;
             d[0] = w_a[0]; d[1] = w_a[1]; d[2] = 0; d[3] = w_b; d[4] = w_acc; d[5] = clock64() - t_begin; d[6] = it; d[7] = w_commit;
         }
     } else {
@@ -430,13 +430,18 @@ sa_fused_tc_kernel(const FusedParams p) {
         uint64_t *my_grants = a_grant + LG * FZ_MAX_RING;
         uint32_t bits = 0;
         uint32_t it = 0;
+        const bool eprof = p.dbg != nullptr && tid == 0;
+        long long e_full0 = 0, e_conv = 0, e_slot = 0, e_full1 = 0, e_pool = 0, e_t = 0, e_t2 = 0;
+        const long long e_begin = eprof ? clock64() : 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int64_t m0 = tile * FZ_BLOCK_M;
             {
                 // ---- layer 2 activations -> operand chunks of layer 3 ----
                 const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[0] + ((uint32_t)(q * 32) << 16);
                 const float *bias_g = bias_s + p.bias_off[0];
+                if (eprof) e_t = clock64();
                 tc::mbar_wait(acc_full + 0, it & 1, 60);
+                if (eprof) { e_t2 = clock64(); e_full0 += e_t2 - e_t; e_t = e_t2; }
                 tc::tc_fence_after();
                 for (int c = 0; c < nc1; ++c) {
                     uint32_t raw[KC];
@@ -449,19 +454,23 @@ sa_fused_tc_kernel(const FusedParams p) {
                         const int col = c * KC + j;
                         v[j] = col < p.n[0] ? fmaxf(__uint_as_float(raw[j]) + bias_g[col], 0.f) : 0.f;
                     }
+                    if (eprof) e_t2 = clock64();
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)(nc0 + c), p.sa, bits, 70);
+                    if (eprof) e_slot += clock64() - e_t2;
                     store_row_chunk(a_ring + (size_t)slot * p.a_slot_bytes, r, v);
                     tc::fence_proxy_async();
                     tc::mbar_arrive(a_full + slot);
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 0);
+                if (eprof) { e_t2 = clock64(); e_conv += e_t2 - e_t; e_t = e_t2; }
             }
             {
                 // ---- layer 3: bias + ReLU + max over the K rows of each group ----
                 const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + ((uint32_t)(q * 32) << 16);
                 const float *bias_g = bias_s + p.bias_off[1];
                 tc::mbar_wait(acc_full + 1, it & 1, 61);
+                if (eprof) { e_t2 = clock64(); e_full1 += e_t2 - e_t; e_t = e_t2; }
                 tc::tc_fence_after();
                 const int n_last = p.n[1];
                 const bool row_ok = (m0 + r) < M;
@@ -470,20 +479,30 @@ sa_fused_tc_kernel(const FusedParams p) {
                     uint32_t raw[32];
                     tc::tmem_ld32(t_addr + c0, raw);
                     tc::tmem_ld_wait();
-                    float mine_v = 0.f;
+                    // max over the 32 rows (lanes) of this warp for 32 columns at once: butterfly
+                    // transpose-reduce, 31 shuffles; column c0 + L ends up in lane L.  Bias and ReLU
+                    // commute with the max (both monotone), so they are applied once per column after it.
+                    float w[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = c0 + j;
-                        const float v = col < n_last ? fmaxf(__uint_as_float(raw[j]) + bias_g[col], 0.f) : 0.f;
-                        const unsigned m = __reduce_max_sync(0xffffffffu, row_ok ? __float_as_uint(v) : 0u);
-                        if (lane == j) mine_v = __uint_as_float(m);
+                    for (int j = 0; j < 32; ++j) w[j] = row_ok ? __uint_as_float(raw[j]) : -INFINITY;
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        const bool up = (lane & s) != 0;
+#pragma unroll
+                        for (int i = 0; i < s; ++i) {
+                            const float keep = up ? w[i + s] : w[i];
+                            const float send = up ? w[i] : w[i + s];
+                            w[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s));
+                        }
                     }
+                    const int col = c0 + lane;
+                    const float mine_v = col < n_last ? fmaxf(w[0] + bias_g[col], 0.f) : 0.f;
                     if (K == 32) {
                         const int64_t row0 = m0 + q * 32;
-                        if (row0 < M && c0 + lane < p.c_out)
-                            p.out[(row0 / 32) * (int64_t)p.ld_out + p.out_col + c0 + lane] = mine_v;
-                    } else if (c0 + lane < n_last) {
-                        red_w[c0 + lane] = mine_v;
+                        if (row0 < M && col < p.c_out)
+                            p.out[(row0 / 32) * (int64_t)p.ld_out + p.out_col + col] = mine_v;
+                    } else if (col < n_last) {
+                        red_w[col] = mine_v;
                     }
                 }
                 tc::tc_fence_before();
@@ -506,7 +525,12 @@ sa_fused_tc_kernel(const FusedParams p) {
                                     fmaxf(fmaxf(rr[c], rr[n_last + c]), fmaxf(rr[2 * n_last + c], rr[3 * n_last + c]));
                     }
                 }
+                if (eprof) e_pool += clock64() - e_t;
             }
+        }
+        if (eprof) {
+            long long *d = p.dbg + (size_t)blockIdx.x * 16 + 8;
+            d[0] = e_full0; d[1] = e_conv; d[2] = e_slot; d[3] = e_full1; d[4] = e_pool; d[5] = clock64() - e_begin;
         }
     }
 

@@ -51,12 +51,27 @@ static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
     }
     __trap();
 }
+// Probe with a suspend-time hint: the warp sleeps inside the instruction (no issue slots used) and is
+// woken by the barrier's phase change, so a long hint costs no latency.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = 0) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(tag, parity);   // ~2 s
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if ((++spins & 15u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(tag, parity);   // ~2 s
     }
 }
 

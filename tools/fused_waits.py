@@ -17,7 +17,7 @@ with torch.no_grad():
 torch.cuda.synchronize()
 # patch sa_msg_fused to capture per-launch counters
 orig = _capi.sa_msg_fused
-buf = torch.zeros(512, 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(512, 16, dtype=torch.int64, device=dev)
 def wrapped(*a, **k):
     buf.zero_(); _capi.lib().ev2h_fused_set_debug_buffer(buf.data_ptr())
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -29,6 +29,9 @@ def wrapped(*a, **k):
     print("%s K=%d widths=%s: %.3f ms | issuer cycles/CTA total=%.0f tiles=%.1f | wait a_full g0=%.1f%% g1=%.1f%% g2=%.1f%% b_full=%.1f%% acc_empty=%.1f%% | commit=%.1f%% issue+other=%.1f%% | cycles/tile=%.0f" % (
         prec, a[6], a[18], t0.elapsed_time(t1), m[5], m[6], 100*m[0]/m[5], 100*m[1]/m[5], 100*m[2]/m[5], 100*m[3]/m[5], 100*m[4]/m[5],
         100*m[7]/m[5], 100*(m[5]-m[:5].sum()-m[7])/m[5], m[5]/max(m[6],1)), flush=True)
+    t = max(m[6], 1)
+    print("      epilogue warp 0, cycles/tile: wait acc_full[0]=%.0f  convert(incl slot wait)=%.0f  slot wait=%.0f  wait acc_full[1]=%.0f  pool=%.0f  total=%.0f" % (
+        m[8]/t, m[9]/t, m[10]/t, m[11]/t, m[12]/t, m[13]/t), flush=True)
 _capi.sa_msg_fused = wrapped
 import ev2hands_b200.pointnet2_utils as pu
 with torch.no_grad():
