@@ -31,7 +31,7 @@ _SIGNATURES = {
     "ev2h_fold_conv_bn_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_linear_relu_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_tc_pack_weights": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
-    "ev2h_tc_pack_weights_kc": [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_tc_pack_weights_kc": [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "ev2h_sa_msg_fused_kc": [c_int, ctypes.POINTER(ctypes.c_int32)],
     "ev2h_linear_relu_tc": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_tc_set_debug": [c_int],
@@ -67,7 +67,7 @@ def lib() -> ctypes.CDLL:
         L.ev2h_last_error.restype = ctypes.c_char_p
         L.ev2h_tc_packed_bytes.argtypes = [c_int, c_int, c_int]
         L.ev2h_tc_packed_bytes.restype = c_i64
-        L.ev2h_tc_packed_bytes_kc.argtypes = [c_int, c_int, c_int, c_int]
+        L.ev2h_tc_packed_bytes_kc.argtypes = [c_int, c_int, c_int, c_int, c_int]
         L.ev2h_tc_packed_bytes_kc.restype = c_i64
         for name, args in _SIGNATURES.items():
             fn = getattr(L, name)
@@ -272,16 +272,16 @@ def tc_supported(Cout: int, pool_rows: int) -> bool:
     return (Cout <= 256 or Cout % 256 == 0) and (pool_rows in (0, 32, 64) or pool_rows % 128 == 0)
 
 
-def tc_pack(wt: torch.Tensor, Cin: int, Cout: int, mode: int, kc: int = 32) -> torch.Tensor:
+def tc_pack(wt: torch.Tensor, Cin: int, Cout: int, mode: int, kc: int = 32, row_align: int = 16) -> torch.Tensor:
     """folded wt [Cin_pad, Cout_pad] -> packed shared-memory images (uint8 buffer) for `mode`,
-    `kc` input channels per image."""
-    n = lib().ev2h_tc_packed_bytes_kc(Cin, Cout, mode, kc)
+    `kc` input channels per image, image rows padded to a multiple of `row_align`."""
+    n = lib().ev2h_tc_packed_bytes_kc(Cin, Cout, mode, kc, row_align)
     if n <= 0:
-        raise RuntimeError("ev2h_tc_packed_bytes_kc(%d, %d, %d, %d) failed" % (Cin, Cout, mode, kc))
+        raise RuntimeError("ev2h_tc_packed_bytes_kc(%d, %d, %d, %d, %d) failed" % (Cin, Cout, mode, kc, row_align))
     packed = torch.empty((n,), dtype=torch.uint8, device=wt.device)
     with torch.cuda.device(wt.device):
         with _timed("ev2h_tc_pack_weights"):
-            _check(lib().ev2h_tc_pack_weights_kc(_p(wt), wt.shape[1], Cin, Cout, mode, kc, _p(packed), _stream(wt)),
+            _check(lib().ev2h_tc_pack_weights_kc(_p(wt), wt.shape[1], Cin, Cout, mode, kc, row_align, _p(packed), _stream(wt)),
                    "ev2h_tc_pack_weights_kc")
     return packed
 

@@ -361,29 +361,36 @@ static bool tc_pool_supported(int K) { return K == 0 || K == 32 || K == 64 || (K
 
 extern "C" int ev2h_tc_set_debug(int flags) { ev2h::g_tc_debug = flags; return 0; }
 
-extern "C" int64_t ev2h_tc_packed_bytes_kc(int Cin, int Cout, int mode, int kc) {
-    using namespace ev2h;
-    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3) || (kc != 16 && kc != 32)) return -1;
-    const int n_blk = tc_n_blk(Cout);
-    return (int64_t)tc_n_blocks(Cout) * ((Cin + kc - 1) / kc) * tc_parts(mode) * n_blk * kc * tc_elem_bytes(mode);
+static int tc_n_blk_aligned(int Cout, int row_align) {
+    const int n = ev2h::round_up(Cout, row_align);
+    return n >= ev2h::TC_MAX_N ? ev2h::TC_MAX_N : n;
 }
-extern "C" int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode) { return ev2h_tc_packed_bytes_kc(Cin, Cout, mode, ev2h::TC_KC); }
 
-extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cout, int mode, int kc, void *packed,
-                                       ev2h_stream_t stream);
+extern "C" int64_t ev2h_tc_packed_bytes_kc(int Cin, int Cout, int mode, int kc, int row_align) {
+    using namespace ev2h;
+    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3) || (kc != 16 && kc != 32) ||
+        (row_align != 16 && row_align != 128)) return -1;
+    const int n_blk = tc_n_blk_aligned(Cout, row_align);
+    return (int64_t)((Cout + n_blk - 1) / n_blk) * ((Cin + kc - 1) / kc) * tc_parts(mode) * n_blk * kc * tc_elem_bytes(mode);
+}
+extern "C" int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode) { return ev2h_tc_packed_bytes_kc(Cin, Cout, mode, ev2h::TC_KC, 16); }
+
+extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cout, int mode, int kc, int row_align,
+                                       void *packed, ev2h_stream_t stream);
 extern "C" int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
                                     ev2h_stream_t stream) {
-    return ev2h_tc_pack_weights_kc(wt, ld_w, Cin, Cout, mode, ev2h::TC_KC, packed, stream);
+    return ev2h_tc_pack_weights_kc(wt, ld_w, Cin, Cout, mode, ev2h::TC_KC, 16, packed, stream);
 }
 
-extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cout, int mode, int kc, void *packed,
-                                       ev2h_stream_t stream) {
+extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cout, int mode, int kc, int row_align,
+                                       void *packed, ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(kc == 16 || kc == 32, "ev2h_tc_pack_weights: K chunk must be 16 or 32");
+    EV2H_REQUIRE(row_align == 16 || row_align == 128, "ev2h_tc_pack_weights: row_align must be 16 or 128");
     EV2H_REQUIRE(wt && packed, "ev2h_tc_pack_weights: null argument");
     EV2H_REQUIRE(Cin > 0 && Cout > 0 && ld_w >= Cout, "ev2h_tc_pack_weights: bad sizes");
     EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3, "ev2h_tc_pack_weights: unknown mode %d", mode);
-    const int n_blk = tc_n_blk(Cout), n_blocks = tc_n_blocks(Cout), n_kc = (Cin + kc - 1) / kc;
+    const int n_blk = tc_n_blk_aligned(Cout, row_align), n_blocks = (Cout + n_blk - 1) / n_blk, n_kc = (Cin + kc - 1) / kc;
     const int64_t total = (int64_t)n_blocks * n_kc * n_blk * kc;
     const unsigned grid = (unsigned)((total + 255) / 256);
     // wt comes from ev2h_fold_conv_bn_f32: round_up(Cin,16) rows of ld_w columns, zero padded

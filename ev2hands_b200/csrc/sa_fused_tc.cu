@@ -17,6 +17,13 @@
 // and are consumed in order by ONE elected thread issuing tcgen05.mma, which signals completion
 // through tcgen05.commit -> mbarrier.
 //
+// Layer 2 is computed as rows x channels (operand A = activation rows, B = weights): its epilogue
+// thread owns a ROW and writes that row's 16-byte operand pieces for layer 3, conflict free.
+// Layer 3 is computed TRANSPOSED, channels x rows (A = weights, one 128-channel block per UMMA,
+// B = the same activation chunk): its accumulator has an output channel per TMEM lane and the
+// tile's rows along the columns, so the max over the K neighbours of a group is a per-thread max
+// over columns - no shuffles, no shared memory - and the pooled features leave coalesced.
+//
 // Layer 1 never runs as a per-row GEMM:
 //   gather mode     (<= 8 input channels: sa1, regressor): the loader gathers the 32-byte point
 //                   record [features | xyz], subtracts the centre and evaluates layer 1 in exact
@@ -67,6 +74,7 @@ struct FusedParams {
     int bias_off[FZ_GEMMS];
     const uint8_t *w[FZ_GEMMS];                  // packed weight images (ev2h_tc_pack_weights_kc)
     const float *bias[FZ_GEMMS];
+    int mb3;                                     // 128-channel blocks of layer 3 (1 or 2)
     int tmem_cols;                               // TMEM columns to allocate (power of two)
     // output: pooled features of this scale, rows = centres
     float *out; int ld_out, out_col, c_out;
@@ -122,8 +130,7 @@ sa_fused_tc_kernel(const FusedParams p) {
     uint64_t *acc_empty = acc_full + FZ_GEMMS;           // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + FZ_GEMMS);
     float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);          // [n0 + n1]; tail offset 432, 16-byte aligned
-    float *red = bias_s + p.n[0] + p.n[1];                             // [2][4][n1]
-    float *w1s = red + 2 * 4 * p.n[1];                                 // [c1_pad][8] layer-1 weights (gather mode)
+    float *w1s = bias_s + p.n[0] + p.n[1];                             // [c1_pad][8] layer-1 weights (gather mode)
     float *b1s = w1s + (p.per_point ? 0 : p.n_chunks[0] * KC * 8);     // [c1_pad]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -342,7 +349,8 @@ sa_fused_tc_kernel(const FusedParams p) {
             Ring rb{0, 0, p.sb};
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int g = 0; g < FZ_GEMMS; ++g) {
-                    const uint32_t bytes = (uint32_t)(PARTS * p.n[g] * KC * EB);
+                    const uint32_t w_rows = g == 0 ? (uint32_t)p.n[0] : 128u * (uint32_t)p.mb3;
+                    const uint32_t bytes = (uint32_t)PARTS * w_rows * KC * EB;
                     for (int c = 0; c < p.n_chunks[g]; ++c) {
                         tc::mbar_wait(b_empty + rb.slot, rb.phase ^ 1, 20);     // sole producer of this ring: always in step
                         tc::mbar_arrive_expect_tx(b_full + rb.slot, bytes);
@@ -369,9 +377,13 @@ sa_fused_tc_kernel(const FusedParams p) {
         const uint32_t a_ring_addr = tc::smem_u32(a_ring), b_ring_addr = tc::smem_u32(b_ring);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             for (int g = 0; g < FZ_GEMMS; ++g) {
-                const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M, (uint32_t)p.n[g]);
-                const uint32_t b_lbo = (uint32_t)p.n[g] * 16;
-                const uint32_t b_part = (uint32_t)(p.n[g] * KC * EB);
+                // g == 0: D[rows x n0]      = X[rows x K] * W2[n0 x K]^T      (A = activations, B = weights)
+                // g == 1: D[chan x rows]^T: per 128-channel block  D = W3[128 x K] * X[rows x K]^T  (A = weights, B = activations)
+                const uint32_t w_rows = g == 0 ? (uint32_t)p.n[0] : 128u * (uint32_t)p.mb3;
+                const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M,
+                                                      g == 0 ? (uint32_t)p.n[0] : (uint32_t)FZ_BLOCK_M);
+                const uint32_t b_lbo = w_rows * 16;
+                const uint32_t b_part = w_rows * KC * EB;
                 const uint32_t d_tmem = tmem_base + (uint32_t)p.tmem_col[g];
                 const int n_chunks = p.n_chunks[g];
                 if (prof) t0 = clock64();
@@ -398,12 +410,26 @@ sa_fused_tc_kernel(const FusedParams p) {
 #pragma unroll 1
                         for (int j = 0; j < ks; ++j) {
                             const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
-                            if (MODE == FZ_MODE_TF32X3) {
-                                tc::umma_tf32(d_tmem, tc::make_desc(a_hi + a_lo_off, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
-                                tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi + b_lo_off, desc_hi), idesc, 1u);
-                                tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, 1u);
+                            if (g == 0) {
+                                if (MODE == FZ_MODE_TF32X3) {
+                                    tc::umma_tf32(d_tmem, tc::make_desc(a_hi + a_lo_off, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
+                                    tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi + b_lo_off, desc_hi), idesc, 1u);
+                                    tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, 1u);
+                                } else {
+                                    tc::umma_f16(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
+                                }
                             } else {
-                                tc::umma_f16(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
+                                for (int mb = 0; mb < p.mb3; ++mb) {
+                                    const uint32_t w = b_hi + (uint32_t)mb * ((128u * 16u) >> 4);   // 128 weight rows further
+                                    const uint32_t d = d_tmem + (uint32_t)mb * FZ_BLOCK_M;
+                                    if (MODE == FZ_MODE_TF32X3) {
+                                        tc::umma_tf32(d, tc::make_desc(w + b_lo_off, desc_hi), tc::make_desc(a_hi, desc_hi), idesc, acc);
+                                        tc::umma_tf32(d, tc::make_desc(w, desc_hi), tc::make_desc(a_hi + a_lo_off, desc_hi), idesc, 1u);
+                                        tc::umma_tf32(d, tc::make_desc(w, desc_hi), tc::make_desc(a_hi, desc_hi), idesc, 1u);
+                                    } else {
+                                        tc::umma_f16(d, tc::make_desc(w, desc_hi), tc::make_desc(a_hi, desc_hi), idesc, acc);
+                                    }
+                                }
                             }
                             a_hi += a_step; b_hi += b_step;
                         }
@@ -466,65 +492,37 @@ sa_fused_tc_kernel(const FusedParams p) {
                 if (eprof) { e_t2 = clock64(); e_conv += e_t2 - e_t; e_t = e_t2; }
             }
             {
-                // ---- layer 3: bias + ReLU + max over the K rows of each group ----
-                const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + ((uint32_t)(q * 32) << 16);
-                const float *bias_g = bias_s + p.bias_off[1];
+                // ---- layer 3 (transposed accumulator): lane = output channel, columns = the tile's rows.
+                // max over the K rows of a group = per-thread max over K columns; bias and ReLU commute
+                // with the max (both monotone) and are applied once per pooled value.
                 tc::mbar_wait(acc_full + 1, it & 1, 61);
                 if (eprof) { e_t2 = clock64(); e_full1 += e_t2 - e_t; e_t = e_t2; }
                 tc::tc_fence_after();
-                const int n_last = p.n[1];
-                const bool row_ok = (m0 + r) < M;
-                float *red_w = red + ((size_t)(it & 1) * 4 + q) * n_last;
-                for (int c0 = 0; c0 < n_last; c0 += 32) {
-                    uint32_t raw[32];
-                    tc::tmem_ld32(t_addr + c0, raw);
-                    tc::tmem_ld_wait();
-                    // max over the 32 rows (lanes) of this warp for 32 columns at once: butterfly
-                    // transpose-reduce, 31 shuffles; column c0 + L ends up in lane L.  Bias and ReLU
-                    // commute with the max (both monotone), so they are applied once per column after it.
-                    float w[32];
+                const int64_t rows_left = M - m0;                       // rows >= M do not exist (last tile)
+                for (int mb = 0; mb < p.mb3; ++mb) {
+                    const int ch = mb * 128 + q * 32 + lane;
+                    const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + (uint32_t)(mb * FZ_BLOCK_M) + ((uint32_t)(q * 32) << 16);
+                    const float b = ch < p.n[1] ? bias_s[p.bias_off[1] + ch] : 0.f;
+                    float gmax = -INFINITY;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < FZ_BLOCK_M; c0 += 32) {
+                        uint32_t raw[32];
+                        tc::tmem_ld32(t_addr + c0, raw);
+                        tc::tmem_ld_wait();
+                        float m = -INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) w[j] = row_ok ? __uint_as_float(raw[j]) : -INFINITY;
-#pragma unroll
-                    for (int s = 16; s >= 1; s >>= 1) {
-                        const bool up = (lane & s) != 0;
-#pragma unroll
-                        for (int i = 0; i < s; ++i) {
-                            const float keep = up ? w[i + s] : w[i];
-                            const float send = up ? w[i] : w[i + s];
-                            w[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s));
+                        for (int j = 0; j < 32; ++j) m = fmaxf(m, (c0 + j) < rows_left ? __uint_as_float(raw[j]) : -INFINITY);
+                        gmax = fmaxf(gmax, m);
+                        if (((c0 + 32) % K) == 0) {                      // a group of K rows is complete (K in {32, 64, 128})
+                            const int64_t row0 = m0 + c0 + 32 - K;
+                            if (row0 < M && ch < p.c_out)
+                                p.out[(row0 / K) * (int64_t)p.ld_out + p.out_col + ch] = fmaxf(gmax + b, 0.f);
+                            gmax = -INFINITY;
                         }
-                    }
-                    const int col = c0 + lane;
-                    const float mine_v = col < n_last ? fmaxf(w[0] + bias_g[col], 0.f) : 0.f;
-                    if (K == 32) {
-                        const int64_t row0 = m0 + q * 32;
-                        if (row0 < M && col < p.c_out)
-                            p.out[(row0 / 32) * (int64_t)p.ld_out + p.out_col + col] = mine_v;
-                    } else if (col < n_last) {
-                        red_w[col] = mine_v;
                     }
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 1);
-                if (K > 32) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const float *rr = red + (size_t)(it & 1) * 4 * n_last;
-                    if (K == 64) {
-                        for (int i = tid; i < 2 * n_last; i += 128) {
-                            const int gg = i / n_last, c = i % n_last;
-                            const int64_t row0 = m0 + gg * 64;
-                            if (row0 < M && c < p.c_out)
-                                p.out[(row0 / 64) * (int64_t)p.ld_out + p.out_col + c] =
-                                    fmaxf(rr[(2 * gg) * n_last + c], rr[(2 * gg + 1) * n_last + c]);
-                        }
-                    } else {   // K == 128
-                        for (int c = tid; c < n_last; c += 128)
-                            if (c < p.c_out && m0 < M)
-                                p.out[(m0 / 128) * (int64_t)p.ld_out + p.out_col + c] =
-                                    fmaxf(fmaxf(rr[c], rr[n_last + c]), fmaxf(rr[2 * n_last + c], rr[3 * n_last + c]));
-                    }
-                }
                 if (eprof) e_pool += clock64() - e_t;
             }
         }
@@ -546,19 +544,17 @@ static long long *g_fused_dbg = nullptr;
 
 // Which kernel instance serves a layer pair: two CTAs per SM (KC 16 for tf32, one loader group) whenever
 // one tile's accumulators fit 256 TMEM columns, so one CTA's epilogues overlap the other's UMMAs.
-struct FusedPlan { int kc, occ, tmem_cols, col[FZ_GEMMS], n[FZ_GEMMS]; bool ok; };
+struct FusedPlan { int kc, occ, tmem_cols, mb3, col[FZ_GEMMS], n[FZ_GEMMS]; bool ok; };
 
 static FusedPlan fused_plan(int mode, const int32_t *cout) {
     FusedPlan pl;
     memset(&pl, 0, sizeof(pl));
-    int c = 0, ext = 0;
-    for (int g = 0; g < FZ_GEMMS; ++g) {
-        pl.n[g] = round_up(cout[g], 16);
-        pl.col[g] = c;
-        c += pl.n[g];
-        const int e = pl.col[g] + round_up(pl.n[g], 32);      // TMEM loads read whole 16/32-column chunks
-        if (e > ext) ext = e;
-    }
+    pl.n[0] = round_up(cout[0], 16);
+    pl.n[1] = round_up(cout[1], 16);
+    pl.mb3 = (cout[1] + 127) / 128;
+    pl.col[0] = 0;
+    pl.col[1] = round_up(pl.n[0], 32);                        // layer-2 accumulator is read in 16/32-column chunks
+    const int ext = pl.col[1] + 128 * pl.mb3;                 // layer 3: one 128-column (= 128 rows) block per 128 channels
     pl.ok = cout[0] <= 256 && cout[1] <= 256 && ext <= 512;
     pl.occ = ext <= 256 ? 2 : 1;
     pl.kc = (pl.occ == 2 && mode == FZ_MODE_TF32X3) ? 16 : 32;
@@ -619,7 +615,7 @@ extern "C" int ev2h_sa_msg_fused_tc(
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
     p.per_point = per_point ? 1 : 0; p.pts8 = pts8; p.D = D; p.first_wt = first_wt; p.first_ld = first_ld; p.first_bias = first_bias;
     p.P = P; p.ld_p = ld_p; p.p_col = p_col; p.C = C; p.ld_c = ld_c; p.c_col = c_col; p.c1 = c1;
-    p.tmem_cols = pl.tmem_cols;
+    p.tmem_cols = pl.tmem_cols; p.mb3 = pl.mb3;
     int boff = 0, max_n = 0;
     for (int g = 0; g < FZ_GEMMS; ++g) {
         const int cin = g == 0 ? c1 : cout_host[0];
@@ -631,7 +627,8 @@ extern "C" int ev2h_sa_msg_fused_tc(
         p.bias_off[g] = boff; boff += p.n[g];
         p.w[g] = (const uint8_t *)w_packed_host[g]; p.bias[g] = bias_host[g];
         EV2H_REQUIRE(p.w[g] && p.bias[g] && ((uintptr_t)p.w[g] & 15) == 0, "ev2h_sa_msg_fused_tc: layer %d weights null or misaligned", g + 2);
-        if (p.n[g] > max_n) max_n = p.n[g];
+        const int w_rows = g == 0 ? p.n[0] : 128 * pl.mb3;
+        if (w_rows > max_n) max_n = w_rows;
     }
     p.out = out_rows; p.ld_out = ld_out; p.out_col = out_col; p.c_out = cout_host[1];
     EV2H_REQUIRE(ld_out >= out_col + p.c_out, "ev2h_sa_msg_fused_tc: ld_out too small");
@@ -639,7 +636,7 @@ extern "C" int ev2h_sa_msg_fused_tc(
 
     p.a_slot_bytes = PARTS * FZ_BLOCK_M * KC * EB;
     p.b_slot_bytes = PARTS * max_n * KC * EB;
-    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 2 * FZ_GEMMS) * 8 + 16 + (boff + 2 * 4 * p.n[1]) * 4 +
+    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 2 * FZ_GEMMS) * 8 + 16 + boff * 4 +
                      (per_point ? 0 : p.n_chunks[0] * KC * 9 * 4);
     int occ = pl.occ;
     int budget = (occ == 2 ? 113 : 227) * 1024 - tail - 512;

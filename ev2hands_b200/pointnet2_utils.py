@@ -369,10 +369,12 @@ class PointNetSetAbstractionMsg(nn.Module):
                 use = layers[1:]      # layer 1: per point (wide inputs) or in the loader warps (<= 8 channels)
                 kc = _capi.fused_kc(mode, [L["cout"] for L in use])
                 packed = []
-                for L in use:
-                    if (mode, kc) not in L["packed"]:
-                        L["packed"][(mode, kc)] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], mode, kc)
-                    packed.append(L["packed"][(mode, kc)])
+                for li, L in enumerate(use):
+                    # the last layer's weights are the UMMA A operand (output channels = TMEM lanes): 128-row images
+                    key = (mode, kc, 128 if li == 1 else 16)
+                    if key not in L["packed"]:
+                        L["packed"][key] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], mode, kc, key[2])
+                    packed.append(L["packed"][key])
                 _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D,
                                    None if per_point else layers[0]["wt"], None if per_point else layers[0]["bias"],
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
