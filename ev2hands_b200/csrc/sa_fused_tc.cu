@@ -47,7 +47,7 @@ constexpr int FZ_MAX_RING = 8;
 constexpr int FZ_MAX_PRODUCERS = 3;       // up to two loader groups + the epilogue warps
 // Template parameters of the kernel:
 //   KC  channels per K chunk (32, or 16 to halve the ring footprint so two CTAs share an SM)
-//   LG  loader groups of 4 warps;  threads = 32 * (6 + 4 LG): 4 epilogue, issuer, weight streamer, loaders
+//   LG  loader groups of 4 warps;  threads = 32 * (6 + 4 LG): loaders, weight streamer, issuer, 4 epilogue warps
 //   OCC CTAs per SM the instance is built for (launch bound; TMEM share is 512 / OCC columns)
 __host__ __device__ constexpr int fz_threads(int lg) { return 32 * (6 + 4 * lg); }
 
@@ -92,7 +92,7 @@ struct Ring {
 // lifetime) and, for n >= ring size, the wait for the issuer's grant of that slot.  `bits` holds one
 // phase bit per slot, toggled every time this producer consumes a grant.
 __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs, int ring, uint32_t &bits, int tag) {
-    const int slot = (int)(n_abs % (uint32_t)ring);
+    const int slot = (int)(ring == 2 ? (n_abs & 1u) : (n_abs % (uint32_t)ring));
     if (n_abs >= (uint32_t)ring) {
         tc::mbar_wait(my_grants + slot, (bits >> slot) & 1u, tag);
         bits ^= 1u << slot;
@@ -158,7 +158,10 @@ sa_fused_tc_kernel(const FusedParams p) {
         }
         for (int i = tid; i < c1_pad; i += THREADS) b1s[i] = i < p.c1 ? p.first_bias[i] : 0.f;
     }
-    if (warp == 4) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    // Warp roles, lowest to highest warp id = lowest to highest scheduler priority: loaders (work with
+    // slack), weight streamer, UMMA issuer, and the epilogue warps, which are the serial bottleneck of a tile.
+    constexpr int STREAMER_WARP = 4 * LG, ISSUER_WARP = 4 * LG + 1, EPI_WARP0 = 4 * LG + 2;
+    if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -191,9 +194,9 @@ sa_fused_tc_kernel(const FusedParams p) {
         }
     };
 
-    if (warp >= 6) {
+    if (warp < STREAMER_WARP) {
         // =============================== loaders: layer 2's operand rows ===============================
-        const int lw = warp - 6, grp = lw >> 2, wq = lw & 3;
+        const int grp = warp >> 2, wq = warp & 3;
         uint64_t *my_grants = a_grant + grp * FZ_MAX_RING;
         uint32_t bits = 0;
         auto mine = [&](uint32_t it, int kc) { return (int)((it * (uint32_t)nc0 + (uint32_t)kc) % LG) == grp; };
@@ -343,7 +346,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                 prefetch(tile + gridDim.x, it + 1);     // my rows are out: fetch the next tile's P rows now
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == STREAMER_WARP) {
         // =============================== weight streamer ===============================
         if (lane == 0) {
             Ring rb{0, 0, p.sb};
@@ -361,7 +364,7 @@ sa_fused_tc_kernel(const FusedParams p) {
             }
         }
         __syncwarp();
-    } else if (warp == 4) {
+    } else if (warp == ISSUER_WARP) {
         // =============================== UMMA issuer ===============================
         // The whole warp walks the chunk sequence (so every value below is warp-uniform and the
         // descriptor arithmetic stays on the uniform datapath); one elected lane issues.
@@ -451,12 +454,12 @@ sa_fused_tc_kernel(const FusedParams p) {
         }
     } else {
         // =============================== epilogue warps ===============================
-        const int q = warp, r = q * 32 + lane;
+        const int q = warp & 3, r = q * 32 + lane;       // TMEM lane quadrant of a warp is warp_id % 4
         const int K = p.K;
         uint64_t *my_grants = a_grant + LG * FZ_MAX_RING;
         uint32_t bits = 0;
         uint32_t it = 0;
-        const bool eprof = p.dbg != nullptr && tid == 0;
+        const bool eprof = p.dbg != nullptr && warp == EPI_WARP0 && lane == 0;
         long long e_full0 = 0, e_conv = 0, e_slot = 0, e_full1 = 0, e_pool = 0, e_t = 0, e_t2 = 0;
         const long long e_begin = eprof ? clock64() : 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -476,9 +479,17 @@ sa_fused_tc_kernel(const FusedParams p) {
                     tc::tmem_ld_wait();
                     float v[KC];
 #pragma unroll
-                    for (int j = 0; j < KC; ++j) {
-                        const int col = c * KC + j;
-                        v[j] = col < p.n[0] ? fmaxf(__uint_as_float(raw[j]) + bias_g[col], 0.f) : 0.f;
+                    for (int j4 = 0; j4 < KC; j4 += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bias_g + c * KC + j4);   // past n[0]: finite, masked below
+                        v[j4 + 0] = fmaxf(__uint_as_float(raw[j4 + 0]) + b4.x, 0.f);
+                        v[j4 + 1] = fmaxf(__uint_as_float(raw[j4 + 1]) + b4.y, 0.f);
+                        v[j4 + 2] = fmaxf(__uint_as_float(raw[j4 + 2]) + b4.z, 0.f);
+                        v[j4 + 3] = fmaxf(__uint_as_float(raw[j4 + 3]) + b4.w, 0.f);
+                    }
+                    if ((c + 1) * KC > p.n[0]) {                  // last chunk only: columns past the accumulator are padding
+#pragma unroll
+                        for (int j = 0; j < KC; ++j)
+                            if (c * KC + j >= p.n[0]) v[j] = 0.f;
                     }
                     if (eprof) e_t2 = clock64();
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)(nc0 + c), p.sa, bits, 70);
@@ -534,7 +545,7 @@ sa_fused_tc_kernel(const FusedParams p) {
 
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == ISSUER_WARP) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
