@@ -1,5 +1,5 @@
-// Multi-radius ball query: one thread per centre, all radii of a layer in one
-// scan over the window's points.
+// Multi-radius ball query: all radii of a layer in one scan over the window's points,
+// 32 centres x 8 point ranges per CTA.
 //
 // Replaces query_ball_point + square_distance (reference
 // src/Ev2Hands/model/pointnet2_utils.py:87-107, :19-40).  The reference builds a
@@ -14,8 +14,9 @@
 namespace ev2h {
 
 constexpr int kMaxScales = 4;
-constexpr int kBqThreads = 64;    // centres per CTA
-constexpr int kBqTile = 1024;     // points staged per pass (16 KB of float4)
+constexpr int kBqCentres = 32;    // centres per CTA (one per lane)
+constexpr int kBqSegs = 8;        // point ranges scanned in parallel (one per warp)
+constexpr int kBqTile = 2048;     // points staged per pass (32 KB of float4)
 
 struct BallParams {
     float r2[kMaxScales];
@@ -40,14 +41,24 @@ __device__ __forceinline__ float sqdist_expanded(float qx, float qy, float qz, f
     return t;
 }
 
+// One CTA = kBqCentres centres of one window x kBqSegs point segments.  Lanes of a warp are 32
+// different centres looking at the SAME point (a broadcast shared-memory read); the warps of a CTA
+// split every staged tile of points into kBqSegs consecutive index ranges.  "First K in index order"
+// is kept by scanning each range twice: pass 1 counts the hits per (centre, range, radius), a prefix
+// over the ranges gives every range its output offset, pass 2 re-evaluates the distances and writes the
+// hits in place while the offset is below K.  Twice the arithmetic, kBqSegs times the parallelism (the
+// one-thread-per-centre scan left the SMs at 7 warps each).
 template <int NS>
-__global__ void __launch_bounds__(kBqThreads)
+__global__ void __launch_bounds__(kBqCentres * kBqSegs)
 ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
                   const float *__restrict__ centres, int N, int S, BallParams prm,
                   int32_t *__restrict__ out) {
     __shared__ float4 pts[kBqTile];
+    __shared__ int cnt_s[kBqSegs][NS][kBqCentres];      // hits of this tile per (range, radius, centre)
+    __shared__ int first_s[kBqSegs][NS][kBqCentres];    // first hit of this tile per (range, radius, centre), N if none
     const int b = blockIdx.y;
-    const int s = blockIdx.x * kBqThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int s = blockIdx.x * kBqCentres + lane;
     const bool live = s < S;
     const float *base = xyz + (int64_t)b * sb;
 
@@ -59,41 +70,79 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
     const float qn = sq_norm3(qx, qy, qz);
     int32_t *row = out + ((int64_t)b * S + (live ? s : 0)) * prm.k_total;
 
-    int cnt[NS], first[NS];
+    int total[NS], first[NS];                            // running over the tiles already processed (same in every warp)
 #pragma unroll
-    for (int i = 0; i < NS; ++i) { cnt[i] = 0; first[i] = N; }
-    bool full = !live;
+    for (int k = 0; k < NS; ++k) { total[k] = 0; first[k] = N; }
 
     for (int t0 = 0; t0 < N; t0 += kBqTile) {
         const int n_tile = min(kBqTile, N - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < n_tile; i += kBqThreads) {
+        for (int i = threadIdx.x; i < n_tile; i += kBqCentres * kBqSegs) {
             const int64_t g = (int64_t)(t0 + i) * sn;
             const float x = base[g], y = base[sc + g], z = base[2 * sc + g];
             pts[i] = make_float4(x, y, z, sq_norm3(x, y, z));
         }
         __syncthreads();
-        if (full) continue;
-        for (int i = 0; i < n_tile; ++i) {
+        const int per = (n_tile + kBqSegs - 1) / kBqSegs;
+        const int i0 = min(seg * per, n_tile), i1 = min(i0 + per, n_tile);
+
+        // pass 1: count
+        int cnt[NS], fst[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { cnt[k] = 0; fst[k] = N; }
+        for (int i = i0; i < i1; ++i) {
             const float d = sqdist_expanded(qx, qy, qz, qn, pts[i]);
-            if (d > prm.r2_max) continue;            // outside every radius
-            bool all_full = true;
+            if (d > prm.r2_max) continue;                // outside every radius
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-                if (!(d > prm.r2[k]) && cnt[k] < prm.K[k]) {   // group_idx[sqrdists > r**2] = N  (:102)
-                    if (cnt[k] == 0) first[k] = t0 + i;
-                    row[prm.k_off[k] + cnt[k]] = t0 + i;
+                if (!(d > prm.r2[k])) {                   // group_idx[sqrdists > r**2] = N  (:102)
+                    if (cnt[k] == 0) fst[k] = t0 + i;
                     ++cnt[k];
                 }
-                all_full = all_full && (cnt[k] >= prm.K[k]);
             }
-            if (all_full) { full = true; break; }
         }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { cnt_s[seg][k][lane] = cnt[k]; first_s[seg][k][lane] = fst[k]; }
+        __syncthreads();
+
+        // offsets of this range, and the tile's totals
+        int off[NS], tile_total[NS];
+        bool any_room = false;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            int o = total[k], tt = 0;
+            for (int g = 0; g < kBqSegs; ++g) {
+                const int c = cnt_s[g][k][lane];
+                if (g < seg) o += c;
+                tt += c;
+                if (first[k] == N && first_s[g][k][lane] != N) first[k] = first_s[g][k][lane];
+            }
+            off[k] = o; tile_total[k] = tt;
+            any_room = any_room || (cnt[k] > 0 && o < prm.K[k]);
+        }
+
+        // pass 2: write the hits of this range at their final positions
+        if (live && any_room) {
+            for (int i = i0; i < i1; ++i) {
+                const float d = sqdist_expanded(qx, qy, qz, qn, pts[i]);
+                if (d > prm.r2_max) continue;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    if (!(d > prm.r2[k])) {
+                        if (off[k] < prm.K[k]) row[prm.k_off[k] + off[k]] = t0 + i;
+                        ++off[k];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) total[k] += tile_total[k];
     }
     if (!live) return;
+    // pad with the first hit (:104-106); the ranges share the padding slots
 #pragma unroll
-    for (int k = 0; k < NS; ++k)                     // pad with the first hit (:104-106)
-        for (int j = cnt[k]; j < prm.K[k]; ++j) row[prm.k_off[k] + j] = first[k];
+    for (int k = 0; k < NS; ++k)
+        for (int j = total[k] + seg; j < prm.K[k]; j += kBqSegs) row[prm.k_off[k] + j] = first[k];
 }
 
 // square_distance as a standalone op (pointnet2_utils.py:19-40): out[b,s,n], bit-exact.
@@ -171,7 +220,8 @@ extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t s
         }
     }
     prm.k_total = off;
-    dim3 grid((S + kBqThreads - 1) / kBqThreads, B);
+    dim3 grid((S + kBqCentres - 1) / kBqCentres, B);
+    constexpr int kBqThreads = kBqCentres * kBqSegs;
     cudaStream_t st = as_stream(stream);
     switch (n_scales) {
         case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
