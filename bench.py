@@ -277,7 +277,7 @@ def run_ours(args):
     windows = B * world * args.steps
     value = windows / (total_ms / 1e3)
     mlp_n, mlp_ms = 0, 0.0
-    for kname in ("ev2h_linear_relu_f32", "ev2h_linear_relu_tc", "ev2h_linear_f32", "ev2h_sa_msg_fused_tc"):
+    for kname in ("ev2h_linear_relu_f32", "ev2h_linear_relu_tc", "ev2h_linear_f32", "ev2h_linear_tc", "ev2h_sa_msg_fused_tc"):
         n_, ms_ = kern.get(kname, (0, 0.0))
         mlp_n, mlp_ms = mlp_n + n_, mlp_ms + ms_
     mlp_flops_per_step = 2.0 * MLP_MAC_PER_WINDOW * B

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "ev2h_sa_msg_fused_kc": [c_int, ctypes.POINTER(ctypes.c_int32)],
     "ev2h_linear_relu_tc": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_tc_set_debug": [c_int],
+    "ev2h_linear_tc": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_fused_set_debug_buffer": [c_vp],
     "ev2h_linear_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_sa_msg_fused_tc": [c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int,
@@ -297,6 +298,13 @@ def linear_relu_tc(x, M, ld_x, Cin, packed, bias, Cout, pool_rows, y, ld_y, y_co
         with _timed("ev2h_linear_relu_tc"):
             _check(lib().ev2h_linear_relu_tc(_p(x), M, ld_x, Cin, _p(packed), _p(bias), Cout, pool_rows, _p(y), ld_y,
                                              y_col_off, mode, _stream(x)), "ev2h_linear_relu_tc")
+
+
+def linear_tc_no_relu(x, M, ld_x, Cin, packed, bias, Cout, y, ld_y, y_col_off, mode):
+    with torch.cuda.device(x.device):
+        with _timed("ev2h_linear_tc"):
+            _check(lib().ev2h_linear_tc(_p(x), M, ld_x, Cin, _p(packed), _p(bias), Cout, _p(y), ld_y, y_col_off, mode,
+                                        _stream(x)), "ev2h_linear_tc")
 
 
 def linear_no_relu(x, M, ld_x, Cin, wt, bias, Cout, y, ld_y, y_col_off=0):

@@ -54,6 +54,7 @@ struct TcParams {
     int n_store_total;  // columns of y that may be written (>= Cout when zero padding exists)
     int stages;
     int debug;
+    int relu;           // 0: y = x W' + b' (no activation)
 };
 
 // ---- weight packing: folded [Cin_pad16, ld_w] fp32 (input-channel major) -> per (n-block, stage)
@@ -282,7 +283,10 @@ linear_tc_kernel(const TcParams p) {
                 tc::tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(raw[j]) + bias_s[col0 + c0 + j], 0.f);
+                for (int j = 0; j < 32; ++j) {
+                    const float t = __uint_as_float(raw[j]) + bias_s[col0 + c0 + j];
+                    v[j] = p.relu ? fmaxf(t, 0.f) : t;
+                }
                 if (K == 0) {
                     if (row_ok) {
                         float *yr = p.y + (m0 + r) * (int64_t)p.ld_y + p.y_col_off + col0 + c0;
@@ -403,9 +407,22 @@ extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int C
     return check_launch("ev2h_tc_pack_weights");
 }
 
+static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed, const float *bias, int Cout,
+                          int pool_rows, float *y, int ld_y, int y_col_off, int mode, int relu, ev2h_stream_t stream);
+
 extern "C" int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
                                    const float *bias, int Cout, int pool_rows, float *y, int ld_y, int y_col_off,
                                    int mode, ev2h_stream_t stream) {
+    return linear_tc_impl(x, M, ld_x, Cin, w_packed, bias, Cout, pool_rows, y, ld_y, y_col_off, mode, 1, stream);
+}
+
+extern "C" int ev2h_linear_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed, const float *bias,
+                              int Cout, float *y, int ld_y, int y_col_off, int mode, ev2h_stream_t stream) {
+    return linear_tc_impl(x, M, ld_x, Cin, w_packed, bias, Cout, 0, y, ld_y, y_col_off, mode, 0, stream);
+}
+
+static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed, const float *bias, int Cout,
+                          int pool_rows, float *y, int ld_y, int y_col_off, int mode, int relu, ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(x && w_packed && bias && y, "ev2h_linear_relu_tc: null argument");
     EV2H_REQUIRE(M > 0 && Cin > 0 && Cout > 0, "ev2h_linear_relu_tc: bad sizes");
@@ -437,6 +454,7 @@ extern "C" int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin,
     if (stages < 2) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_linear_relu_tc: stage of %d bytes does not fit twice", stage_bytes);
     p.stages = stages;
     p.debug = g_tc_debug;
+    p.relu = relu;
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes;
 
     int dev = 0, sms = 0;

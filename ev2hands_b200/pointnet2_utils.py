@@ -355,7 +355,15 @@ class PointNetSetAbstractionMsg(nn.Module):
                     wx = torch.zeros((16, L0["wt"].shape[1]), dtype=torch.float32, device=xyz.device)
                     wx[:3] = L0["wt"][D:D + 3]
                     L0["wt_xyz"], L0["zero_bias"] = wx, torch.zeros_like(L0["bias"])
-                _capi.linear_no_relu(x_pts, B * N, ld_pts, D + 3, L0["wt"], L0["bias"], L0["cout"], P, c1_total, col)
+                if mode == _capi.TC_TF32X3 and _capi.tc_supported(L0["cout"], 0):
+                    # the wide per-point layer on the tensor cores (fp32-level accuracy); bf16 mode keeps it
+                    # in exact fp32 so that only the two tensor-core layers carry bf16 rounding
+                    key = (mode, 32, 16)
+                    if key not in L0["packed"]:
+                        L0["packed"][key] = _capi.tc_pack(L0["wt"], L0["cin"], L0["cout"], mode)
+                    _capi.linear_tc_no_relu(x_pts, B * N, ld_pts, D + 3, L0["packed"][key], L0["bias"], L0["cout"], P, c1_total, col, mode)
+                else:
+                    _capi.linear_no_relu(x_pts, B * N, ld_pts, D + 3, L0["wt"], L0["bias"], L0["cout"], P, c1_total, col)
                 _capi.linear_no_relu(ctr4, B * S, 4, 3, L0["wt_xyz"], L0["zero_bias"], L0["cout"], C, c1_total, col)
                 p_cols.append(col)
                 col += L0["cout"]

@@ -178,6 +178,10 @@ EV2H_API int ev2h_linear_f32(const float *x, int64_t M, int ld_x, int Cin, const
 EV2H_API int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode);
 EV2H_API int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
                                   ev2h_stream_t stream);
+/* The tensor-core layer without the ReLU (y = x W' + b'), cf. ev2h_linear_f32. */
+EV2H_API int ev2h_linear_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed, const float *bias,
+                            int Cout, float *y, int ld_y, int y_col_off, int mode, ev2h_stream_t stream);
+
 /* Same with an explicit K-chunk length (16 or 32 input channels per shared-memory image;
  * ev2h_sa_msg_fused_kc tells which one the fused kernel wants) and row padding of the image:
  * row_align 16 when the weights are the UMMA B operand, 128 when they are the A operand (the
