@@ -520,9 +520,20 @@ sa_fused_tc_kernel(const FusedParams p) {
                         uint32_t raw[32];
                         tc::tmem_ld32(t_addr + c0, raw);
                         tc::tmem_ld_wait();
-                        float m = -INFINITY;
+                        float m;
+                        if (rows_left >= FZ_BLOCK_M) {               // every tile but possibly the last: no row mask
+                            float m0_ = -INFINITY, m1_ = -INFINITY, m2_ = -INFINITY, m3_ = -INFINITY;   // 4 chains for ILP
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) m = fmaxf(m, (c0 + j) < rows_left ? __uint_as_float(raw[j]) : -INFINITY);
+                            for (int j = 0; j < 32; j += 4) {
+                                m0_ = fmaxf(m0_, __uint_as_float(raw[j])); m1_ = fmaxf(m1_, __uint_as_float(raw[j + 1]));
+                                m2_ = fmaxf(m2_, __uint_as_float(raw[j + 2])); m3_ = fmaxf(m3_, __uint_as_float(raw[j + 3]));
+                            }
+                            m = fmaxf(fmaxf(m0_, m1_), fmaxf(m2_, m3_));
+                        } else {
+                            m = -INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) m = fmaxf(m, (c0 + j) < rows_left ? __uint_as_float(raw[j]) : -INFINITY);
+                        }
                         gmax = fmaxf(gmax, m);
                         if (((c0 + 32) % K) == 0) {                      // a group of K rows is complete (K in {32, 64, 128})
                             const int64_t row0 = m0 + c0 + 32 - K;
