@@ -92,7 +92,7 @@ struct Ring {
 // lifetime) and, for n >= ring size, the wait for the issuer's grant of that slot.  `bits` holds one
 // phase bit per slot, toggled every time this producer consumes a grant.
 __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs, int ring, uint32_t &bits, int tag) {
-    const int slot = (int)(ring == 2 ? (n_abs & 1u) : (n_abs % (uint32_t)ring));
+    const int slot = (int)(ring == 2 ? (n_abs & 1u) : (n_abs % 3u));          // the operand ring has 2 or 3 slots
     if (n_abs >= (uint32_t)ring) {
         tc::mbar_wait(my_grants + slot, (bits >> slot) & 1u, tag);
         bits ^= 1u << slot;
@@ -153,7 +153,8 @@ sa_fused_tc_kernel(const FusedParams p) {
     if (!p.per_point) {
         const int c1_pad = nc0 * KC;
         for (int i = tid; i < c1_pad * 8; i += THREADS) {
-            const int ch = i >> 3, k = i & 7;
+            // channel pairs interleaved, [pair][k][2], so one 64-bit word feeds one packed FMA
+            const int ch = 2 * (i >> 4) + (i & 1), k = (i >> 1) & 7;
             w1s[i] = ch < p.c1 ? p.first_wt[(size_t)k * p.first_ld + ch] : 0.f;
         }
         for (int i = tid; i < c1_pad; i += THREADS) b1s[i] = i < p.c1 ? p.first_bias[i] : 0.f;
@@ -174,8 +175,8 @@ sa_fused_tc_kernel(const FusedParams p) {
 #pragma unroll
             for (int cc = 0; cc < NCH; ++cc) {
                 float4 hi, lo;
-                tc::split_tf32(v[4 * cc], hi.x, lo.x); tc::split_tf32(v[4 * cc + 1], hi.y, lo.y);
-                tc::split_tf32(v[4 * cc + 2], hi.z, lo.z); tc::split_tf32(v[4 * cc + 3], hi.w, lo.w);
+                tc::split_tf32x2(v[4 * cc], v[4 * cc + 1], hi.x, hi.y, lo.x, lo.y);
+                tc::split_tf32x2(v[4 * cc + 2], v[4 * cc + 3], hi.z, hi.w, lo.z, lo.w);
                 *reinterpret_cast<float4 *>(st + cc * CHUNK_ROWS_BYTES + r * 16) = hi;
                 *reinterpret_cast<float4 *>(st + A_PART + cc * CHUNK_ROWS_BYTES + r * 16) = lo;
             }
@@ -235,20 +236,31 @@ sa_fused_tc_kernel(const FusedParams p) {
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = xn[i];
+                uint64_t xx[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xx[i] = tc::pack2(x[i], x[i]);
                 valid = valid_n;
                 gather(tile + gridDim.x, xn, valid_n);            // next tile's record is in flight during this tile
                 for (int kc = 0; kc < nc0; ++kc) {
                     if (!mine(it, kc)) continue;
                     float v[KC];
 #pragma unroll
-                    for (int j = 0; j < KC; ++j) {
+                    for (int j = 0; j < KC; j += 2) {
                         const int ch = kc * KC + j;
-                        const float4 wa = *reinterpret_cast<const float4 *>(w1s + ch * 8);
-                        const float4 wb = *reinterpret_cast<const float4 *>(w1s + ch * 8 + 4);
-                        float acc = b1s[ch];
-                        acc = fmaf(wa.x, x[0], acc); acc = fmaf(wa.y, x[1], acc); acc = fmaf(wa.z, x[2], acc); acc = fmaf(wa.w, x[3], acc);
-                        acc = fmaf(wb.x, x[4], acc); acc = fmaf(wb.y, x[5], acc); acc = fmaf(wb.z, x[6], acc); acc = fmaf(wb.w, x[7], acc);
-                        v[j] = valid ? fmaxf(acc, 0.f) : 0.f;
+                        const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w1s + ch * 8);
+                        const ulonglong2 w01 = wp[0], w23 = wp[1], w45 = wp[2], w67 = wp[3];
+                        uint64_t acc = *reinterpret_cast<const uint64_t *>(b1s + ch);
+                        acc = tc::fma2(w01.x, xx[0], acc); acc = tc::fma2(w01.y, xx[1], acc);
+                        acc = tc::fma2(w23.x, xx[2], acc); acc = tc::fma2(w23.y, xx[3], acc);
+                        acc = tc::fma2(w45.x, xx[4], acc); acc = tc::fma2(w45.y, xx[5], acc);
+                        acc = tc::fma2(w67.x, xx[6], acc); acc = tc::fma2(w67.y, xx[7], acc);
+                        float a0, a1;
+                        tc::unpack2(acc, a0, a1);
+                        v[j] = fmaxf(a0, 0.f); v[j + 1] = fmaxf(a1, 0.f);
+                    }
+                    if (!valid) {
+#pragma unroll
+                        for (int j = 0; j < KC; ++j) v[j] = 0.f;
                     }
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)kc, p.sa, bits, 10);
                     store_row_chunk(a_ring + (size_t)slot * p.a_slot_bytes, r, v);
@@ -480,11 +492,12 @@ sa_fused_tc_kernel(const FusedParams p) {
                     float v[KC];
 #pragma unroll
                     for (int j4 = 0; j4 < KC; j4 += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4 *>(bias_g + c * KC + j4);   // past n[0]: finite, masked below
-                        v[j4 + 0] = fmaxf(__uint_as_float(raw[j4 + 0]) + b4.x, 0.f);
-                        v[j4 + 1] = fmaxf(__uint_as_float(raw[j4 + 1]) + b4.y, 0.f);
-                        v[j4 + 2] = fmaxf(__uint_as_float(raw[j4 + 2]) + b4.z, 0.f);
-                        v[j4 + 3] = fmaxf(__uint_as_float(raw[j4 + 3]) + b4.w, 0.f);
+                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2 *>(bias_g + c * KC + j4);   // past n[0]: finite, masked below
+                        float t0, t1, t2, t3;
+                        tc::unpack2(tc::add2(tc::pack2(__uint_as_float(raw[j4 + 0]), __uint_as_float(raw[j4 + 1])), b4.x), t0, t1);
+                        tc::unpack2(tc::add2(tc::pack2(__uint_as_float(raw[j4 + 2]), __uint_as_float(raw[j4 + 3])), b4.y), t2, t3);
+                        v[j4 + 0] = fmaxf(t0, 0.f); v[j4 + 1] = fmaxf(t1, 0.f);
+                        v[j4 + 2] = fmaxf(t2, 0.f); v[j4 + 3] = fmaxf(t3, 0.f);
                     }
                     if ((c + 1) * KC > p.n[0]) {                  // last chunk only: columns past the accumulator are padding
 #pragma unroll

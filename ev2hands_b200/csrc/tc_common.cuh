@@ -202,5 +202,39 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
     lo = x - hi;
 }
 
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 issue two IEEE operations per lane per instruction; each
+// half rounds exactly like the scalar instruction, so results are bit-identical to fmaf / __fadd_rn).
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// two fp32 -> (hi, lo) pairs; the subtraction is one packed instruction
+__device__ __forceinline__ void split_tf32x2(float x0, float x1, float &h0, float &h1, float &l0, float &l1) {
+    uint32_t a, b;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(x0));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x1));
+    h0 = __uint_as_float(a); h1 = __uint_as_float(b);
+    unpack2(sub2(pack2(x0, x1), pack2(h0, h1)), l0, l1);
+}
+
 }  // namespace tc
 }  // namespace ev2h
