@@ -12,7 +12,8 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libev2h.so")
+# EV2H_LIB selects another build of the same ABI (kernel experiments); default is the in-tree library
+LIB_PATH = os.environ.get("EV2H_LIB") or os.path.join(_PKG, "libev2h.so")
 _lib = None
 
 c_int, c_i64, c_f, c_d, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
@@ -265,7 +266,7 @@ def linear_relu(x, M, ld_x, Cin, wt, bias, Cout, pool_rows, y, ld_y, y_col_off=0
                                           y_col_off, _stream(x)), "ev2h_linear_relu_f32")
 
 
-TC_BF16, TC_TF32X3 = 0, 1
+TC_BF16, TC_TF32X3, TC_TF32_BF16C = 0, 1, 2
 
 
 def tc_supported(Cout: int, pool_rows: int) -> bool:

@@ -33,7 +33,7 @@ constexpr int TC_LOADER_GROUPS = 2;    // groups of 4 loader warps working on di
 constexpr int TC_THREADS = 32 * (5 + 4 * TC_LOADER_GROUPS);   // 4 epilogue + 1 issuer + loader warps
 constexpr int TC_MAX_STAGES = 8;
 
-enum { TC_MODE_BF16 = 0, TC_MODE_TF32X3 = 1 };
+enum { TC_MODE_BF16 = 0, TC_MODE_TF32X3 = 1, TC_MODE_MIXED = 2 };   // MIXED: weight images for sa_fused_tc.cu only
 
 __host__ __device__ constexpr int tc_elem_bytes(int mode) { return mode == TC_MODE_BF16 ? 2 : 4; }
 // bytes of one operand image holding `rows` rows x TC_KC channels (one precision part)
@@ -81,6 +81,15 @@ tc_pack_kernel(const float *__restrict__ wt, int ld_w, int cin_rows, int cout_co
     const size_t off = (size_t)(kk / CH) * ((size_t)n_blk * 16) + (size_t)n * 16 + (size_t)(kk % CH) * EB;
     if (MODE == TC_MODE_BF16) {
         *reinterpret_cast<__nv_bfloat16 *>(stage + off) = __float2bfloat16_rn(w);
+    } else if (MODE == TC_MODE_MIXED) {
+        // [hi as tf32 | w as bf16 | lo as bf16]: the fused kernel's hi*hi runs in tf32, the two correction
+        // products on the bf16 copies (16-byte chunks of 8 channels)
+        float hi, lo;
+        tc::split_tf32(w, hi, lo);
+        *reinterpret_cast<float *>(stage + off) = hi;
+        const size_t off16 = (size_t)(kk / 8) * ((size_t)n_blk * 16) + (size_t)n * 16 + (size_t)(kk % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(stage + part + off16) = __float2bfloat16_rn(w);
+        *reinterpret_cast<__nv_bfloat16 *>(stage + part + part / 2 + off16) = __float2bfloat16_rn(lo);
     } else {
         float hi, lo;
         tc::split_tf32(w, hi, lo);
@@ -372,7 +381,7 @@ static int tc_n_blk_aligned(int Cout, int row_align) {
 
 extern "C" int64_t ev2h_tc_packed_bytes_kc(int Cin, int Cout, int mode, int kc, int row_align) {
     using namespace ev2h;
-    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3) || (kc != 16 && kc != 32) ||
+    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3 && mode != TC_MODE_MIXED) || (kc != 16 && kc != 32) ||
         (row_align != 16 && row_align != 128)) return -1;
     const int n_blk = tc_n_blk_aligned(Cout, row_align);
     return (int64_t)((Cout + n_blk - 1) / n_blk) * ((Cin + kc - 1) / kc) * tc_parts(mode) * n_blk * kc * tc_elem_bytes(mode);
@@ -393,7 +402,7 @@ extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int C
     EV2H_REQUIRE(row_align == 16 || row_align == 128, "ev2h_tc_pack_weights: row_align must be 16 or 128");
     EV2H_REQUIRE(wt && packed, "ev2h_tc_pack_weights: null argument");
     EV2H_REQUIRE(Cin > 0 && Cout > 0 && ld_w >= Cout, "ev2h_tc_pack_weights: bad sizes");
-    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3, "ev2h_tc_pack_weights: unknown mode %d", mode);
+    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3 || mode == TC_MODE_MIXED, "ev2h_tc_pack_weights: unknown mode %d", mode);
     const int n_blk = tc_n_blk_aligned(Cout, row_align), n_blocks = (Cout + n_blk - 1) / n_blk, n_kc = (Cin + kc - 1) / kc;
     const int64_t total = (int64_t)n_blocks * n_kc * n_blk * kc;
     const unsigned grid = (unsigned)((total + 255) / 256);
@@ -402,6 +411,8 @@ extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int C
     const int cout_cols = ld_w;
     if (mode == TC_MODE_BF16)
         tc_pack_kernel<TC_MODE_BF16><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
+    else if (mode == TC_MODE_MIXED)
+        tc_pack_kernel<TC_MODE_MIXED><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
     else
         tc_pack_kernel<TC_MODE_TF32X3><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
     return check_launch("ev2h_tc_pack_weights");

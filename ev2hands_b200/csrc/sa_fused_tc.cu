@@ -33,7 +33,12 @@
 //                   per POINT and C = W1_xyz c per centre, both precomputed (32x fewer MACs);
 //                   the loader gathers P, subtracts C and applies the ReLU.
 //
-// Arithmetic modes as in linear_tc.cu: TF32X3 (fp32-level accuracy) or BF16.
+// Arithmetic modes: BF16 (one kind::f16 UMMA per product), TF32X3 (x = hi + lo, w = hi + lo in tf32, three
+// kind::tf32 UMMAs lo*hi + hi*lo + hi*hi: fp32-level accuracy) and MIXED, the default fp32-level mode:
+// hi*hi as kind::tf32 and the two correction products x_lo*w_hi + x_hi*w_lo as kind::f16 UMMAs on bf16
+// copies.  The corrections are 2^-11 of the result, so bf16's 2^-9 relative error on them is 2^-20 of the
+// result (measured end to end: same error against the reference as TF32X3), while tensor time and the
+// shared-memory operand reads per product drop by a third (the kernel is shared-memory-bandwidth bound).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
@@ -51,7 +56,7 @@ constexpr int FZ_MAX_PRODUCERS = 3;       // up to two loader groups + the epilo
 //   OCC CTAs per SM the instance is built for (launch bound; TMEM share is 512 / OCC columns)
 __host__ __device__ constexpr int fz_threads(int lg) { return 32 * (6 + 4 * lg); }
 
-enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1 };
+enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1, FZ_MODE_MIXED = 2 };
 
 struct FusedParams {
     // geometry of the grouping
@@ -88,6 +93,16 @@ struct Ring {
     __device__ __forceinline__ void advance() { if (++slot == size) { slot = 0; phase ^= 1; } }
 };
 
+#ifdef EV2H_FUSED_TRACE
+// timeline trace of CTA 0 (steady-state tiles): (tag << 40 | clock) stored per role from row 300 of the debug
+// buffer, 800 entries per role, private counters (plain stores only: no round trip, little perturbation)
+#define FZ_TRACE(role, ev, it_, c_) do { if (p.dbg && blockIdx.x == 0 && (it_) >= 6 && (it_) < 9 && trace_n < 799) { \
+    p.dbg[4800 + ((role) - 1) * 800 + 1 + trace_n] = ((long long)((role) * 1000000 + (ev) * 10000 + ((it_) % 100) * 100 + (c_)) << 40) | (clock64() & 0xFFFFFFFFFFll); \
+    ++trace_n; p.dbg[4800 + ((role) - 1) * 800] = trace_n; } } while (0)
+#else
+#define FZ_TRACE(role, ev, it_, c_) do { } while (0)
+#endif
+
 // A producer's view of the operand ring: the slot of chunk n (absolute index over the CTA's
 // lifetime) and, for n >= ring size, the wait for the issuer's grant of that slot.  `bits` holds one
 // phase bit per slot, toggled every time this producer consumes a grant.
@@ -108,11 +123,12 @@ sa_fused_tc_kernel(const FusedParams p) {
     constexpr int EB = MODE == FZ_MODE_BF16 ? 2 : 4;
     constexpr int PARTS = MODE == FZ_MODE_BF16 ? 1 : 2;
     constexpr int A_PART = FZ_BLOCK_M * KC * EB;         // per precision part: 16 KB (tf32, KC 32) ... 8 KB
+    constexpr int A_B16 = FZ_BLOCK_M * KC * 2;           // MIXED: bf16 copy of hi at A_PART, bf16 lo at A_PART + A_B16
     constexpr int NCH = KC * EB / 16;                    // 16-byte operand chunks per row per K chunk
     constexpr int UMMA_K = 32 / EB;
     constexpr int K_STEPS = KC / UMMA_K;
     constexpr int CHUNK_ROWS_BYTES = FZ_BLOCK_M * 16;    // one 16-byte operand chunk for all 128 rows
-    static_assert(NCH >= 2 && (MODE == FZ_MODE_TF32X3 || KC == 32), "unsupported chunk geometry");
+    static_assert(NCH >= 2 && (MODE != FZ_MODE_BF16 || KC == 32), "unsupported chunk geometry");
 
     uint8_t *a_ring = fz_smem;
     uint8_t *b_ring = a_ring + (size_t)p.sa * p.a_slot_bytes;
@@ -134,6 +150,9 @@ sa_fused_tc_kernel(const FusedParams p) {
     float *b1s = w1s + (p.per_point ? 0 : p.n_chunks[0] * KC * 8);     // [c1_pad]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef EV2H_FUSED_TRACE
+    int trace_n = 0;
+#endif
     const int64_t M = (int64_t)p.B * p.S * p.K;
     const int64_t n_tiles = (M + FZ_BLOCK_M - 1) / FZ_BLOCK_M;
     const int nc0 = p.n_chunks[0], nc1 = p.n_chunks[1];
@@ -171,7 +190,25 @@ sa_fused_tc_kernel(const FusedParams p) {
     // fp32 values of one row -> operand chunk(s) in the K-major, no-swizzle UMMA layout.  Thread = row:
     // consecutive threads write consecutive 16-byte pieces, conflict free.
     auto store_row_chunk = [&](uint8_t *st, int r, const float (&v)[KC]) {
-        if (MODE == FZ_MODE_TF32X3) {
+        if (MODE == FZ_MODE_MIXED) {
+#pragma unroll
+            for (int c8 = 0; c8 < KC / 8; ++c8) {
+                float4 h0, l0, h1, l1;
+                tc::split_tf32x2(v[8 * c8], v[8 * c8 + 1], h0.x, h0.y, l0.x, l0.y);
+                tc::split_tf32x2(v[8 * c8 + 2], v[8 * c8 + 3], h0.z, h0.w, l0.z, l0.w);
+                tc::split_tf32x2(v[8 * c8 + 4], v[8 * c8 + 5], h1.x, h1.y, l1.x, l1.y);
+                tc::split_tf32x2(v[8 * c8 + 6], v[8 * c8 + 7], h1.z, h1.w, l1.z, l1.w);
+                *reinterpret_cast<float4 *>(st + (2 * c8) * CHUNK_ROWS_BYTES + r * 16) = h0;
+                *reinterpret_cast<float4 *>(st + (2 * c8 + 1) * CHUNK_ROWS_BYTES + r * 16) = h1;
+                uint4 xb, lb;
+                xb.x = tc::bf16x2(v[8 * c8], v[8 * c8 + 1]); xb.y = tc::bf16x2(v[8 * c8 + 2], v[8 * c8 + 3]);
+                xb.z = tc::bf16x2(v[8 * c8 + 4], v[8 * c8 + 5]); xb.w = tc::bf16x2(v[8 * c8 + 6], v[8 * c8 + 7]);
+                lb.x = tc::bf16x2(l0.x, l0.y); lb.y = tc::bf16x2(l0.z, l0.w);
+                lb.z = tc::bf16x2(l1.x, l1.y); lb.w = tc::bf16x2(l1.z, l1.w);
+                *reinterpret_cast<uint4 *>(st + A_PART + c8 * CHUNK_ROWS_BYTES + r * 16) = xb;
+                *reinterpret_cast<uint4 *>(st + A_PART + A_B16 + c8 * CHUNK_ROWS_BYTES + r * 16) = lb;
+            }
+        } else if (MODE == FZ_MODE_TF32X3) {
 #pragma unroll
             for (int cc = 0; cc < NCH; ++cc) {
                 float4 hi, lo;
@@ -262,10 +299,13 @@ sa_fused_tc_kernel(const FusedParams p) {
 #pragma unroll
                         for (int j = 0; j < KC; ++j) v[j] = 0.f;
                     }
+                    if (tid == 0) FZ_TRACE(1, 1, it, kc);
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)kc, p.sa, bits, 10);
+                    if (tid == 0) FZ_TRACE(1, 2, it, kc);
                     store_row_chunk(a_ring + (size_t)slot * p.a_slot_bytes, r, v);
                     tc::fence_proxy_async();
                     tc::mbar_arrive(a_full + slot);
+                    if (tid == 0) FZ_TRACE(1, 3, it, kc);
                 }
             }
         } else {
@@ -313,10 +353,18 @@ sa_fused_tc_kernel(const FusedParams p) {
                 for (int i = 0; i < NV; ++i) {
                     const int row = 32 * wq + (i / QP) * 8 + l8;
                     const int quad = oct + 4 * (i % QP);
-                    if (MODE == FZ_MODE_TF32X3) {
+                    if (MODE == FZ_MODE_MIXED) {     // a 16-byte bf16 chunk holds two fp32 quads
                         float4 hi, lo;
-                        tc::split_tf32(v[i].x, hi.x, lo.x); tc::split_tf32(v[i].y, hi.y, lo.y);
-                        tc::split_tf32(v[i].z, hi.z, lo.z); tc::split_tf32(v[i].w, hi.w, lo.w);
+                        tc::split_tf32x2(v[i].x, v[i].y, hi.x, hi.y, lo.x, lo.y);
+                        tc::split_tf32x2(v[i].z, v[i].w, hi.z, hi.w, lo.z, lo.w);
+                        *reinterpret_cast<float4 *>(st + quad * CHUNK_ROWS_BYTES + row * 16) = hi;
+                        const uint32_t o16 = (quad >> 1) * CHUNK_ROWS_BYTES + row * 16 + (quad & 1) * 8;
+                        *reinterpret_cast<uint2 *>(st + A_PART + o16) = make_uint2(tc::bf16x2(v[i].x, v[i].y), tc::bf16x2(v[i].z, v[i].w));
+                        *reinterpret_cast<uint2 *>(st + A_PART + A_B16 + o16) = make_uint2(tc::bf16x2(lo.x, lo.y), tc::bf16x2(lo.z, lo.w));
+                    } else if (MODE == FZ_MODE_TF32X3) {
+                        float4 hi, lo;
+                        tc::split_tf32x2(v[i].x, v[i].y, hi.x, hi.y, lo.x, lo.y);
+                        tc::split_tf32x2(v[i].z, v[i].w, hi.z, hi.w, lo.z, lo.w);
                         *reinterpret_cast<float4 *>(st + quad * CHUNK_ROWS_BYTES + row * 16) = hi;
                         *reinterpret_cast<float4 *>(st + A_PART + quad * CHUNK_ROWS_BYTES + row * 16) = lo;
                     } else {                         // bf16: a 16-byte operand chunk holds two fp32 quads
@@ -368,6 +416,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                     const uint32_t bytes = (uint32_t)PARTS * w_rows * KC * EB;
                     for (int c = 0; c < p.n_chunks[g]; ++c) {
                         tc::mbar_wait(b_empty + rb.slot, rb.phase ^ 1, 20);     // sole producer of this ring: always in step
+                        FZ_TRACE(2, 1, (uint32_t)((tile - blockIdx.x) / gridDim.x), g * 50 + c);
                         tc::mbar_arrive_expect_tx(b_full + rb.slot, bytes);
                         tc::bulk_g2s(b_ring + (size_t)rb.slot * p.b_slot_bytes, p.w[g] + (size_t)c * bytes, bytes, b_full + rb.slot);
                         rb.advance();
@@ -395,21 +444,25 @@ sa_fused_tc_kernel(const FusedParams p) {
                 // g == 0: D[rows x n0]      = X[rows x K] * W2[n0 x K]^T      (A = activations, B = weights)
                 // g == 1: D[chan x rows]^T: per 128-channel block  D = W3[128 x K] * X[rows x K]^T  (A = weights, B = activations)
                 const uint32_t w_rows = g == 0 ? (uint32_t)p.n[0] : 128u * (uint32_t)p.mb3;
-                const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M,
-                                                      g == 0 ? (uint32_t)p.n[0] : (uint32_t)FZ_BLOCK_M);
+                const uint32_t n_umma = g == 0 ? (uint32_t)p.n[0] : (uint32_t)FZ_BLOCK_M;
+                const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M, n_umma);
+                const uint32_t idesc16 = tc::instr_desc(tc::FMT_BF16, FZ_BLOCK_M, n_umma);     // MIXED: the correction products
                 const uint32_t b_lbo = w_rows * 16;
                 const uint32_t b_part = w_rows * KC * EB;
                 const uint32_t d_tmem = tmem_base + (uint32_t)p.tmem_col[g];
                 const int n_chunks = p.n_chunks[g];
                 if (prof) t0 = clock64();
                 tc::mbar_wait(acc_empty + g, (it & 1) ^ 1, 30 + g);       // previous tile's epilogue drained this accumulator
+                if (lane == 0) FZ_TRACE(3, 1, it, g * 50);
                 if (prof) w_acc += clock64() - t0;
                 tc::tc_fence_after();
                 for (int c = 0; c < n_chunks; ++c) {
                     if (prof) t0 = clock64();
                     tc::mbar_wait(a_full + ra.slot, ra.phase, 40 + g);
                     if (prof) { t1 = clock64(); w_a[g] += t1 - t0; }
+                    if (lane == 0) FZ_TRACE(3, 2, it, g * 50 + c);
                     tc::mbar_wait(b_full + rb.slot, rb.phase, 50 + g);
+                    if (lane == 0) FZ_TRACE(3, 3, it, g * 50 + c);
                     if (prof) w_b += clock64() - t1;
                     tc::tc_fence_after();
                     const uint32_t a0 = a_ring_addr + (uint32_t)ra.slot * (uint32_t)p.a_slot_bytes;
@@ -422,6 +475,36 @@ sa_fused_tc_kernel(const FusedParams p) {
                         uint32_t a_hi = tc::smem_desc_lo(a0, a_lbo), b_hi = tc::smem_desc_lo(b0, b_lbo);
                         const uint32_t a_step = (2 * a_lbo) >> 4, b_step = (2 * b_lbo) >> 4;
                         const uint32_t a_lo_off = A_PART >> 4, b_lo_off = b_part >> 4;
+                        if (MODE == FZ_MODE_MIXED) {
+                            // hi*hi in tf32 (ks steps of 8 channels), then x_lo*w_hi and x_hi*w_lo on the bf16
+                            // copies (steps of 16 channels); all accumulate into the same fp32 accumulator
+                            const uint32_t a16 = a_hi + (A_PART >> 4), b16 = b_hi + (b_part >> 4);
+                            const uint32_t a16_lo = a16 + (A_B16 >> 4), b16_lo = b16 + (b_part >> 5);
+                            const int ks16 = (ks + 1) >> 1;
+#pragma unroll 1
+                            for (int mb = 0; mb < (g == 0 ? 1 : p.mb3); ++mb) {
+                                const uint32_t wo = g == 0 ? 0u : (uint32_t)mb * ((128u * 16u) >> 4);   // 128 weight rows further
+                                const uint32_t d = d_tmem + (g == 0 ? 0u : (uint32_t)mb * FZ_BLOCK_M);
+#pragma unroll 1
+                                for (int j = 0; j < ks; ++j) {
+                                    const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
+                                    const uint32_t ax = a_hi + j * a_step, bx = b_hi + wo + j * b_step;
+                                    if (g == 0) tc::umma_tf32(d, tc::make_desc(ax, desc_hi), tc::make_desc(bx, desc_hi), idesc, acc);
+                                    else tc::umma_tf32(d, tc::make_desc(bx, desc_hi), tc::make_desc(ax, desc_hi), idesc, acc);
+                                }
+#pragma unroll 1
+                                for (int j = 0; j < ks16; ++j) {
+                                    const uint32_t ao = j * a_step, bo = wo + j * b_step;
+                                    if (g == 0) {
+                                        tc::umma_f16(d, tc::make_desc(a16_lo + ao, desc_hi), tc::make_desc(b16 + bo, desc_hi), idesc16, 1u);
+                                        tc::umma_f16(d, tc::make_desc(a16 + ao, desc_hi), tc::make_desc(b16_lo + bo, desc_hi), idesc16, 1u);
+                                    } else {
+                                        tc::umma_f16(d, tc::make_desc(b16 + bo, desc_hi), tc::make_desc(a16_lo + ao, desc_hi), idesc16, 1u);
+                                        tc::umma_f16(d, tc::make_desc(b16_lo + bo, desc_hi), tc::make_desc(a16 + ao, desc_hi), idesc16, 1u);
+                                    }
+                                }
+                            }
+                        } else {
 #pragma unroll 1
                         for (int j = 0; j < ks; ++j) {
                             const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
@@ -448,6 +531,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                             }
                             a_hi += a_step; b_hi += b_step;
                         }
+                        }
                         if (prof) t0 = clock64();
                         tc::umma_commit(a_grant + next_prod * FZ_MAX_RING + ra.slot);
                         tc::umma_commit(b_empty + rb.slot);
@@ -455,6 +539,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                         if (prof) w_commit += clock64() - t0;
                     }
                     __syncwarp();
+                    if (lane == 0) FZ_TRACE(3, 4, it, g * 50 + c);
                     ra.advance(); rb.advance();
                     if (++g_q == Q) { g_q = 0; ++g_it; }
                 }
@@ -482,6 +567,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                 const float *bias_g = bias_s + p.bias_off[0];
                 if (eprof) e_t = clock64();
                 tc::mbar_wait(acc_full + 0, it & 1, 60);
+                if (eprof) FZ_TRACE(4, 1, it, 0);
                 if (eprof) { e_t2 = clock64(); e_full0 += e_t2 - e_t; e_t = e_t2; }
                 tc::tc_fence_after();
                 for (int c = 0; c < nc1; ++c) {
@@ -505,11 +591,14 @@ sa_fused_tc_kernel(const FusedParams p) {
                             if (c * KC + j >= p.n[0]) v[j] = 0.f;
                     }
                     if (eprof) e_t2 = clock64();
+                    if (eprof) FZ_TRACE(4, 2, it, c);
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)(nc0 + c), p.sa, bits, 70);
                     if (eprof) e_slot += clock64() - e_t2;
+                    if (eprof) FZ_TRACE(4, 3, it, c);
                     store_row_chunk(a_ring + (size_t)slot * p.a_slot_bytes, r, v);
                     tc::fence_proxy_async();
                     tc::mbar_arrive(a_full + slot);
+                    if (eprof) FZ_TRACE(4, 4, it, c);
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 0);
@@ -520,6 +609,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                 // max over the K rows of a group = per-thread max over K columns; bias and ReLU commute
                 // with the max (both monotone) and are applied once per pooled value.
                 tc::mbar_wait(acc_full + 1, it & 1, 61);
+                if (eprof) FZ_TRACE(4, 5, it, 0);
                 if (eprof) { e_t2 = clock64(); e_full1 += e_t2 - e_t; e_t = e_t2; }
                 tc::tc_fence_after();
                 const int64_t rows_left = M - m0;                       // rows >= M do not exist (last tile)
@@ -559,6 +649,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 1);
                 if (eprof) e_pool += clock64() - e_t;
+                if (eprof) FZ_TRACE(4, 6, it, 0);
             }
         }
         if (eprof) {
@@ -592,7 +683,7 @@ static FusedPlan fused_plan(int mode, const int32_t *cout) {
     const int ext = pl.col[1] + 128 * pl.mb3;                 // layer 3: one 128-column (= 128 rows) block per 128 channels
     pl.ok = cout[0] <= 256 && cout[1] <= 256 && ext <= 512;
     pl.occ = ext <= 256 ? 2 : 1;
-    pl.kc = (pl.occ == 2 && mode == FZ_MODE_TF32X3) ? 16 : 32;
+    pl.kc = (pl.occ == 2 && mode != FZ_MODE_BF16) ? 16 : 32;
     pl.tmem_cols = 32;
     while (pl.tmem_cols < ext) pl.tmem_cols *= 2;
     return pl;
@@ -613,7 +704,7 @@ extern "C" int ev2h_fused_set_debug_buffer(void *buf) { ev2h::g_fused_dbg = (lon
 
 extern "C" int ev2h_sa_msg_fused_kc(int mode, const int32_t *cout_host) {
     using namespace ev2h;
-    if (!cout_host || (mode != FZ_MODE_BF16 && mode != FZ_MODE_TF32X3)) return -1;
+    if (!cout_host || (mode != FZ_MODE_BF16 && mode != FZ_MODE_TF32X3 && mode != FZ_MODE_MIXED)) return -1;
     const FusedPlan pl = fused_plan(mode, cout_host);
     return pl.ok ? pl.kc : -1;
 }
@@ -627,7 +718,7 @@ extern "C" int ev2h_sa_msg_fused_tc(
     using namespace ev2h;
     EV2H_REQUIRE(idx && centres_rows && out_rows && cout_host && w_packed_host && bias_host, "ev2h_sa_msg_fused_tc: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0 && k_off >= 0 && k_off + K <= idx_ld && c1 > 0, "ev2h_sa_msg_fused_tc: bad sizes");
-    EV2H_REQUIRE(mode == FZ_MODE_BF16 || mode == FZ_MODE_TF32X3, "ev2h_sa_msg_fused_tc: unknown mode %d", mode);
+    EV2H_REQUIRE(mode == FZ_MODE_BF16 || mode == FZ_MODE_TF32X3 || mode == FZ_MODE_MIXED, "ev2h_sa_msg_fused_tc: unknown mode %d", mode);
     if (K != 32 && K != 64 && K != 128)
         return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: K=%d (supported: 32, 64, 128)", K);
     const bool per_point = P != nullptr;
@@ -691,6 +782,11 @@ extern "C" int ev2h_sa_msg_fused_tc(
     const int64_t slots = (int64_t)sms * occ;
     const unsigned grid = (unsigned)(n_tiles < slots ? n_tiles : slots);
     cudaStream_t st = as_stream(stream);
+    if (mode == FZ_MODE_MIXED) {
+        if (KC == 16) return occ == 2 ? launch_fused<FZ_MODE_MIXED, 16, 1, 2>(p, smem, grid, st)
+                                      : launch_fused<FZ_MODE_MIXED, 16, 1, 1>(p, smem, grid, st);
+        return launch_fused<FZ_MODE_MIXED, 32, 2, 1>(p, smem, grid, st);
+    }
     if (mode == FZ_MODE_TF32X3) {
         if (KC == 16) return occ == 2 ? launch_fused<FZ_MODE_TF32X3, 16, 1, 2>(p, smem, grid, st)
                                       : launch_fused<FZ_MODE_TF32X3, 16, 1, 1>(p, smem, grid, st);

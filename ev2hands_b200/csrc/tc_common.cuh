@@ -227,6 +227,12 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// two fp32 -> packed bf16x2 (round to nearest even), first value in the low half
+__device__ __forceinline__ uint32_t bf16x2(float lo_half, float hi_half) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_half), "f"(lo_half));
+    return d;
+}
 // two fp32 -> (hi, lo) pairs; the subtraction is one packed instruction
 __device__ __forceinline__ void split_tf32x2(float x0, float x1, float &h0, float &h1, float &l0, float &l1) {
     uint32_t a, b;

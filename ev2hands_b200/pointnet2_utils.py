@@ -44,6 +44,9 @@ _mlp_precision = os.environ.get("EV2H_MLP", "tf32x3")
 # The fused grouping + MLP + max-pool kernel (sa_fused_tc.cu) is used for every scale it
 # covers when a tensor-core precision is selected; EV2H_FUSED=0 forces the layer-by-layer path.
 _FUSED_ENABLED = os.environ.get("EV2H_FUSED", "1") != "0"
+# fp32-level precision ("tf32x3") in the fused kernel: tf32 hi*hi + bf16 correction products (default), or
+# three tf32 products with EV2H_TF32X3_PURE=1.
+_TF32X3_PURE = os.environ.get("EV2H_TF32X3_PURE", "0") == "1"
 # Evaluate layer 1 per point (instead of per gathered row) also for narrow inputs; experiment switch.
 _PER_POINT_ALWAYS = os.environ.get("EV2H_PER_POINT", "0") == "1"
 
@@ -317,12 +320,13 @@ class PointNetSetAbstractionMsg(nn.Module):
         c_total = sum(convs[-1].out_channels for convs in self.conv_blocks)
         out_rows = torch.zeros((B, S, c_total), dtype=torch.float32, device=xyz.device)
         mode = {"tf32x3": _capi.TC_TF32X3, "bf16": _capi.TC_BF16}.get(_mlp_precision)
+        fmode = _capi.TC_TF32_BF16C if (mode == _capi.TC_TF32X3 and not _TF32X3_PURE) else mode   # fused kernel's mode
         all_layers = [self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]) for i in range(len(self.nsample_list))]
         widths = [[L["cout"] for L in layers] for layers in all_layers]
 
         # Which scales can run in the fused tensor-core kernel, and with which first-layer mode.
         per_point = D + 3 > 8 or _PER_POINT_ALWAYS
-        fused = [mode is not None and _FUSED_ENABLED and _capi.fused_supported(K, w, D + 3, per_point, mode)
+        fused = [mode is not None and _FUSED_ENABLED and _capi.fused_supported(K, w, D + 3, per_point, fmode)
                  for K, w in zip(self.nsample_list, widths)]
 
         pts8 = P = C = None
@@ -375,20 +379,20 @@ class PointNetSetAbstractionMsg(nn.Module):
             layers = all_layers[i]
             if fused[i]:
                 use = layers[1:]      # layer 1: per point (wide inputs) or in the loader warps (<= 8 channels)
-                kc = _capi.fused_kc(mode, [L["cout"] for L in use])
+                kc = _capi.fused_kc(fmode, [L["cout"] for L in use])
                 packed = []
                 for li, L in enumerate(use):
                     # the last layer's weights are the UMMA A operand (output channels = TMEM lanes): 128-row images
-                    key = (mode, kc, 128 if li == 1 else 16)
+                    key = (fmode, kc, 128 if li == 1 else 16)
                     if key not in L["packed"]:
-                        L["packed"][key] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], mode, kc, key[2])
+                        L["packed"][key] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], fmode, kc, key[2])
                     packed.append(L["packed"][key])
                 _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D,
                                    None if per_point else layers[0]["wt"], None if per_point else layers[0]["bias"],
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
                                    C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
                                    layers[0]["cout"], [L["cout"] for L in use], packed, [L["bias"] for L in use],
-                                   out_rows, c_total, col, mode)
+                                   out_rows, c_total, col, fmode)
             else:
                 if feats_rows is None and points is not None:
                     feats_rows = _to_rows(points)

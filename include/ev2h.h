@@ -168,6 +168,10 @@ EV2H_API int ev2h_linear_f32(const float *x, int64_t M, int ld_x, int Cin, const
  *   EV2H_TC_BF16   (0)  operands rounded to bf16, fp32 accumulate  (feature bar 1e-2)
  *   EV2H_TC_TF32X3 (1)  error-compensated split x = hi + lo, w = hi + lo, three tf32 products,
  *                       fp32 accumulate: fp32-level accuracy     (feature bar 1e-5)
+ *   EV2H_TC_TF32_BF16C (2)  the same split with hi*hi in tf32 and the two correction products
+ *                       x_lo*w_hi + x_hi*w_lo on bf16 copies (their 2^-9 rounding is 2^-20 of the result):
+ *                       fp32-level accuracy at two thirds of the tensor work (feature bar 1e-5).
+ *                       Accepted by ev2h_sa_msg_fused_tc and by ev2h_tc_pack_weights_kc for its weights.
  * Weights must first be packed from the folded layout (wt, ld_w = round_up(Cout,128) as
  * written by ev2h_fold_conv_bn_f32) into the kernel's shared-memory image:
  * ev2h_tc_packed_bytes gives the buffer size, ev2h_tc_pack_weights fills it.
@@ -175,6 +179,7 @@ EV2H_API int ev2h_linear_f32(const float *x, int64_t M, int ld_x, int Cin, const
  * other shapes return EV2H_ERR_UNSUPPORTED (callers use ev2h_linear_relu_f32 for those). */
 #define EV2H_TC_BF16 0
 #define EV2H_TC_TF32X3 1
+#define EV2H_TC_TF32_BF16C 2
 EV2H_API int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode);
 EV2H_API int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
                                   ev2h_stream_t stream);
@@ -211,7 +216,7 @@ EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, c
  * Layers 2 and 3 run on the tensor cores: cout_host[2] their widths, w_packed_host[2] their
  * ev2h_tc_pack_weights_kc images (kc from ev2h_sa_msg_fused_kc), bias_host[2] their folded biases
  * (device pointers in host arrays).  out_rows [B*S, ld_out]: the pooled features of this scale
- * are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3. */
+ * are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3 / EV2H_TC_TF32_BF16C. */
 EV2H_API int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
     const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
