@@ -181,6 +181,8 @@ sa_fused_tc_kernel(const FusedParams p) {
     // Warp roles, lowest to highest warp id = lowest to highest scheduler priority: loaders (work with
     // slack), weight streamer, UMMA issuer, and the epilogue warps, which are the serial bottleneck of a tile.
     constexpr int STREAMER_WARP = 4 * LG, ISSUER_WARP = 4 * LG + 1, EPI_WARP0 = 4 * LG + 2;
+    const int loader_idx = warp;
+    const bool is_loader = warp < STREAMER_WARP;
     if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc::tc_fence_before();
     __syncthreads();
@@ -232,9 +234,9 @@ sa_fused_tc_kernel(const FusedParams p) {
         }
     };
 
-    if (warp < STREAMER_WARP) {
+    if (is_loader) {
         // =============================== loaders: layer 2's operand rows ===============================
-        const int grp = warp >> 2, wq = warp & 3;
+        const int grp = loader_idx >> 2, wq = loader_idx & 3;
         uint64_t *my_grants = a_grant + grp * FZ_MAX_RING;
         uint32_t bits = 0;
         auto mine = [&](uint32_t it, int kc) { return (int)((it * (uint32_t)nc0 + (uint32_t)kc) % LG) == grp; };
@@ -427,128 +429,113 @@ sa_fused_tc_kernel(const FusedParams p) {
         __syncwarp();
     } else if (warp == ISSUER_WARP) {
         // =============================== UMMA issuer ===============================
-        // The whole warp walks the chunk sequence (so every value below is warp-uniform and the
-        // descriptor arithmetic stays on the uniform datapath); one elected lane issues.
-        Ring ra{0, 0, p.sa}, rb{0, 0, p.sb};
-        // (tile iteration, position in tile) of the chunk that will reuse the slot being freed: sa chunks ahead
-        uint32_t g_it = (uint32_t)p.sa / Q, g_q = (uint32_t)p.sa % Q;
-        uint32_t it = 0;
-        const bool prof = p.dbg != nullptr;
-        long long w_a[2] = {0, 0}, w_b = 0, w_acc = 0, w_commit = 0, t0 = 0, t1 = 0;
-        const long long t_begin = prof ? clock64() : 0;
-        const uint32_t a_lbo = CHUNK_ROWS_BYTES, sbo = 128;
-        const uint32_t desc_hi = tc::smem_desc_hi(sbo);
-        const uint32_t a_ring_addr = tc::smem_u32(a_ring), b_ring_addr = tc::smem_u32(b_ring);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            for (int g = 0; g < FZ_GEMMS; ++g) {
-                // g == 0: D[rows x n0]      = X[rows x K] * W2[n0 x K]^T      (A = activations, B = weights)
-                // g == 1: D[chan x rows]^T: per 128-channel block  D = W3[128 x K] * X[rows x K]^T  (A = weights, B = activations)
-                const uint32_t w_rows = g == 0 ? (uint32_t)p.n[0] : 128u * (uint32_t)p.mb3;
-                const uint32_t n_umma = g == 0 ? (uint32_t)p.n[0] : (uint32_t)FZ_BLOCK_M;
-                const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M, n_umma);
-                const uint32_t idesc16 = tc::instr_desc(tc::FMT_BF16, FZ_BLOCK_M, n_umma);     // MIXED: the correction products
-                const uint32_t b_lbo = w_rows * 16;
-                const uint32_t b_part = w_rows * KC * EB;
-                const uint32_t d_tmem = tmem_base + (uint32_t)p.tmem_col[g];
-                const int n_chunks = p.n_chunks[g];
-                if (prof) t0 = clock64();
-                tc::mbar_wait(acc_empty + g, (it & 1) ^ 1, 30 + g);       // previous tile's epilogue drained this accumulator
-                if (lane == 0) FZ_TRACE(3, 1, it, g * 50);
-                if (prof) w_acc += clock64() - t0;
-                tc::tc_fence_after();
-                for (int c = 0; c < n_chunks; ++c) {
-                    if (prof) t0 = clock64();
-                    tc::mbar_wait(a_full + ra.slot, ra.phase, 40 + g);
-                    if (prof) { t1 = clock64(); w_a[g] += t1 - t0; }
-                    if (lane == 0) FZ_TRACE(3, 2, it, g * 50 + c);
-                    tc::mbar_wait(b_full + rb.slot, rb.phase, 50 + g);
-                    if (lane == 0) FZ_TRACE(3, 3, it, g * 50 + c);
-                    if (prof) w_b += clock64() - t1;
+        // ONE thread walks the chunk sequence; its per-chunk latency bounds the whole kernel (every chunk of
+        // every tile passes through it), so everything loop invariant is hoisted into registers, barriers are
+        // addressed in the shared window directly and the K steps of a full chunk are straight-line code.
+        if (lane == 0) {
+            const uint32_t sa = (uint32_t)p.sa, sb = (uint32_t)p.sb, mb3 = (uint32_t)p.mb3;
+            const uint32_t a_full_u = tc::smem_u32(a_full), a_grant_u = tc::smem_u32(a_grant), b_full_u = tc::smem_u32(b_full),
+                           b_empty_u = tc::smem_u32(b_empty), acc_full_u = tc::smem_u32(acc_full), acc_empty_u = tc::smem_u32(acc_empty);
+            const uint32_t desc_hi = tc::smem_desc_hi(128);
+            const uint32_t a_slot_d = (uint32_t)p.a_slot_bytes >> 4, b_slot_d = (uint32_t)p.b_slot_bytes >> 4;
+            const uint32_t a_base = tc::smem_desc_lo(tc::smem_u32(a_ring), CHUNK_ROWS_BYTES);
+            const uint32_t b_ring_d = (tc::smem_u32(b_ring) >> 4) & 0x3fff;
+            constexpr uint32_t a_step = (2 * CHUNK_ROWS_BYTES) >> 4;      // one K step = two 16-byte chunks further along K
+            constexpr uint32_t A_PART_D = A_PART >> 4, A_B16_D = A_B16 >> 4;
+            const uint32_t nch[2] = {(uint32_t)nc0, (uint32_t)nc1}, ksl[2] = {(uint32_t)p.k_steps_last[0], (uint32_t)p.k_steps_last[1]};
+            const uint32_t wr[2] = {(uint32_t)p.n[0], 128u * mb3};
+            const uint32_t dt[2] = {tmem_base + (uint32_t)p.tmem_col[0], tmem_base + (uint32_t)p.tmem_col[1]};
+            uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+            // (tile iteration, position in tile) of the chunk that will reuse the slot being freed: sa chunks ahead
+            uint32_t g_it = sa / Q, g_q = sa % Q;
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+#pragma unroll
+                for (int g = 0; g < FZ_GEMMS; ++g) {
+                    // g == 0: D[rows x n0]      = X[rows x K] * W2[n0 x K]^T      (A = activations, B = weights)
+                    // g == 1: D[chan x rows]^T: per 128-channel block  D = W3[128 x K] * X[rows x K]^T  (A = weights, B = activations)
+                    const uint32_t n_umma = g == 0 ? wr[0] : (uint32_t)FZ_BLOCK_M;
+                    const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M, n_umma);
+                    const uint32_t idesc16 = tc::instr_desc(tc::FMT_BF16, FZ_BLOCK_M, n_umma);     // MIXED: the correction products
+                    const uint32_t b_lbo_d = wr[g];                      // (w_rows * 16) >> 4
+                    const uint32_t b_step = 2 * b_lbo_d;
+                    const uint32_t b_part_d = (wr[g] * KC * EB) >> 4;
+                    const uint32_t b_base = b_ring_d | (b_lbo_d << 16);
+                    const uint32_t n_mb = g == 0 ? 1u : mb3;
+                    tc::mbar_wait_u32(acc_empty_u + 8 * g, (it & 1) ^ 1, 30 + g);      // previous tile's epilogue drained this accumulator
+                    FZ_TRACE(3, 1, it, g * 50);
                     tc::tc_fence_after();
-                    const uint32_t a0 = a_ring_addr + (uint32_t)ra.slot * (uint32_t)p.a_slot_bytes;
-                    const uint32_t b0 = b_ring_addr + (uint32_t)rb.slot * (uint32_t)p.b_slot_bytes;
-                    const int ks = (c == n_chunks - 1) ? p.k_steps_last[g] : K_STEPS;
-                    // producer that fills this operand slot next: loader group or the epilogue warps
-                    const uint32_t next_prod = g_q < (uint32_t)nc0 ? (g_it * (uint32_t)nc0 + g_q) % LG : (uint32_t)LG;
-                    if (tc::elect_one()) {
-                        // descriptor low words; one K step = two 16-byte chunks further along K
-                        uint32_t a_hi = tc::smem_desc_lo(a0, a_lbo), b_hi = tc::smem_desc_lo(b0, b_lbo);
-                        const uint32_t a_step = (2 * a_lbo) >> 4, b_step = (2 * b_lbo) >> 4;
-                        const uint32_t a_lo_off = A_PART >> 4, b_lo_off = b_part >> 4;
-                        if (MODE == FZ_MODE_MIXED) {
-                            // hi*hi in tf32 (ks steps of 8 channels), then x_lo*w_hi and x_hi*w_lo on the bf16
-                            // copies (steps of 16 channels); all accumulate into the same fp32 accumulator
-                            const uint32_t a16 = a_hi + (A_PART >> 4), b16 = b_hi + (b_part >> 4);
-                            const uint32_t a16_lo = a16 + (A_B16 >> 4), b16_lo = b16 + (b_part >> 5);
-                            const int ks16 = (ks + 1) >> 1;
-#pragma unroll 1
-                            for (int mb = 0; mb < (g == 0 ? 1 : p.mb3); ++mb) {
-                                const uint32_t wo = g == 0 ? 0u : (uint32_t)mb * ((128u * 16u) >> 4);   // 128 weight rows further
-                                const uint32_t d = d_tmem + (g == 0 ? 0u : (uint32_t)mb * FZ_BLOCK_M);
-#pragma unroll 1
-                                for (int j = 0; j < ks; ++j) {
-                                    const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
-                                    const uint32_t ax = a_hi + j * a_step, bx = b_hi + wo + j * b_step;
-                                    if (g == 0) tc::umma_tf32(d, tc::make_desc(ax, desc_hi), tc::make_desc(bx, desc_hi), idesc, acc);
-                                    else tc::umma_tf32(d, tc::make_desc(bx, desc_hi), tc::make_desc(ax, desc_hi), idesc, acc);
-                                }
-#pragma unroll 1
-                                for (int j = 0; j < ks16; ++j) {
-                                    const uint32_t ao = j * a_step, bo = wo + j * b_step;
-                                    if (g == 0) {
-                                        tc::umma_f16(d, tc::make_desc(a16_lo + ao, desc_hi), tc::make_desc(b16 + bo, desc_hi), idesc16, 1u);
-                                        tc::umma_f16(d, tc::make_desc(a16 + ao, desc_hi), tc::make_desc(b16_lo + bo, desc_hi), idesc16, 1u);
-                                    } else {
-                                        tc::umma_f16(d, tc::make_desc(b16 + bo, desc_hi), tc::make_desc(a16_lo + ao, desc_hi), idesc16, 1u);
-                                        tc::umma_f16(d, tc::make_desc(b16_lo + bo, desc_hi), tc::make_desc(a16 + ao, desc_hi), idesc16, 1u);
-                                    }
-                                }
-                            }
+                    // one product: x = activation operand, w = weight operand (descriptor low words)
+                    auto mma = [&](bool k16, uint32_t d, uint32_t x, uint32_t w, uint32_t acc) {
+                        const uint64_t dx = tc::make_desc(x, desc_hi), dw = tc::make_desc(w, desc_hi);
+                        if (k16) { if (g == 0) tc::umma_f16(d, dx, dw, idesc16, acc); else tc::umma_f16(d, dw, dx, idesc16, acc); }
+                        else if (MODE == FZ_MODE_BF16) { if (g == 0) tc::umma_f16(d, dx, dw, idesc, acc); else tc::umma_f16(d, dw, dx, idesc, acc); }
+                        else { if (g == 0) tc::umma_tf32(d, dx, dw, idesc, acc); else tc::umma_tf32(d, dw, dx, idesc, acc); }
+                    };
+                    // the products of K step j (8 tf32 / 16 bf16 channels) of one chunk into accumulator block mb
+                    auto k_step = [&](uint32_t x0, uint32_t w0, uint32_t mb, uint32_t j, uint32_t acc) {
+                        const uint32_t d = dt[g] + mb * FZ_BLOCK_M, x = x0 + j * a_step, w = w0 + mb * 128u + j * b_step;
+                        if (MODE == FZ_MODE_TF32X3) {
+                            mma(false, d, x + A_PART_D, w, acc);
+                            mma(false, d, x, w + b_part_d, 1u);
+                            mma(false, d, x, w, 1u);
                         } else {
-#pragma unroll 1
-                        for (int j = 0; j < ks; ++j) {
-                            const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
-                            if (g == 0) {
-                                if (MODE == FZ_MODE_TF32X3) {
-                                    tc::umma_tf32(d_tmem, tc::make_desc(a_hi + a_lo_off, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
-                                    tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi + b_lo_off, desc_hi), idesc, 1u);
-                                    tc::umma_tf32(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, 1u);
-                                } else {
-                                    tc::umma_f16(d_tmem, tc::make_desc(a_hi, desc_hi), tc::make_desc(b_hi, desc_hi), idesc, acc);
-                                }
-                            } else {
-                                for (int mb = 0; mb < p.mb3; ++mb) {
-                                    const uint32_t w = b_hi + (uint32_t)mb * ((128u * 16u) >> 4);   // 128 weight rows further
-                                    const uint32_t d = d_tmem + (uint32_t)mb * FZ_BLOCK_M;
-                                    if (MODE == FZ_MODE_TF32X3) {
-                                        tc::umma_tf32(d, tc::make_desc(w + b_lo_off, desc_hi), tc::make_desc(a_hi, desc_hi), idesc, acc);
-                                        tc::umma_tf32(d, tc::make_desc(w, desc_hi), tc::make_desc(a_hi + a_lo_off, desc_hi), idesc, 1u);
-                                        tc::umma_tf32(d, tc::make_desc(w, desc_hi), tc::make_desc(a_hi, desc_hi), idesc, 1u);
-                                    } else {
-                                        tc::umma_f16(d, tc::make_desc(w, desc_hi), tc::make_desc(a_hi, desc_hi), idesc, acc);
+                            mma(false, d, x, w, acc);
+                        }
+                    };
+                    // MIXED: correction products of 16-channel step j on the bf16 copies
+                    auto k_step16 = [&](uint32_t x0, uint32_t w0, uint32_t mb, uint32_t j) {
+                        const uint32_t d = dt[g] + mb * FZ_BLOCK_M;
+                        const uint32_t x = x0 + A_PART_D + j * a_step, w = w0 + b_part_d + mb * 128u + j * b_step;
+                        mma(true, d, x + A_B16_D, w, 1u);                    // x_lo * w_hi
+                        mma(true, d, x, w + (b_part_d >> 1), 1u);            // x_hi * w_lo
+                    };
+                    for (uint32_t c = 0; c < nch[g]; ++c) {
+                        tc::mbar_wait_u32(a_full_u + 8 * a_slot, a_phase, 40 + g);
+                        FZ_TRACE(3, 2, it, g * 50 + c);
+                        tc::mbar_wait_u32(b_full_u + 8 * b_slot, b_phase, 50 + g);
+                        FZ_TRACE(3, 3, it, g * 50 + c);
+                        tc::tc_fence_after();
+                        const uint32_t x0 = a_base + a_slot * a_slot_d, w0 = b_base + b_slot * b_slot_d;
+                        const uint32_t acc0 = c > 0 ? 1u : 0u;
+                        if (c + 1 < nch[g] || ksl[g] == (uint32_t)K_STEPS) {
+#pragma unroll
+                            for (uint32_t mb = 0; mb < 2; ++mb) {
+                                if (mb < n_mb) {
+#pragma unroll
+                                    for (uint32_t j = 0; j < (uint32_t)K_STEPS; ++j) k_step(x0, w0, mb, j, j > 0 ? 1u : acc0);
+                                    if (MODE == FZ_MODE_MIXED) {
+#pragma unroll
+                                        for (uint32_t j = 0; j < (uint32_t)K_STEPS / 2; ++j) k_step16(x0, w0, mb, j);
                                     }
                                 }
                             }
-                            a_hi += a_step; b_hi += b_step;
+                        } else {                                             // last, partial chunk
+                            const uint32_t ks = ksl[g];
+                            for (uint32_t mb = 0; mb < n_mb; ++mb) {
+#pragma unroll 1
+                                for (uint32_t j = 0; j < ks; ++j) k_step(x0, w0, mb, j, j > 0 ? 1u : acc0);
+                                if (MODE == FZ_MODE_MIXED) {
+#pragma unroll 1
+                                    for (uint32_t j = 0; j < (ks + 1) / 2; ++j) k_step16(x0, w0, mb, j);
+                                }
+                            }
                         }
-                        }
-                        if (prof) t0 = clock64();
-                        tc::umma_commit(a_grant + next_prod * FZ_MAX_RING + ra.slot);
-                        tc::umma_commit(b_empty + rb.slot);
-                        if (c == n_chunks - 1) tc::umma_commit(acc_full + g);
-                        if (prof) w_commit += clock64() - t0;
+                        FZ_TRACE(3, 6, it, g * 50 + c);
+                        // the producer that fills this operand slot next: a loader group or the epilogue warps
+                        const uint32_t next_prod = g_q < (uint32_t)nc0 ? (LG == 1 ? 0u : (g_it * (uint32_t)nc0 + g_q) % LG) : (uint32_t)LG;
+                        tc::umma_commit_u32(a_grant_u + 8 * (next_prod * FZ_MAX_RING + a_slot));
+                        tc::umma_commit_u32(b_empty_u + 8 * b_slot);
+                        if (c + 1 == nch[g]) tc::umma_commit_u32(acc_full_u + 8 * g);
+                        FZ_TRACE(3, 7, it, g * 50 + c);
+                        if (++a_slot == sa) { a_slot = 0; a_phase ^= 1; }
+                        if (++b_slot == sb) { b_slot = 0; b_phase ^= 1; }
+                        if (++g_q == Q) { g_q = 0; ++g_it; }
                     }
-                    __syncwarp();
-                    if (lane == 0) FZ_TRACE(3, 4, it, g * 50 + c);
-                    ra.advance(); rb.advance();
-                    if (++g_q == Q) { g_q = 0; ++g_it; }
                 }
             }
         }
-        if (prof && lane == 0) {
-            long long *d = p.dbg + (size_t)blockIdx.x * 16;
-            d[0] = w_a[0]; d[1] = w_a[1]; d[2] = 0; d[3] = w_b; d[4] = w_acc; d[5] = clock64() - t_begin; d[6] = it; d[7] = w_commit;
-        }
+        __syncwarp();
     } else {
         // =============================== epilogue warps ===============================
         const int q = warp & 3, r = q * 32 + lane;       // TMEM lane quadrant of a warp is warp_id % 4
@@ -556,19 +543,15 @@ sa_fused_tc_kernel(const FusedParams p) {
         uint64_t *my_grants = a_grant + LG * FZ_MAX_RING;
         uint32_t bits = 0;
         uint32_t it = 0;
-        const bool eprof = p.dbg != nullptr && warp == EPI_WARP0 && lane == 0;
-        long long e_full0 = 0, e_conv = 0, e_slot = 0, e_full1 = 0, e_pool = 0, e_t = 0, e_t2 = 0;
-        const long long e_begin = eprof ? clock64() : 0;
+        const bool eprof = warp == EPI_WARP0 && lane == 0;    // traces only
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int64_t m0 = tile * FZ_BLOCK_M;
             {
                 // ---- layer 2 activations -> operand chunks of layer 3 ----
                 const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[0] + ((uint32_t)(q * 32) << 16);
                 const float *bias_g = bias_s + p.bias_off[0];
-                if (eprof) e_t = clock64();
                 tc::mbar_wait(acc_full + 0, it & 1, 60);
                 if (eprof) FZ_TRACE(4, 1, it, 0);
-                if (eprof) { e_t2 = clock64(); e_full0 += e_t2 - e_t; e_t = e_t2; }
                 tc::tc_fence_after();
                 for (int c = 0; c < nc1; ++c) {
                     uint32_t raw[KC];
@@ -590,10 +573,8 @@ sa_fused_tc_kernel(const FusedParams p) {
                         for (int j = 0; j < KC; ++j)
                             if (c * KC + j >= p.n[0]) v[j] = 0.f;
                     }
-                    if (eprof) e_t2 = clock64();
                     if (eprof) FZ_TRACE(4, 2, it, c);
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)(nc0 + c), p.sa, bits, 70);
-                    if (eprof) e_slot += clock64() - e_t2;
                     if (eprof) FZ_TRACE(4, 3, it, c);
                     store_row_chunk(a_ring + (size_t)slot * p.a_slot_bytes, r, v);
                     tc::fence_proxy_async();
@@ -602,7 +583,6 @@ sa_fused_tc_kernel(const FusedParams p) {
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 0);
-                if (eprof) { e_t2 = clock64(); e_conv += e_t2 - e_t; e_t = e_t2; }
             }
             {
                 // ---- layer 3 (transposed accumulator): lane = output channel, columns = the tile's rows.
@@ -610,7 +590,6 @@ sa_fused_tc_kernel(const FusedParams p) {
                 // with the max (both monotone) and are applied once per pooled value.
                 tc::mbar_wait(acc_full + 1, it & 1, 61);
                 if (eprof) FZ_TRACE(4, 5, it, 0);
-                if (eprof) { e_t2 = clock64(); e_full1 += e_t2 - e_t; e_t = e_t2; }
                 tc::tc_fence_after();
                 const int64_t rows_left = M - m0;                       // rows >= M do not exist (last tile)
                 for (int mb = 0; mb < p.mb3; ++mb) {
@@ -648,13 +627,8 @@ sa_fused_tc_kernel(const FusedParams p) {
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 1);
-                if (eprof) e_pool += clock64() - e_t;
                 if (eprof) FZ_TRACE(4, 6, it, 0);
             }
-        }
-        if (eprof) {
-            long long *d = p.dbg + (size_t)blockIdx.x * 16 + 8;
-            d[0] = e_full0; d[1] = e_conv; d[2] = e_slot; d[3] = e_full1; d[4] = e_pool; d[5] = clock64() - e_begin;
         }
     }
 

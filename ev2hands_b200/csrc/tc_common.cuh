@@ -75,6 +75,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
     }
 }
 
+// The same wait / commit on a shared-window address (no generic -> shared conversion per call)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity, int tag = 0) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    for (;;) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return;
+        if ((++spins & 15u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(tag, parity);   // ~2 s
+    }
+}
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (UMMA operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
