@@ -43,6 +43,7 @@
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace ev2h {
 
@@ -657,6 +658,7 @@ static FusedPlan fused_plan(int mode, const int32_t *cout) {
     const int ext = pl.col[1] + 128 * pl.mb3;                 // layer 3: one 128-column (= 128 rows) block per 128 channels
     pl.ok = cout[0] <= 256 && cout[1] <= 256 && ext <= 512;
     pl.occ = ext <= 256 ? 2 : 1;
+    if (const char *e = getenv("EV2H_FUSED_OCC")) { if (e[0] == '1') pl.occ = 1; }     // experiment switch: one CTA per SM, 32-channel chunks
     pl.kc = (pl.occ == 2 && mode != FZ_MODE_BF16) ? 16 : 32;
     pl.tmem_cols = 32;
     while (pl.tmem_cols < ext) pl.tmem_cols *= 2;
