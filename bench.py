@@ -266,8 +266,37 @@ def run_ours(args):
     barrier()
     e2e_ms = float(sum(a.elapsed_time(b) for a, b in e_evs))
 
+    # ---- optional secondary number: encoder + feature-propagation decoder, same timing rules
+    dec_ms = 0.0
+    if args.with_decoder:
+        from ev2hands_b200.encoder import load_numpy_state
+        dec = e2h.FeaturePropagationDecoder()
+        for i, n in enumerate(("fp3", "fp2", "fp1")):
+            load_numpy_state(getattr(dec, n), synth.random_state_for(synth.DECODER_SPECS[n], seed=300 + i))
+        dec = dec.to(device).eval()
+        l3_xyz = torch.zeros((B, 3, 1), dtype=torch.float32, device=device)
+
+        def step_dec():
+            with torch.no_grad():
+                l3, lv = enc(ev_dev, fps_starts=(s1, s2), return_levels=True)
+                return dec(ev_dev[:, :3, :], lv["l1_xyz"], lv["l2_xyz"], l3_xyz, lv["l1_points"], lv["l2_points"], l3.unsqueeze(-1))
+
+        for _ in range(3):
+            step_dec()
+        barrier()
+        d_evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_dec()
+            b.record()
+            d_evs.append((a, b))
+        barrier()
+        dec_ms = float(sum(a.elapsed_time(b) for a, b in d_evs))
+
     # ---- max over ranks
-    total_ms, e2e_ms = sharding.max_over_ranks([total_ms, e2e_ms], device=device)
+    total_ms, e2e_ms, dec_ms = sharding.max_over_ranks([total_ms, e2e_ms, dec_ms], device=device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -298,7 +327,7 @@ def run_ours(args):
         "config": {"workload": "encoder forward sa1->sa2->sa3 (TEHNet.py:172-181), %d windows per GPU, "
                                "N=%d points/window, 5 channels, random-init weights, eval mode" % (B, args.points),
                    "windows_per_gpu": B, "global_windows": B * world,
-                   "mlp_path": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 kind::tf32, 3-product split (fp32-level accuracy)",
+                   "mlp_path": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 3-product split x=hi+lo, w=hi+lo: tf32 hi*hi + two bf16 correction products (fp32-level accuracy)",
                                 "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate"}[args.mlp],
                    "l2": "256 MiB buffer written between timed steps (L2 flush)"},
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
@@ -315,6 +344,9 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks, "wall_s": wall,
         "checksum": float(out.double().sum().item()),
     }
+    if args.with_decoder:
+        line["secondary"] = {"metric": "encoder + fp3/fp2/fp1 decoder event-windows/s (TEHNet.py:172-186)",
+                             "value": windows / (dec_ms / 1e3), "unit": "windows/s", "ms_per_step": dec_ms / args.steps}
     if world == 1 and not args.no_cpu_baseline:
         wps, threads, times = time_cpu_oracle(4, 3, 1)
         line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": threads, "kind": "port",
@@ -334,6 +366,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-decoder", action="store_true", help="also time encoder + feature-propagation decoder (secondary number)")
     ap.add_argument("--points", type=int, default=N_POINTS, help="events per window (2048 = the model's default; 16384 = config 5)")
     ap.add_argument("--mlp", choices=["fp32", "tf32x3", "bf16"], default=os.environ.get("EV2H_MLP", "tf32x3"),
                     help="arithmetic of the shared MLP: fp32 = CUDA-core FFMA, tf32x3 = tensor cores with fp32-level "

@@ -44,6 +44,8 @@ _SIGNATURES = {
                              c_vp, c_int, c_int, c_vp, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                              c_vp, c_int, c_int, c_int, c_vp],
+    "ev2h_three_nn_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "ev2h_three_interp_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_group_max_bwd_f32": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
 }
@@ -363,3 +365,25 @@ def group_max_bwd(grad_out: torch.Tensor, arg: torch.Tensor, K: int) -> torch.Te
             _check(lib().ev2h_group_max_bwd_f32(_p(grad_out), _p(arg), B, C, K, S, _p(gx), _stream(gx)),
                "ev2h_group_max_bwd_f32")
     return gx
+
+
+def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """xyz1 [B,3,N] queries, xyz2 [B,3,S] sources (channel-first, any strides) ->
+    (idx int32 [B,N,3], weight fp32 [B,N,3]): three nearest sources and inverse-distance weights."""
+    B, _, N = xyz1.shape
+    S = xyz2.shape[2]
+    idx = torch.empty((B, N, 3), dtype=torch.int32, device=xyz1.device)
+    w = torch.empty((B, N, 3), dtype=torch.float32, device=xyz1.device)
+    with torch.cuda.device(xyz1.device):
+        with _timed("ev2h_three_nn_f32"):
+            _check(lib().ev2h_three_nn_f32(_p(xyz1), xyz1.stride(0), xyz1.stride(1), xyz1.stride(2),
+                                           _p(xyz2), xyz2.stride(0), xyz2.stride(1), xyz2.stride(2),
+                                           B, N, S, _p(idx), _p(w), _stream(xyz1)), "ev2h_three_nn_f32")
+    return idx, w
+
+
+def three_interp(feats_rows, ld_f, idx, weight, B, N, S, D, out_rows, ld_out, col):
+    with torch.cuda.device(out_rows.device):
+        with _timed("ev2h_three_interp_f32"):
+            _check(lib().ev2h_three_interp_f32(_p(feats_rows), ld_f, _p(idx), _p(weight), B, N, S, D, _p(out_rows), ld_out, col,
+                                               _stream(out_rows)), "ev2h_three_interp_f32")

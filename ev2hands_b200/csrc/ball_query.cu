@@ -10,6 +10,7 @@
 // Bit-exactness with the reference lives in sqdist_expanded(): same expression,
 // same rounding order as aten's  -2*matmul + |q|^2 + |p|^2  (see SURVEY.md 7.1).
 #include "common.cuh"
+#include "geom.cuh"
 
 namespace ev2h {
 
@@ -25,21 +26,6 @@ struct BallParams {
     int k_total;
     float r2_max;
 };
-
-__device__ __forceinline__ float sq_norm3(float x, float y, float z) {
-    // torch.sum(v ** 2, -1): (x*x + y*y) + z*z, nothing fused
-    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
-}
-
-__device__ __forceinline__ float sqdist_expanded(float qx, float qy, float qz, float qn, const float4 p) {
-    float dot = __fmul_rn(qx, p.x);          // sgemm with K = 3: x*x', then two FMAs
-    dot = __fmaf_rn(qy, p.y, dot);
-    dot = __fmaf_rn(qz, p.z, dot);
-    float t = __fmul_rn(-2.0f, dot);         // dist = -2 * matmul           (:37)
-    t = __fadd_rn(t, qn);                    // dist += sum(src**2)          (:38)
-    t = __fadd_rn(t, p.w);                   // dist += sum(dst**2)          (:39)
-    return t;
-}
 
 // One CTA = kBqCentres centres of one window x kBqSegs point segments.  Lanes of a warp are 32
 // different centres looking at the SAME point (a broadcast shared-memory read); the warps of a CTA

@@ -11,7 +11,7 @@ import os
 import torch
 import torch.nn as nn
 
-from .pointnet2_utils import PointNetSetAbstraction, PointNetSetAbstractionMsg
+from .pointnet2_utils import PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg
 
 
 class SetAbstractionEncoder(nn.Module):
@@ -43,6 +43,23 @@ class SetAbstractionEncoder(nn.Module):
         if return_levels:
             return out, {"l1_xyz": l1_xyz, "l1_points": l1_points, "l2_xyz": l2_xyz, "l2_points": l2_points}
         return out
+
+
+class FeaturePropagationDecoder(nn.Module):
+    """fp3 -> fp2 -> fp1 as TEHNet wires them (constructor arguments TEHNet.py:130-133, data flow :184-186):
+    the encoder's three levels -> per-point features [B, 256, N] (the input of the segmentation classifier)."""
+
+    def __init__(self):
+        super().__init__()
+        self.fp3 = PointNetFeaturePropagation(in_channel=1536, mlp=[256, 256])
+        self.fp2 = PointNetFeaturePropagation(in_channel=576, mlp=[256, 128])
+        self.fp1 = PointNetFeaturePropagation(128, [128, 128, 256])
+
+    def forward(self, l0_xyz, l1_xyz, l2_xyz, l3_xyz, l1_points, l2_points, l3_points, return_levels=False):
+        l2_up = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
+        l1_up = self.fp2(l1_xyz, l2_xyz, l1_points, l2_up)
+        l0_up = self.fp1(l0_xyz, l1_xyz, None, l1_up)
+        return (l0_up, l1_up, l2_up) if return_levels else l0_up
 
 
 class RegressorSetAbstraction(nn.Module):

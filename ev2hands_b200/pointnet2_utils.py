@@ -222,7 +222,11 @@ def _mlp_rows(x, M, ld_x, layers, pool_rows, out, ld_out, out_col):
         else:
             ld_y, col = _pad4(cout), 0
             y = torch.empty((M, ld_y), dtype=torch.float32, device=x.device)
-        if mode is not None and _capi.tc_supported(cout, pool):
+        # The tensor cores' fp32 accumulation error grows with the contraction length (measured: 2e-6 of max|y| at
+        # 515 input channels, 1.1e-5 at 1536); past 1024 channels the fp32-level mode keeps its 1e-5 bar by running
+        # the layer on the CUDA cores in exact fp32 (only fp3's first layer, 1536 channels, is that long).
+        too_long = mode == _capi.TC_TF32X3 and cin > 1024
+        if mode is not None and not too_long and _capi.tc_supported(cout, pool):
             packed = L["packed"].get(mode)
             if packed is None:
                 packed = L["packed"][mode] = _capi.tc_pack(L["wt"], cin, cout, mode)
@@ -514,8 +518,10 @@ class PointNetSetAbstraction(nn.Module):
 
 
 class PointNetFeaturePropagation(nn.Module):
-    """Decoder block (reference :265-315).  Outside the accelerated hot path (SURVEY.md
-    section 8f, row N1): plain PyTorch, kept so the model file can import the name."""
+    """Decoder block (reference :265-315): inverse-distance interpolation of
+    the coarse level's features onto the fine level's points, concat with the skip features, Conv1d +
+    BatchNorm1d + ReLU stack.  ``eval()`` + ``no_grad`` runs the CUDA path (3-NN scan, interpolation written
+    straight into the concat buffer, tensor-core MLP over rows); training keeps the PyTorch formulation."""
 
     def __init__(self, in_channel, mlp):
         super().__init__()
@@ -526,9 +532,50 @@ class PointNetFeaturePropagation(nn.Module):
             self.mlp_convs.append(nn.Conv1d(last, w, 1))
             self.mlp_bns.append(nn.BatchNorm1d(w))
             last = w
+        self._folded = _FoldedMLP()
 
     def forward(self, xyz1, xyz2, points1, points2):
         """xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S] -> [B,D',N]."""
+        S = xyz2.shape[2]
+        if not xyz1.is_cuda:
+            raise RuntimeError("ev2hands_b200 runs on CUDA devices only (xyz1 is on %s); there is no CPU path" % xyz1.device)
+        if _wants_autograd(self, points1, points2) or (S != 1 and S < 3):
+            return self._forward_autograd(xyz1, xyz2, points1, points2)
+        with torch.no_grad():
+            return self._forward_cuda(xyz1, xyz2, points1, points2)
+
+    def _forward_cuda(self, xyz1, xyz2, points1, points2):
+        _check_inputs(xyz1, points1)
+        _check_inputs(xyz2, points2)
+        B, _, N = xyz1.shape
+        S = xyz2.shape[2]
+        D1 = 0 if points1 is None else points1.shape[1]
+        D2 = points2.shape[1]
+        dev = xyz1.device
+        if S == 1:        # points2.repeat(1, N, 1) (:291): the single source with weight 1
+            idx = torch.zeros((B, N, 3), dtype=torch.int32, device=dev)
+            weight = torch.zeros((B, N, 3), dtype=torch.float32, device=dev)
+            weight[:, :, 0] = 1.0
+        else:
+            idx, weight = _capi.three_nn(xyz1, xyz2)
+        self.last_idx, self.last_weight = idx, weight             # exposed for parity tests
+        f2 = _to_rows(points2)                                    # [B,S,ld2]
+        ld_x = _pad4(D1 + D2)
+        # rows = [points1 | interpolated], the order of the reference's cat (:305)
+        x = (torch.zeros if ld_x != D1 + D2 else torch.empty)((B * N, ld_x), dtype=torch.float32, device=dev)
+        if points1 is not None:
+            _capi.transpose(points1, (points1.stride(0), points1.stride(1), points1.stride(2)), B, D1, N, x, N * ld_x, ld_x, 0)
+        _capi.three_interp(f2, f2.shape[2], idx, weight, B, N, S, D2, x, ld_x, D1)
+        layers = self._folded.get(self.mlp_convs, self.mlp_bns)
+        c_out = layers[-1]["cout"]
+        ld_o = _pad4(c_out)
+        out = torch.empty((B, N, ld_o), dtype=torch.float32, device=dev)
+        _mlp_rows(x, B * N, ld_x, layers, 0, out, ld_o, 0)
+        cf = torch.empty((B, c_out, N), dtype=torch.float32, device=dev)
+        _capi.transpose(out, (N * ld_o, ld_o, 1), B, N, c_out, cf, c_out * N, N, 0)
+        return cf
+
+    def _forward_autograd(self, xyz1, xyz2, points1, points2):
         p1 = xyz1.transpose(1, 2)
         p2 = xyz2.transpose(1, 2)
         f2 = points2.transpose(1, 2)

@@ -134,7 +134,25 @@ REGRESSOR_SPECS = {
 }
 
 
+# The decoder's feature-propagation blocks (TEHNet.py:130-133), SURVEY.md section 8f row N1.
+DECODER_SPECS = {
+    "fp3": dict(kind="fp", in_channel=1536, mlp=[256, 256]),
+    "fp2": dict(kind="fp", in_channel=576, mlp=[256, 128]),
+    "fp1": dict(kind="fp", in_channel=128, mlp=[128, 128, 256]),
+}
+
+
+def decoder_test_features(batch: int, seed: int):
+    """Seeded stand-ins for (l1_points [B,320,512], l2_points [B,512,128], l3_points [B,1024,1]), the feature
+    inputs of fp2 / fp3 (TEHNet.py:184-185), for the decoder parity fixtures."""
+    rs = np.random.RandomState(seed)
+    return tuple(rs.randn(batch, c, n).astype(np.float32) for c, n in ((320, 512), (512, 128), (1024, 1)))
+
+
 def random_state_for(spec: dict, seed: int) -> dict:
+    if spec["kind"] == "fp":      # Conv1d / BatchNorm1d stack: weights are [Cout, Cin, 1]
+        st = random_sa_state("mlp_convs.{j}", "mlp_bns.{j}", [spec["mlp"]], [spec["in_channel"]], seed)
+        return {k: (v.reshape(v.shape[:3]) if k.endswith(".weight") and v.ndim == 4 else v) for k, v in st.items()}
     if spec["kind"] == "msg":
         cins = [spec["in_channel"] + 3] * len(spec["mlp_list"])
         return random_sa_state("conv_blocks.{i}.{j}", "bn_blocks.{i}.{j}",

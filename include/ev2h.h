@@ -245,6 +245,22 @@ EV2H_API int ev2h_group_max_f32(const float *x, int B, int C, int K, int S, floa
 EV2H_API int ev2h_group_max_bwd_f32(const float *grad_out, const int32_t *arg, int B, int C, int K, int S,
                            float *grad_x, ev2h_stream_t stream);
 
+/* ---- feature propagation (decoder) -------------------------
+ * Replaces the geometric half of PointNetFeaturePropagation.forward (pointnet2_utils.py:294-301):
+ * square_distance(xyz1, xyz2), the full sort of every row, the first three, and
+ * weight = (1 / (d + 1e-8)) / sum.  xyz1 (queries, N per window) and xyz2 (sources, S >= 3 per
+ * window) are channel-first [B,3,*] addressed through element strides; idx int32 [B,N,3] holds the
+ * three nearest sources in ascending distance (ties: lower index first), weight fp32 [B,N,3]. */
+EV2H_API int ev2h_three_nn_f32(const float *xyz1, int64_t q_stride_b, int64_t q_stride_c, int64_t q_stride_n,
+                               const float *xyz2, int64_t s_stride_b, int64_t s_stride_c, int64_t s_stride_n,
+                               int B, int N, int S, int32_t *idx, float *weight, ev2h_stream_t stream);
+/* interpolated[b,n,:] = sum_k feats[b, idx[b,n,k], :] * weight[b,n,k]  (:301), written at column col
+ * of out_rows [B*N, ld_out] (the concat with points1 happens by writing next to it).
+ * feats_rows [B*S, ld_f], D channels. */
+EV2H_API int ev2h_three_interp_f32(const float *feats_rows, int ld_f, const int32_t *idx, const float *weight,
+                                   int B, int N, int S, int D, float *out_rows, int ld_out, int col,
+                                   ev2h_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,9 @@ Function <-> reference line map
     shared_mlp_max        pointnet2_utils.py:193-199, :253-257
     sa_msg_forward        pointnet2_utils.py:224-262 (PointNetSetAbstractionMsg.forward)
     sa_all_forward        pointnet2_utils.py:176-202 (PointNetSetAbstraction.forward, group_all)
+    three_nn_weights      pointnet2_utils.py:294-301 (3 nearest sources + inverse-distance weights)
+    fp_forward            pointnet2_utils.py:276-315 (PointNetFeaturePropagation.forward)
+    decoder_forward       TEHNet.py:184-186          (fp3 -> fp2 -> fp1)
 """
 from __future__ import annotations
 
@@ -175,3 +178,45 @@ def regressor_sa_forward(states: dict, specs: dict, xyz_cf: torch.Tensor, hand_f
     if return_aux:
         return out, {"sa1": r1[2], "l1_xyz": r1[0], "l1_points": r1[1]}
     return out
+
+
+def three_nn_weights(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """xyz1 [B,N,3] queries, xyz2 [B,S,3] sources (S >= 3) -> (idx int64 [B,N,3], weight [B,N,3]):
+    the three nearest sources by the expanded squared distance (full sort, as the reference
+    does) and the normalised inverse-distance weights 1 / (d + 1e-8)."""
+    d = pairwise_sqdist(xyz1, xyz2)
+    d, idx = d.sort(dim=-1)
+    d, idx = d[:, :, :3], idx[:, :, :3]
+    recip = 1.0 / (d + 1e-8)
+    norm = torch.sum(recip, dim=2, keepdim=True)
+    return idx, recip / norm
+
+
+def fp_forward(state: dict, spec: dict, xyz1_cf: torch.Tensor, xyz2_cf: torch.Tensor,
+               points1_cf: torch.Tensor | None, points2_cf: torch.Tensor, return_aux: bool = False):
+    """Feature propagation: xyz1 [B,3,N], xyz2 [B,3,S], points1 [B,D1,N] or None, points2 [B,D2,S]
+    -> [B,D',N] (inverse-distance interpolation of points2 onto xyz1, concat, Conv1d+BN1d+ReLU stack)."""
+    xyz1 = xyz1_cf.permute(0, 2, 1).contiguous()
+    xyz2 = xyz2_cf.permute(0, 2, 1).contiguous()
+    p2 = points2_cf.permute(0, 2, 1).contiguous()
+    B, N, _ = xyz1.shape
+    S = xyz2.shape[1]
+    aux = {}
+    if S == 1:
+        up = p2.repeat(1, N, 1)
+    else:
+        idx, w = three_nn_weights(xyz1, xyz2)
+        aux = {"idx": idx, "weight": w}
+        up = torch.sum(take_rows(p2, idx) * w.view(B, N, 3, 1), dim=2)
+    h = up if points1_cf is None else torch.cat([points1_cf.permute(0, 2, 1).contiguous(), up], dim=-1)
+    h = h.permute(0, 2, 1).contiguous()
+    for (w_, b_, gamma, beta, mean, var) in _layers(state, "mlp_convs.{j}", "mlp_bns.{j}", len(spec["mlp"])):
+        h = F.relu(F.batch_norm(F.conv1d(h, w_, b_), mean, var, gamma, beta, False, 0.1, BN_EPS))
+    return (h, aux) if return_aux else h
+
+
+def decoder_forward(states: dict, specs: dict, l0_xyz, l1_xyz, l2_xyz, l3_xyz, l1_points, l2_points, l3_points):
+    """fp3 -> fp2 -> fp1 as TEHNet.forward wires them (TEHNet.py:184-186) -> per-point features [B,256,N]."""
+    l2p = fp_forward(states["fp3"], specs["fp3"], l2_xyz, l3_xyz, l2_points, l3_points)
+    l1p = fp_forward(states["fp2"], specs["fp2"], l1_xyz, l2_xyz, l1_points, l2p)
+    return fp_forward(states["fp1"], specs["fp1"], l0_xyz, l1_xyz, None, l1p), l1p, l2p

@@ -63,6 +63,18 @@ def small_idx(a):
     return a.astype(np.int16) if a.max() < 32768 else a.astype(np.int32)
 
 
+_ONLY = set(sys.argv[1:])      # e.g. `python make_golden.py decoder`: rewrite only decoder.npz
+_savez = np.savez_compressed
+
+
+def _savez_selected(path, **kw):
+    if not _ONLY or os.path.basename(path)[:-4] in _ONLY:
+        _savez(path, **kw)
+
+
+np.savez_compressed = _savez_selected
+
+
 def main():
     pu, th = load_reference()
     torch.set_num_threads(8)
@@ -162,6 +174,28 @@ def main():
     np.savez_compressed(os.path.join(HERE, "regressor.npz"), events=events.numpy(), hand_feats=hand.numpy(),
                         start_sa1=s3.numpy(), r1_xyz=r1_xyz.numpy(), r1_points_w0=r1_points[0].numpy(),
                         r2_points=r2_points.numpy(), weight_seeds=np.array([200, 201]))
+
+    # ---- 5. decoder fp3 -> fp2 -> fp1 on the encoder's outputs (TEHNet.py:184-186) ----------
+    dstates = {n: synth.random_state_for(synth.DECODER_SPECS[n], seed=300 + i) for i, n in enumerate(("fp3", "fp2", "fp1"))}
+    for n in dstates:
+        getattr(net, n).load_state_dict(to_t(dstates[n]), strict=True)
+    # point features are seeded noise (regenerated by the tests, not stored); coordinates are the encoder's
+    f1r, f2r, f3r = (torch.from_numpy(a) for a in synth.decoder_test_features(2, seed=55))
+    with torch.no_grad():
+        d2 = net.fp3(l2_xyz, l3_xyz, f2r, f3r)
+        d1 = net.fp2(l1_xyz, l2_xyz, f1r, d2)
+        d0 = net.fp1(l0_xyz, l1_xyz, None, d1)
+        # the 3-NN tables of fp2 / fp1, recomputed with the reference's own functions (:294-301)
+        nn_tabs = {}
+        for tag, q, src in (("fp2", l1_xyz, l2_xyz), ("fp1", l0_xyz, l1_xyz)):
+            dd, ii = pu.square_distance(q.permute(0, 2, 1).contiguous(), src.permute(0, 2, 1).contiguous()).sort(dim=-1)
+            dd, ii = dd[:, :, :3], ii[:, :, :3]
+            rc = 1.0 / (dd + 1e-8)
+            nn_tabs[tag + "_idx"] = small_idx(ii.numpy())
+            nn_tabs[tag + "_weight"] = (rc / torch.sum(rc, dim=2, keepdim=True)).numpy()
+    np.savez_compressed(os.path.join(HERE, "decoder.npz"), d2=d2.numpy(), d1_every2=d1[:, :, ::2].numpy(),
+                        d0_every16=d0[:, :, ::16].numpy(), weight_seeds=np.array([300, 301, 302]),
+                        feature_seed=np.array(55), **nn_tabs)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

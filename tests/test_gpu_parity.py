@@ -443,3 +443,74 @@ def test_long_window_16k_fp32_vs_bf16_and_oracle_indices():
         e2h.set_mlp_precision(old)
     assert rel_err(outs["tf32x3"], outs["fp32"]) <= 1e-5
     assert rel_err(outs["bf16"], outs["fp32"]) <= 1e-2
+
+
+# ---- decoder: feature propagation -------------------------------------------------------
+
+def _decoder_with(seeds):
+    dec = e2h.FeaturePropagationDecoder()
+    for n, s in zip(("fp3", "fp2", "fp1"), seeds):
+        load_numpy_state(getattr(dec, n), synth.random_state_for(synth.DECODER_SPECS[n], seed=int(s)))
+    return dec.to(DEV).eval()
+
+
+def test_decoder_golden(golden, precision):
+    """fp3 -> fp2 -> fp1 against the reference's own outputs: 3-NN indices bit-exact, weights and features
+    within the precision's bar."""
+    e, g = golden("encoder"), golden("decoder")
+    FEAT_TOL = PRECISION_TOL[precision]
+    dec = _decoder_with(g["weight_seeds"])
+    f1, f2, f3 = (dev(a) for a in synth.decoder_test_features(2, seed=int(g["feature_seed"])))
+    ev = dev(e["events"])
+    with torch.no_grad():
+        d0, d1, d2 = dec(ev[:, :3, :], dev(e["l1_xyz"]), dev(e["l2_xyz"]), dev(e["l3_xyz"]), f1, f2, f3, return_levels=True)
+    for tag, fp in (("fp2", dec.fp2), ("fp1", dec.fp1)):
+        assert np.array_equal(fp.last_idx.cpu().numpy(), g[tag + "_idx"].astype(np.int32))
+        assert rel_err(fp.last_weight, g[tag + "_weight"]) <= 1e-6
+    assert rel_err(d2, g["d2"]) <= FEAT_TOL
+    assert rel_err(d1[:, :, ::2], g["d1_every2"]) <= FEAT_TOL
+    assert rel_err(d0[:, :, ::16], g["d0_every16"]) <= FEAT_TOL
+
+
+def test_three_nn_matches_c_free_oracle_on_ragged_sizes():
+    """3-NN + weights against the torch oracle for sizes that are not multiples of the CTA / tile sizes,
+    a strided (non-contiguous) query view, and exact duplicates among the sources (ties keep the lower index)."""
+    rs = np.random.RandomState(5)
+    for B, N, S in ((1, 1, 3), (2, 130, 7), (3, 257, 1025), (1, 2048, 512)):
+        q = rs.rand(B, 5, N).astype(np.float32)
+        src = rs.rand(B, 3, S).astype(np.float32)
+        if S >= 7:
+            src[:, :, 5] = src[:, :, 2]                      # duplicate source point
+        qd = dev(q)[:, :3, :]                                # strided view, like xyz[:, :3, :] in the model
+        idx, w = _capi.three_nn(qd, dev(src))
+        want_i, want_w = sa_oracle.three_nn_weights(torch.from_numpy(q[:, :3, :]).permute(0, 2, 1).contiguous(),
+                                                    torch.from_numpy(src).permute(0, 2, 1).contiguous())
+        wi = want_i.numpy()
+        gi = idx.cpu().numpy().astype(np.int64)
+        if not np.array_equal(gi, wi):                      # only exact ties may be ordered differently by torch's sort
+            d = sa_oracle.pairwise_sqdist(torch.from_numpy(q[:, :3, :]).permute(0, 2, 1).contiguous(),
+                                          torch.from_numpy(src).permute(0, 2, 1).contiguous()).numpy()
+            bad = np.argwhere(gi != wi)
+            for b, n, k in bad:
+                assert d[b, n, gi[b, n, k]] == d[b, n, wi[b, n, k]]
+        assert rel_err(w, want_w.numpy()) <= 1e-6
+
+
+def test_feature_propagation_train_mode_matches_eval_formulation():
+    """The training (autograd) path and the CUDA path are the same function: compare them in eval mode with
+    gradients enabled vs disabled."""
+    dec = _decoder_with((7, 8, 9))
+    rs = np.random.RandomState(3)
+    xyz1, xyz2 = dev(rs.rand(2, 3, 300).astype(np.float32)), dev(rs.rand(2, 3, 40).astype(np.float32))
+    p1, p2 = dev(rs.randn(2, 320, 300).astype(np.float32)), dev(rs.randn(2, 256, 40).astype(np.float32))
+    with torch.no_grad():
+        fast = dec.fp2(xyz1, xyz2, p1, p2)
+    p1g = p1.clone().requires_grad_(True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # cuDNN would otherwise run the Conv1d stack in plain tf32
+    try:
+        slow = dec.fp2(xyz1, xyz2, p1g, p2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert slow.requires_grad
+    assert rel_err(fast, slow.detach().cpu().numpy()) <= 1e-5

@@ -65,13 +65,16 @@ def test_no_cpu_fallback():
 
 
 def test_feature_propagation_matches_oracle_formula():
-    # decoder block stays in PyTorch; check it against a direct evaluation of its formula
+    # the decoder block's training-path formulation (host logic) against a direct evaluation of its formula;
+    # the module itself has no CPU path
     torch.manual_seed(0)
     fp = e2h.PointNetFeaturePropagation(6 + 5, [8]).eval()
     xyz1, xyz2 = torch.rand(2, 3, 20), torch.rand(2, 3, 7)
     p1, p2 = torch.rand(2, 6, 20), torch.rand(2, 5, 7)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fp(xyz1, xyz2, p1, p2)
     with torch.no_grad():
-        got = fp(xyz1, xyz2, p1, p2)
+        got = fp._forward_autograd(xyz1, xyz2, p1, p2)
     a, b = xyz1.permute(0, 2, 1), xyz2.permute(0, 2, 1)
     d = ((a[:, :, None] - b[:, None]) ** 2).sum(-1)
     dd, ii = d.topk(3, dim=-1, largest=False)

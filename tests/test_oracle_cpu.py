@@ -121,3 +121,22 @@ def test_f64_mlp_yardstick_agrees_with_torch():
     xt = t(x).permute(2, 1, 0).unsqueeze(0).contiguous()   # [1,C,K,G]
     want = sa_oracle.shared_mlp_max(xt, [tuple(t(a) for a in l) for l in layers_np])[0].numpy().T
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_decoder_matches_reference(golden):
+    """fp3 -> fp2 -> fp1: 3-NN indices bit-exact, weights and features to 1e-6."""
+    e, g = golden("encoder"), golden("decoder")
+    states = {n: synth.random_state_for(synth.DECODER_SPECS[n], seed=int(s))
+              for n, s in zip(("fp3", "fp2", "fp1"), g["weight_seeds"])}
+    f1, f2, f3 = (t(a) for a in synth.decoder_test_features(2, seed=int(g["feature_seed"])))
+    l0_xyz = t(e["events"])[:, :3, :]
+    l1_xyz, l2_xyz, l3_xyz = t(e["l1_xyz"]), t(e["l2_xyz"]), t(e["l3_xyz"])
+    with torch.no_grad():
+        d0, d1, d2 = sa_oracle.decoder_forward(states, synth.DECODER_SPECS, l0_xyz, l1_xyz, l2_xyz, l3_xyz, f1, f2, f3)
+        for tag, q, src in (("fp2", l1_xyz, l2_xyz), ("fp1", l0_xyz, l1_xyz)):
+            idx, w = sa_oracle.three_nn_weights(q.permute(0, 2, 1).contiguous(), src.permute(0, 2, 1).contiguous())
+            assert np.array_equal(idx.numpy(), g[tag + "_idx"].astype(np.int64))
+            assert _close(w.numpy(), g[tag + "_weight"])
+    assert _close(d2.numpy(), g["d2"])
+    assert _close(d1.numpy()[:, :, ::2], g["d1_every2"])
+    assert _close(d0.numpy()[:, :, ::16], g["d0_every16"])
