@@ -12,3 +12,9 @@ if [ "$2" == "ncu" ]; then
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --mlp ${NCU_MLP:-tf32x3} > gpurun_out/${TAG}_ncu_bench.log 2>&1
 fi
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_smoke.log; cat gpurun_out/${TAG}_bench_*.json | cut -c1-1500; tail -3 gpurun_out/${TAG}_bench.err
+if [ "$3" == "full" ]; then
+  # one --set full capture of the five fused launches of a step (skip the warm-up steps' launches)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:sa_fused -s 15 -c 5 -o gpurun_out/${TAG}_fused -f \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --mlp ${NCU_MLP:-tf32x3} > gpurun_out/${TAG}_ncu_full.log 2>&1
+  ncu -i gpurun_out/${TAG}_fused.ncu-rep --page raw --csv > gpurun_out/${TAG}_fused_raw.csv 2>/dev/null
+fi
