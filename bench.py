@@ -344,6 +344,15 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks, "wall_s": wall,
         "checksum": float(out.double().sum().item()),
     }
+    comp = {}
+    for name in ("sa1", "sa2"):
+        m = getattr(enc, name)
+        if getattr(m, "last_compact_rows", None) is not None:
+            rows = m.last_compact_rows.cpu().tolist()
+            comp[name] = [r / float(B * m.npoint * k) for r, k in zip(rows, m.nsample_list)]
+    # rows the fused kernel evaluates / dense B*S*K rows per scale: padded duplicate neighbours are skipped
+    # (bit-identical pooled features); roofline.achieved counts the dense algorithmic FLOPs
+    line["compaction"] = {"rows_evaluated_fraction": comp} if comp else None
     if args.with_decoder:
         line["secondary"] = {"metric": "encoder + fp3/fp2/fp1 decoder event-windows/s (TEHNet.py:172-186)",
                              "value": windows / (dec_ms / 1e3), "unit": "windows/s", "ms_per_step": dec_ms / args.steps}

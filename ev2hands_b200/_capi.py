@@ -44,6 +44,15 @@ _SIGNATURES = {
                              c_vp, c_int, c_int, c_vp, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
                              c_vp, c_int, c_int, c_int, c_vp],
+    "ev2h_ball_query_cnt_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f),
+                                ctypes.POINTER(ctypes.c_int32), c_vp, c_vp, c_vp],
+    "ev2h_group_compact_i32": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_vp,
+                               ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp],
+    "ev2h_sa_msg_fused_compact_tc": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                     c_vp, c_int, c_vp, c_int, c_vp,
+                                     c_vp, c_int, c_int, c_vp, c_int, c_int,
+                                     c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                     c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_three_nn_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_three_interp_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
@@ -83,7 +92,7 @@ def lib() -> ctypes.CDLL:
 
 class LaunchLog:
     """Counts kernel launches (every compute entry point of the ABI enqueues exactly one
-    kernel) and, when ``timing`` is on, brackets each with CUDA events on its stream so
+    kernel, ev2h_group_compact_i32 two) and, when ``timing`` is on, brackets each with CUDA events on its stream so
     bench.py can report per-kernel device time from inside the timed region."""
 
     def __init__(self):
@@ -109,11 +118,12 @@ LOG = LaunchLog()
 
 
 class _timed:
-    def __init__(self, name):
+    def __init__(self, name, launches=1):
         self.name = name
+        self.launches = launches
 
     def __enter__(self):
-        LOG.count += 1
+        LOG.count += self.launches
         if LOG.timing:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
@@ -179,8 +189,8 @@ def radius_sq_f32(radius: float) -> float:
     return torch.tensor(float(radius) ** 2, dtype=torch.float32).item()
 
 
-def ball_query(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: int, radii, nsamples):
-    """-> idx int32 [B,S,sum(K)]"""
+def ball_query(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: int, radii, nsamples, with_counts: bool = False):
+    """-> idx int32 [B,S,sum(K)]  (with_counts: also cnt int32 [n_scales,B,S], the real neighbours per scale)"""
     _need_cuda_f32(xyz, "xyz")
     _need_cuda_f32(centres_rows, "centres")
     B, S, _ = centres_rows.shape
@@ -188,11 +198,36 @@ def ball_query(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: int, r
     r2 = (c_f * ns)(*[radius_sq_f32(r) for r in radii])
     ks = (ctypes.c_int32 * ns)(*[int(k) for k in nsamples])
     out = torch.empty((B, S, int(sum(nsamples))), dtype=torch.int32, device=xyz.device)
+    cnt = torch.empty((ns, B, S), dtype=torch.int32, device=xyz.device) if with_counts else None
     with torch.cuda.device(xyz.device):
         with _timed("ev2h_ball_query_f32"):
-            _check(lib().ev2h_ball_query_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows.contiguous()),
-                                         B, N, S, ns, r2, ks, _p(out), _stream(xyz)), "ev2h_ball_query_f32")
-    return out
+            if with_counts:
+                _check(lib().ev2h_ball_query_cnt_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows.contiguous()),
+                                                     B, N, S, ns, r2, ks, _p(out), _p(cnt), _stream(xyz)), "ev2h_ball_query_cnt_f32")
+            else:
+                _check(lib().ev2h_ball_query_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows.contiguous()),
+                                                 B, N, S, ns, r2, ks, _p(out), _stream(xyz)), "ev2h_ball_query_f32")
+    return (out, cnt) if with_counts else out
+
+
+def group_compact(idx: torch.Tensor, cnt: torch.Tensor, N: int, nsamples):
+    """Compacted row lists of every scale of a layer (ev2h_group_compact_i32):
+    -> (rowmaps, blockgroups, n_rows): two lists of int32 device tensors and the int32 [n_scales] row counts."""
+    B, S, _ = idx.shape
+    ns = len(nsamples)
+    dev = idx.device
+    rowmaps = [torch.empty((B * S * int(k),), dtype=torch.int32, device=dev) for k in nsamples]
+    blockgroups = [torch.empty((B * S * int(k) // 8 + 16,), dtype=torch.int32, device=dev) for k in nsamples]
+    n_rows = torch.empty((ns,), dtype=torch.int32, device=dev)
+    offs = torch.empty((ns * B * S,), dtype=torch.int32, device=dev)
+    ks = (ctypes.c_int32 * ns)(*[int(k) for k in nsamples])
+    a_rm = (c_vp * ns)(*[t.data_ptr() for t in rowmaps])
+    a_bg = (c_vp * ns)(*[t.data_ptr() for t in blockgroups])
+    with torch.cuda.device(dev):
+        with _timed("ev2h_group_compact_i32", launches=2):
+            _check(lib().ev2h_group_compact_i32(_p(idx), idx.shape[-1], _p(cnt), B, N, S, ns, ks, _p(offs), a_rm, a_bg, _p(n_rows),
+                                                _stream(idx)), "ev2h_group_compact_i32")
+    return rowmaps, blockgroups, n_rows
 
 
 def square_distance(src_rows: torch.Tensor, dst_rows: torch.Tensor) -> torch.Tensor:
@@ -330,11 +365,21 @@ def fused_supported(K: int, widths, first_in: int, per_point: bool, mode: int = 
 
 
 def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, first_wt, first_bias, P, ld_p, p_col, C, ld_c, c_col,
-                 c1, couts, packed, biases, out_rows, ld_out, out_col, mode):
+                 c1, couts, packed, biases, out_rows, ld_out, out_col, mode, compact=None):
+    """compact = (rowmap, blockgroup, n_rows_scalar_view) runs the kernel over the compacted row list."""
     a_cout = (ctypes.c_int32 * 2)(*couts)
     a_w = (c_vp * 2)(*[t.data_ptr() for t in packed])
     a_b = (c_vp * 2)(*[t.data_ptr() for t in biases])
     with torch.cuda.device(out_rows.device):
+        if compact is not None:
+            rm, bg, nr = compact
+            with _timed("ev2h_sa_msg_fused_tc"):
+                _check(lib().ev2h_sa_msg_fused_compact_tc(_p(rm), _p(bg), _p(nr), _p(centres_rows), B, N, S, K,
+                                                          _p(pts8), D, _p(first_wt), 0 if first_wt is None else first_wt.shape[1],
+                                                          _p(first_bias), _p(P), ld_p, p_col, _p(C), ld_c, c_col,
+                                                          c1, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode,
+                                                          _stream(out_rows)), "ev2h_sa_msg_fused_compact_tc")
+            return
         with _timed("ev2h_sa_msg_fused_tc"):
             _check(lib().ev2h_sa_msg_fused_tc(_p(idx), idx.shape[-1], k_off, _p(centres_rows), B, N, S, K,
                                               _p(pts8), D, _p(first_wt), 0 if first_wt is None else first_wt.shape[1],

@@ -38,7 +38,7 @@ template <int NS>
 __global__ void __launch_bounds__(kBqCentres * kBqSegs)
 ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
                   const float *__restrict__ centres, int N, int S, BallParams prm,
-                  int32_t *__restrict__ out) {
+                  int32_t *__restrict__ out, int32_t *__restrict__ cnt_out) {
     __shared__ float4 pts[kBqTile];
     __shared__ int cnt_s[kBqSegs][NS][kBqCentres];      // hits of this tile per (range, radius, centre)
     __shared__ int first_s[kBqSegs][NS][kBqCentres];    // first hit of this tile per (range, radius, centre), N if none
@@ -125,6 +125,10 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
         for (int k = 0; k < NS; ++k) total[k] += tile_total[k];
     }
     if (!live) return;
+    if (cnt_out != nullptr && seg == 0) {                // real (unpadded) neighbours per scale, for the row compaction
+#pragma unroll
+        for (int k = 0; k < NS; ++k) cnt_out[(int64_t)k * gridDim.y * S + (int64_t)b * S + s] = min(total[k], prm.K[k]);   // [scale][b*S+s]
+    }
     // pad with the first hit (:104-106); the ranges share the padding slots
 #pragma unroll
     for (int k = 0; k < NS; ++k)
@@ -180,10 +184,31 @@ extern "C" int ev2h_index_rows_f32(const float *table_rows, const int32_t *idx, 
     return check_launch("ev2h_index_rows_f32");
 }
 
+static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                           const float *centres_rows, int B, int N, int S, int n_scales,
+                           const float *radius_sq_host, const int32_t *nsample_host,
+                           int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream);
+
 extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                                    const float *centres_rows, int B, int N, int S, int n_scales,
                                    const float *radius_sq_host, const int32_t *nsample_host,
                                    int32_t *out_idx, ev2h_stream_t stream) {
+    return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
+                           out_idx, nullptr, stream);
+}
+
+extern "C" int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                       const float *centres_rows, int B, int N, int S, int n_scales,
+                                       const float *radius_sq_host, const int32_t *nsample_host,
+                                       int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream) {
+    return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
+                           out_idx, out_cnt, stream);
+}
+
+static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                           const float *centres_rows, int B, int N, int S, int n_scales,
+                           const float *radius_sq_host, const int32_t *nsample_host,
+                           int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(xyz && centres_rows && out_idx && radius_sq_host && nsample_host, "ev2h_ball_query_f32: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0, "ev2h_ball_query_f32: B, N, S must be positive");
@@ -210,10 +235,10 @@ extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t s
     constexpr int kBqThreads = kBqCentres * kBqSegs;
     cudaStream_t st = as_stream(stream);
     switch (n_scales) {
-        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
-        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
-        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
-        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx); break;
+        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
+        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
+        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
+        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
     }
     return check_launch("ev2h_ball_query_f32");
 }

@@ -1,0 +1,141 @@
+// Row compaction for the fused set-abstraction kernel.
+//
+// query_ball_point pads every group to K neighbours by repeating the first one (reference
+// src/Ev2Hands/model/pointnet2_utils.py:104-106), and the shared MLP then evaluates those copies again
+// (:253-257) although max-pooling cannot see them: max over {a, a, ..., b, c} = max over {a, b, c}.  On event
+// windows most groups are far from full (17 % .. 89 % real neighbours per scale on the benchmark's data), so
+// the fused kernel runs over a COMPACTED row list instead: per group its real neighbours, rounded up to a
+// multiple of 8 rows with copies of the first one (8 rows = one UMMA core-matrix row block = the granularity
+// of the pooled epilogue), groups back to back.  Results are bit-identical to the dense evaluation.
+//
+//   rowmap[r]        global point row (b*N + point) feeding compact row r, -1 for "no point" (empty ball)
+//   blockgroup[r/8]  global group (b*S + centre) the 8-row block belongs to, -1 past the end
+//   n_rows           total compact rows of the scale
+#include "common.cuh"
+
+namespace ev2h {
+
+constexpr int kCompactScanThreads = 1024;
+
+__device__ __forceinline__ int compact_rows(int cnt, int K) {
+    cnt = cnt < 1 ? 1 : (cnt > K ? K : cnt);
+    return (cnt + 7) & ~7;
+}
+
+struct CompactScales {
+    int K[4], k_off[4];
+    int32_t *rowmap[4];
+    int32_t *blockgroup[4];
+};
+
+// One CTA per scale: exclusive prefix sum of the rounded neighbour counts over all groups.  cnt is scale-major
+// [n_scales][G], so a thread's run of consecutive groups is one contiguous stretch of memory.
+__global__ void __launch_bounds__(kCompactScanThreads)
+compact_scan_kernel(const int32_t *__restrict__ cnt, int G, CompactScales prm,
+                    int32_t *__restrict__ offs, int32_t *__restrict__ n_rows) {
+    __shared__ int warp_sum[kCompactScanThreads / 32];
+    const int sc = blockIdx.x, K = prm.K[sc];
+    const int32_t *c = cnt + (int64_t)sc * G;
+    int32_t *o = offs + (int64_t)sc * G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;                                       // rows before the current stretch of 4 * 1024 groups
+    for (int g0 = 0; g0 < G; g0 += 4 * kCompactScanThreads) {
+        // four consecutive groups per thread: coalesced 16-byte accesses when G is a multiple of 4
+        const int g = g0 + 4 * threadIdx.x;
+        int r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = g + j < G ? compact_rows(c[g + j], K) : 0;
+        const int mine = r[0] + r[1] + r[2] + r[3];
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        __syncthreads();                                // warp_sum of the previous stretch has been consumed
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kCompactScanThreads / 32; ++w) {
+            const int v = warp_sum[w];
+            if (w < warp) before += v;
+            total += v;
+        }
+        int run = base + before + incl - mine;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (g + j < G) o[g + j] = run;
+            run += r[j];
+        }
+        base += total;
+    }
+    if (threadIdx.x == 0) n_rows[sc] = base;
+}
+
+// lpg lanes per (group, scale) - 8, 16 or 32 for K <= 32, 64, 128 - write the group's compact rows and its
+// block -> group entries.
+__global__ void __launch_bounds__(256)
+compact_fill_kernel(const int32_t *__restrict__ idx, int idx_ld, const int32_t *__restrict__ cnt, int G,
+                    int N, int S, const int32_t *__restrict__ offs, const int32_t *__restrict__ n_rows, CompactScales prm) {
+    const int sc = blockIdx.y;
+    const int K = prm.K[sc];
+    const int lpg = K <= 32 ? 8 : (K <= 64 ? 16 : 32);
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int g = t / lpg, lane = t % lpg;
+    if (g >= G) return;
+    const int c = cnt[(int64_t)sc * G + g];
+    const int real = c < 1 ? 1 : (c > K ? K : c), rows = (real + 7) & ~7;
+    const int off = offs[(int64_t)sc * G + g];
+    const int32_t *src = idx + (int64_t)g * idx_ld + prm.k_off[sc];
+    const int64_t b = g / S;
+    int32_t *rm = prm.rowmap[sc], *bg = prm.blockgroup[sc];
+    for (int k = lane; k < rows; k += lpg) {
+        const int pt = src[k < real ? k : 0];
+        rm[off + k] = (pt >= 0 && pt < N) ? (int32_t)(b * N + pt) : -1;
+        if ((k & 7) == 0) bg[(off + k) >> 3] = g;
+    }
+    if (g == G - 1) {                                   // blocks between the end of the rows and the end of the last tile
+        const int total = n_rows[sc];
+        const int first = total >> 3, last = ((total + 127) / 128) * 16;
+        for (int j = first + lane; j < last; j += lpg) bg[j] = -1;
+    }
+}
+
+}  // namespace ev2h
+
+extern "C" int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int32_t *cnt, int B, int N, int S, int n_scales,
+                                      const int32_t *nsample_host, int32_t *offs_scratch,
+                                      int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
+                                      ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(idx && cnt && nsample_host && offs_scratch && rowmap_host && blockgroup_host && n_rows_dev,
+                 "ev2h_group_compact_i32: null argument");
+    EV2H_REQUIRE(B > 0 && N > 0 && S > 0 && n_scales >= 1 && n_scales <= 4, "ev2h_group_compact_i32: bad sizes");
+    const int64_t G64 = (int64_t)B * S;
+    EV2H_REQUIRE(G64 * 128 < 2147483647LL, "ev2h_group_compact_i32: too many groups for 32-bit row offsets");
+    const int G = (int)G64;
+    CompactScales prm;
+    int off = 0;
+    for (int i = 0; i < 4; ++i) {
+        const bool on = i < n_scales;
+        prm.K[i] = on ? nsample_host[i] : 0;
+        prm.k_off[i] = off;
+        prm.rowmap[i] = on ? rowmap_host[i] : nullptr;
+        prm.blockgroup[i] = on ? blockgroup_host[i] : nullptr;
+        if (on) {
+            EV2H_REQUIRE(nsample_host[i] > 0 && nsample_host[i] % 8 == 0 && prm.rowmap[i] && prm.blockgroup[i],
+                         "ev2h_group_compact_i32: scale %d: K must be a positive multiple of 8 and buffers non-null", i);
+            off += nsample_host[i];
+        }
+    }
+    EV2H_REQUIRE(off <= idx_ld, "ev2h_group_compact_i32: idx_ld smaller than the sum of K");
+    cudaStream_t st = as_stream(stream);
+    compact_scan_kernel<<<n_scales, kCompactScanThreads, 0, st>>>(cnt, G, prm, offs_scratch, n_rows_dev);
+    int rc = check_launch("ev2h_group_compact_i32 (scan)");
+    if (rc) return rc;
+    // sized for 32 lanes per group; scales with fewer lanes per group leave the tail of their grid row idle
+    compact_fill_kernel<<<dim3((unsigned)((G + 7) / 8), (unsigned)n_scales), 256, 0, st>>>(idx, idx_ld, cnt, G, N, S,
+                                                                                            offs_scratch, n_rows_dev, prm);
+    return check_launch("ev2h_group_compact_i32 (fill)");
+}

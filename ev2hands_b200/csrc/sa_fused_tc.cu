@@ -64,6 +64,10 @@ struct FusedParams {
     int B, N, S, K;
     const int32_t *idx; int idx_ld, k_off;       // ball-query result [B,S,idx_ld], this scale at k_off
     const float *centres;                        // [B,S,3]
+    // optional compacted row list (ev2h_group_compact_i32): padded duplicate neighbours skipped
+    const int32_t *rowmap;                       // [n_rows] global point row per compact row, -1 = no point
+    const int32_t *blockgroup;                   // [ceil(n_rows/128)*16] global group of every 8-row block, -1 past the end
+    const int32_t *n_rows_dev;                   // device scalar: compact rows of this scale
     // layer 1
     int per_point;                               // 0 = gather + FFMA, 1 = relu(P - C)
     const float *pts8; int D;                    // gather: [B,N,8] rows = [features(D) | xyz | 0]
@@ -154,7 +158,8 @@ sa_fused_tc_kernel(const FusedParams p) {
 #ifdef EV2H_FUSED_TRACE
     int trace_n = 0;
 #endif
-    const int64_t M = (int64_t)p.B * p.S * p.K;
+    const bool compact = p.rowmap != nullptr;
+    const int64_t M = compact ? (int64_t)__ldg(p.n_rows_dev) : (int64_t)p.B * p.S * p.K;
     const int64_t n_tiles = (M + FZ_BLOCK_M - 1) / FZ_BLOCK_M;
     const int nc0 = p.n_chunks[0], nc1 = p.n_chunks[1];
     const uint32_t Q = (uint32_t)(nc0 + nc1);            // chunks per tile
@@ -253,13 +258,21 @@ sa_fused_tc_kernel(const FusedParams p) {
                 ok = false;
                 const int64_t R = tile * FZ_BLOCK_M + r;
                 if (tile >= n_tiles || R >= M) return;
-                const int64_t bs = R / p.K;
-                const int j = (int)(R - bs * p.K);
-                const int64_t b = bs / p.S;
-                const int pt = p.idx[bs * p.idx_ld + p.k_off + j];
-                if (pt < 0 || pt >= p.N) return;
+                int64_t bs, pt_row;
+                if (compact) {
+                    pt_row = __ldg(p.rowmap + R);
+                    bs = __ldg(p.blockgroup + (R >> 3));
+                    if (pt_row < 0) return;
+                } else {
+                    bs = R / p.K;
+                    const int j = (int)(R - bs * p.K);
+                    const int64_t b = bs / p.S;
+                    const int pt = p.idx[bs * p.idx_ld + p.k_off + j];
+                    if (pt < 0 || pt >= p.N) return;
+                    pt_row = b * p.N + pt;
+                }
                 ok = true;
-                const float4 *src = reinterpret_cast<const float4 *>(p.pts8 + (b * p.N + pt) * 8);
+                const float4 *src = reinterpret_cast<const float4 *>(p.pts8 + pt_row * 8);
                 const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
                 o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
                 const float *c = p.centres + bs * 3;
@@ -325,11 +338,16 @@ sa_fused_tc_kernel(const FusedParams p) {
                     const int64_t R = m0 + 32 * wq + h * 8 + l8;
                     p_row[h] = -1; c_row[h] = 0;
                     if (R < M) {
-                        const int64_t bs = R / p.K;
-                        const int j = (int)(R - bs * p.K);
-                        const int64_t b = bs / p.S;
-                        const int pt = p.idx[bs * p.idx_ld + p.k_off + j];
-                        if (pt >= 0 && pt < p.N) { p_row[h] = b * p.N + pt; c_row[h] = bs; }
+                        if (compact) {
+                            p_row[h] = __ldg(p.rowmap + R);
+                            c_row[h] = __ldg(p.blockgroup + (R >> 3));
+                        } else {
+                            const int64_t bs = R / p.K;
+                            const int j = (int)(R - bs * p.K);
+                            const int64_t b = bs / p.S;
+                            const int pt = p.idx[bs * p.idx_ld + p.k_off + j];
+                            if (pt >= 0 && pt < p.N) { p_row[h] = b * p.N + pt; c_row[h] = bs; }
+                        }
                     }
                 }
             };
@@ -593,6 +611,51 @@ sa_fused_tc_kernel(const FusedParams p) {
                 if (eprof) FZ_TRACE(4, 5, it, 0);
                 tc::tc_fence_after();
                 const int64_t rows_left = M - m0;                       // rows >= M do not exist (last tile)
+                if (compact) {
+                    // Compacted rows: a group is a run of 8-row blocks with the same group id (warp uniform, one id
+                    // per lane fetched once per tile).  Groups may straddle tiles, so the first and the last group of
+                    // a tile are merged into the (zero-initialised) output with an integer atomic max - pooled
+                    // values are >= 0 after the ReLU, where float order equals integer order - the others stored.
+                    const int my_gid = lane < 16 ? __ldg(p.blockgroup + tile * 16 + lane) : -1;
+                    for (int mb = 0; mb < p.mb3; ++mb) {
+                        const int ch = mb * 128 + q * 32 + lane;
+                        const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + (uint32_t)(mb * FZ_BLOCK_M) + ((uint32_t)(q * 32) << 16);
+                        const float b = ch < p.n[1] ? bias_s[p.bias_off[1] + ch] : 0.f;
+                        int cur = -1;
+                        bool first_group = true;
+                        float acc = -INFINITY;
+                        auto flush = [&](bool edge) {
+                            if (cur >= 0 && ch < p.c_out) {
+                                float *dst = p.out + (int64_t)cur * p.ld_out + p.out_col + ch;
+                                const float v = fmaxf(acc + b, 0.f);
+                                if (edge) atomicMax(reinterpret_cast<int *>(dst), __float_as_int(v));
+                                else *dst = v;
+                            }
+                        };
+#pragma unroll 1
+                        for (int c0 = 0; c0 < FZ_BLOCK_M; c0 += 32) {
+                            uint32_t raw[32];
+                            tc::tmem_ld32(t_addr + c0, raw);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int blk = 0; blk < 4; ++blk) {
+                                const int gid = __shfl_sync(0xffffffffu, my_gid, (c0 >> 3) + blk);
+                                float m8 = fmaxf(fmaxf(fmaxf(__uint_as_float(raw[8 * blk]), __uint_as_float(raw[8 * blk + 1])),
+                                                       fmaxf(__uint_as_float(raw[8 * blk + 2]), __uint_as_float(raw[8 * blk + 3]))),
+                                                 fmaxf(fmaxf(__uint_as_float(raw[8 * blk + 4]), __uint_as_float(raw[8 * blk + 5])),
+                                                       fmaxf(__uint_as_float(raw[8 * blk + 6]), __uint_as_float(raw[8 * blk + 7]))));
+                                if (gid != cur) {
+                                    flush(first_group);
+                                    if (cur >= 0) first_group = false;
+                                    cur = gid; acc = m8;
+                                } else {
+                                    acc = fmaxf(acc, m8);
+                                }
+                            }
+                        }
+                        flush(true);
+                    }
+                } else
                 for (int mb = 0; mb < p.mb3; ++mb) {
                     const int ch = mb * 128 + q * 32 + lane;
                     const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + (uint32_t)(mb * FZ_BLOCK_M) + ((uint32_t)(q * 32) << 16);
@@ -685,12 +748,46 @@ extern "C" int ev2h_sa_msg_fused_kc(int mode, const int32_t *cout_host) {
     return pl.ok ? pl.kc : -1;
 }
 
+static int sa_msg_fused_impl(
+    const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
+    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
+    int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
+    float *out_rows, int ld_out, int out_col, int mode,
+    const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev, ev2h_stream_t stream);
+
 extern "C" int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
     const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
     float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream) {
+    return sa_msg_fused_impl(idx, idx_ld, k_off, centres_rows, B, N, S, K, pts8, D, first_wt, first_ld, first_bias, P, ld_p, p_col,
+                             C, ld_c, c_col, c1, cout_host, w_packed_host, bias_host, out_rows, ld_out, out_col, mode,
+                             nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int ev2h_sa_msg_fused_compact_tc(
+    const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev,
+    const float *centres_rows, int B, int N, int S, int K,
+    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
+    int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
+    float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(rowmap && blockgroup && n_rows_dev, "ev2h_sa_msg_fused_compact_tc: null row list");
+    return sa_msg_fused_impl(rowmap, K, 0, centres_rows, B, N, S, K, pts8, D, first_wt, first_ld, first_bias, P, ld_p, p_col,
+                             C, ld_c, c_col, c1, cout_host, w_packed_host, bias_host, out_rows, ld_out, out_col, mode,
+                             rowmap, blockgroup, n_rows_dev, stream);
+}
+
+static int sa_msg_fused_impl(
+    const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
+    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
+    int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
+    float *out_rows, int ld_out, int out_col, int mode,
+    const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev, ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(idx && centres_rows && out_rows && cout_host && w_packed_host && bias_host, "ev2h_sa_msg_fused_tc: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0 && k_off >= 0 && k_off + K <= idx_ld && c1 > 0, "ev2h_sa_msg_fused_tc: bad sizes");
@@ -715,6 +812,7 @@ extern "C" int ev2h_sa_msg_fused_tc(
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
+    p.rowmap = rowmap; p.blockgroup = blockgroup; p.n_rows_dev = n_rows_dev;
     p.per_point = per_point ? 1 : 0; p.pts8 = pts8; p.D = D; p.first_wt = first_wt; p.first_ld = first_ld; p.first_bias = first_bias;
     p.P = P; p.ld_p = ld_p; p.p_col = p_col; p.C = C; p.ld_c = ld_c; p.c_col = c_col; p.c1 = c1;
     p.tmem_cols = pl.tmem_cols; p.mb3 = pl.mb3;

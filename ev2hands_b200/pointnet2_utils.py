@@ -47,6 +47,8 @@ _FUSED_ENABLED = os.environ.get("EV2H_FUSED", "1") != "0"
 # fp32-level precision ("tf32x3") in the fused kernel: tf32 hi*hi + bf16 correction products (default), or
 # three tf32 products with EV2H_TF32X3_PURE=1.
 _TF32X3_PURE = os.environ.get("EV2H_TF32X3_PURE", "0") == "1"
+# Run the fused kernel over compacted rows (padded duplicate neighbours skipped; bit-identical results).
+_COMPACT = os.environ.get("EV2H_COMPACT", "1") != "0"
 # Evaluate layer 1 per point (instead of per gathered row) also for narrow inputs; experiment switch.
 _PER_POINT_ALWAYS = os.environ.get("EV2H_PER_POINT", "0") == "1"
 
@@ -303,7 +305,7 @@ class PointNetSetAbstractionMsg(nn.Module):
             fps_start = torch.randint(0, N, (B,), dtype=torch.long)
         strides = _capi.cf_strides(xyz)
         fps_idx, centres_rows, new_xyz = _capi.fps(xyz, strides, fps_start, B, N, S)
-        ball = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list)
+        ball, self._ball_cnt = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list, with_counts=True)
         return strides, fps_idx, centres_rows, new_xyz, ball
 
     def forward(self, xyz, points, fps_start=None):
@@ -376,6 +378,11 @@ class PointNetSetAbstractionMsg(nn.Module):
                 p_cols.append(col)
                 col += L0["cout"]
 
+        compact = None
+        if any(fused) and _COMPACT and all(k % 8 == 0 for k in self.nsample_list):
+            compact = _capi.group_compact(ball, self._ball_cnt, N, self.nsample_list)
+        self.last_compact_rows = None if compact is None else compact[2]     # int32 [n_scales] on the device (diagnostics)
+
         feats_rows = None
         ld_x = _pad4(D + 3)
         k_off = col = 0
@@ -396,7 +403,8 @@ class PointNetSetAbstractionMsg(nn.Module):
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
                                    C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
                                    layers[0]["cout"], [L["cout"] for L in use], packed, [L["bias"] for L in use],
-                                   out_rows, c_total, col, fmode)
+                                   out_rows, c_total, col, fmode,
+                                   compact=None if compact is None else (compact[0][i], compact[1][i], compact[2][i:i + 1]))
             else:
                 if feats_rows is None and points is not None:
                     feats_rows = _to_rows(points)

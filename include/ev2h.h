@@ -91,6 +91,27 @@ EV2H_API int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t str
                         int n_scales, const float *radius_sq_host, const int32_t *nsample_host,
                         int32_t *out_idx, ev2h_stream_t stream);
 
+/* The same query that also reports, per centre and scale, how many of the K slots hold real
+ * (unpadded) neighbours: out_cnt int32 [n_scales, B, S] (scale-major), 0 when no point is in radius. */
+EV2H_API int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                        const float *centres_rows, int B, int N, int S,
+                        int n_scales, const float *radius_sq_host, const int32_t *nsample_host,
+                        int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream);
+
+/* Row compaction for the fused kernel.  query_ball_point pads every group to K neighbours with copies of
+ * the first one (pointnet2_utils.py:104-106); the max-pool cannot see those copies, so the shared MLP need
+ * not evaluate them.  For every scale i of a layer this builds the list of rows actually needed - per group
+ * its out_cnt real neighbours, rounded up to a multiple of 8 with copies of the first, groups back to back:
+ *   rowmap_host[i]      int32 [B*S*K_i]        global point row b*N + point of every compact row (-1: no point)
+ *   blockgroup_host[i]  int32 [B*S*K_i/8 + 16] global group b*S + centre of every 8-row block (-1 past the end)
+ *   n_rows_dev          int32 [n_scales]       compact rows per scale
+ * (device buffers; the two pointer tables live on the host).  offs_scratch: int32 [n_scales * B*S].
+ * idx / cnt come from ev2h_ball_query_cnt_f32; every K_i must be a multiple of 8. */
+EV2H_API int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int32_t *cnt, int B, int N, int S, int n_scales,
+                                    const int32_t *nsample_host, int32_t *offs_scratch,
+                                    int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
+                                    ev2h_stream_t stream);
+
 /* square_distance as a standalone op (pointnet2_utils.py:19-40), same arithmetic as
  * inside the ball query: src_rows [B,S,3], dst_rows [B,N,3] -> out [B,S,N]. */
 EV2H_API int ev2h_square_distance_f32(const float *src_rows, const float *dst_rows, int B, int S, int N,
@@ -219,6 +240,17 @@ EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, c
  * are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3 / EV2H_TC_TF32_BF16C. */
 EV2H_API int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
+    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
+    int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
+    float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream);
+
+/* The fused kernel over a compacted row list (ev2h_group_compact_i32) instead of the dense [B,S,K] index
+ * block: same arguments otherwise, bit-identical pooled features (out_rows must be zero-filled: groups that
+ * straddle two row tiles are merged with an atomic max), time proportional to the real neighbours. */
+EV2H_API int ev2h_sa_msg_fused_compact_tc(
+    const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev,
+    const float *centres_rows, int B, int N, int S, int K,
     const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,

@@ -514,3 +514,59 @@ def test_feature_propagation_train_mode_matches_eval_formulation():
         torch.backends.cudnn.allow_tf32 = old
     assert slow.requires_grad
     assert rel_err(fast, slow.detach().cpu().numpy()) <= 1e-5
+
+
+# ---- row compaction: skipping the padded duplicate neighbours must not change a single bit ------------------
+
+def test_compacted_rows_are_bit_identical_to_dense(precision):
+    import ev2hands_b200.pointnet2_utils as pu
+    if precision == "fp32":
+        pytest.skip("the fp32 path is layer by layer, not the fused kernel")
+    enc = _encoder_with((41, 42, 43))
+    ev = dev(synth.make_windows(5, 2048, seed=77))
+    starts = (torch.from_numpy(synth.make_start_indices(5, 2048, 8)), torch.from_numpy(synth.make_start_indices(5, 512, 9)))
+    outs = {}
+    old = pu._COMPACT
+    try:
+        for flag in (False, True):
+            pu._COMPACT = flag
+            with torch.no_grad():
+                l3, lv = enc(ev, fps_starts=starts, return_levels=True)
+            outs[flag] = (l3.cpu().numpy(), lv["l1_points"].cpu().numpy(), lv["l2_points"].cpu().numpy())
+    finally:
+        pu._COMPACT = old
+    for a, b in zip(outs[False], outs[True]):
+        assert np.array_equal(a, b)
+
+
+def test_compaction_tables_match_a_numpy_restatement():
+    rs = np.random.RandomState(2)
+    B, N, S = 3, 700, 50
+    xyz = rs.rand(B, 3, N).astype(np.float32)
+    xyz[:, :, 10] = 5.0                                             # a far-away centre: alone in its ball
+    centres_idx = np.stack([np.concatenate([[10], rs.choice(N, S - 1, replace=False)]) for _ in range(B)])
+    centres = np.stack([xyz[b][:, centres_idx[b]].T for b in range(B)]).astype(np.float32)
+    Ks = [8, 32, 64]
+    xd = dev(xyz)
+    idx, cnt = _capi.ball_query(xd, _capi.cf_strides(xd), dev(centres), N, [0.05, 0.15, 0.3], Ks, with_counts=True)
+    rowmaps, blockgroups, n_rows = _capi.group_compact(idx, cnt, N, Ks)
+    idx_h, cnt_h, n_rows_h = idx.cpu().numpy(), cnt.cpu().numpy(), n_rows.cpu().numpy()
+    k_off = 0
+    for i, K in enumerate(Ks):
+        # counts: number of distinct leading entries before the padding (= entries != first after position 0, + 1)
+        blk = idx_h[:, :, k_off:k_off + K]
+        want_cnt = np.array([[len(np.unique(blk[b, s])) for s in range(S)] for b in range(B)])
+        assert np.array_equal(cnt_h[i], want_cnt)
+        rm, bg = [], []
+        for g in range(B * S):
+            b, s = divmod(g, S)
+            c = max(int(want_cnt[b, s]), 1)
+            rows = (c + 7) // 8 * 8
+            rm += [b * N + int(blk[b, s, k if k < c else 0]) for k in range(rows)]
+            bg += [g] * (rows // 8)
+        assert int(n_rows_h[i]) == len(rm)
+        assert np.array_equal(rowmaps[i].cpu().numpy()[:len(rm)], np.array(rm, dtype=np.int32))
+        n_blk = (len(rm) + 127) // 128 * 16
+        want_bg = np.array(bg + [-1] * (n_blk - len(bg)), dtype=np.int32)
+        assert np.array_equal(blockgroups[i].cpu().numpy()[:n_blk], want_bg)
+        k_off += K
