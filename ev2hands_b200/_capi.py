@@ -46,6 +46,9 @@ _SIGNATURES = {
                              c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_ball_query_cnt_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f),
                                 ctypes.POINTER(ctypes.c_int32), c_vp, c_vp, c_vp],
+    "ev2h_first_occurrence_u8": [c_vp, c_int, c_int, c_vp, c_vp],
+    "ev2h_ball_query_uniq_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f),
+                                 ctypes.POINTER(ctypes.c_int32), c_vp, c_vp, c_vp, c_vp, c_vp],
     "ev2h_group_compact_i32": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_vp,
                                ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp],
     "ev2h_sa_msg_fused_compact_tc": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
@@ -208,6 +211,35 @@ def ball_query(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: int, r
                 _check(lib().ev2h_ball_query_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows.contiguous()),
                                                  B, N, S, ns, r2, ks, _p(out), _stream(xyz)), "ev2h_ball_query_f32")
     return (out, cnt) if with_counts else out
+
+
+def first_occurrence(pts8: torch.Tensor) -> torch.Tensor:
+    """pts8 [B,N,8] -> uint8 [B,N]: 1 where the point's record has not occurred earlier in its window."""
+    B, N, _ = pts8.shape
+    out = torch.empty((B, N), dtype=torch.uint8, device=pts8.device)
+    with torch.cuda.device(pts8.device):
+        with _timed("ev2h_first_occurrence_u8"):
+            _check(lib().ev2h_first_occurrence_u8(_p(pts8), B, N, _p(out), _stream(pts8)), "ev2h_first_occurrence_u8")
+    return out
+
+
+def ball_query_uniq(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: int, radii, nsamples, first_flag: torch.Tensor):
+    """-> (idx, uniq_idx, uniq_cnt): the reference's padded list, and the same first-K hits without exact-duplicate points."""
+    _need_cuda_f32(xyz, "xyz")
+    _need_cuda_f32(centres_rows, "centres")
+    B, S, _ = centres_rows.shape
+    ns = len(radii)
+    r2 = (c_f * ns)(*[radius_sq_f32(r) for r in radii])
+    ks = (ctypes.c_int32 * ns)(*[int(k) for k in nsamples])
+    out = torch.empty((B, S, int(sum(nsamples))), dtype=torch.int32, device=xyz.device)
+    uniq = torch.empty_like(out)
+    ucnt = torch.empty((ns, B, S), dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        with _timed("ev2h_ball_query_f32"):
+            _check(lib().ev2h_ball_query_uniq_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows.contiguous()),
+                                                  B, N, S, ns, r2, ks, _p(out), _p(first_flag), _p(uniq), _p(ucnt), _stream(xyz)),
+                   "ev2h_ball_query_uniq_f32")
+    return out, uniq, ucnt
 
 
 def group_compact(idx: torch.Tensor, cnt: torch.Tensor, N: int, nsamples):

@@ -38,8 +38,14 @@ template <int NS>
 __global__ void __launch_bounds__(kBqCentres * kBqSegs)
 ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
                   const float *__restrict__ centres, int N, int S, BallParams prm,
-                  int32_t *__restrict__ out, int32_t *__restrict__ cnt_out) {
+                  int32_t *__restrict__ out, int32_t *__restrict__ cnt_out,
+                  const uint8_t *__restrict__ first_flag, int32_t *__restrict__ uniq_out, int32_t *__restrict__ ucnt_out) {
+    // Optional second list (first_flag != nullptr): the same first-K hits without exact duplicates of an earlier
+    // point (first_flag[b,n] = 0), in index order, for the row compaction; ucnt_out = its length.
     __shared__ float4 pts[kBqTile];
+    __shared__ uint8_t flag_s[kBqTile];
+    __shared__ int ucnt_s[kBqSegs][NS][kBqCentres];
+    __shared__ int uemit_s[NS][kBqCentres];              // unique hits written (i.e. within the first K hits), summed over ranges
     __shared__ int cnt_s[kBqSegs][NS][kBqCentres];      // hits of this tile per (range, radius, centre)
     __shared__ int first_s[kBqSegs][NS][kBqCentres];    // first hit of this tile per (range, radius, centre), N if none
     const int b = blockIdx.y;
@@ -55,6 +61,12 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
     }
     const float qn = sq_norm3(qx, qy, qz);
     int32_t *row = out + ((int64_t)b * S + (live ? s : 0)) * prm.k_total;
+    const bool dedup = first_flag != nullptr;
+    int32_t *urow = dedup ? uniq_out + ((int64_t)b * S + (live ? s : 0)) * prm.k_total : nullptr;
+    int utotal[NS], emitted[NS];                         // unique hits seen so far (same in every warp) / written by this thread
+#pragma unroll
+    for (int k = 0; k < NS; ++k) { utotal[k] = 0; emitted[k] = 0; }
+    if (threadIdx.x < NS * kBqCentres) (&uemit_s[0][0])[threadIdx.x] = 0;     // visible after the first barrier of the tile loop
 
     int total[NS], first[NS];                            // running over the tiles already processed (same in every warp)
 #pragma unroll
@@ -67,43 +79,48 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
             const int64_t g = (int64_t)(t0 + i) * sn;
             const float x = base[g], y = base[sc + g], z = base[2 * sc + g];
             pts[i] = make_float4(x, y, z, sq_norm3(x, y, z));
+            flag_s[i] = dedup ? first_flag[(int64_t)b * N + t0 + i] : 1;
         }
         __syncthreads();
         const int per = (n_tile + kBqSegs - 1) / kBqSegs;
         const int i0 = min(seg * per, n_tile), i1 = min(i0 + per, n_tile);
 
         // pass 1: count
-        int cnt[NS], fst[NS];
+        int cnt[NS], fst[NS], ucnt[NS];
 #pragma unroll
-        for (int k = 0; k < NS; ++k) { cnt[k] = 0; fst[k] = N; }
+        for (int k = 0; k < NS; ++k) { cnt[k] = 0; fst[k] = N; ucnt[k] = 0; }
         for (int i = i0; i < i1; ++i) {
             const float d = sqdist_expanded(qx, qy, qz, qn, pts[i]);
             if (d > prm.r2_max) continue;                // outside every radius
+            const int u = flag_s[i];
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 if (!(d > prm.r2[k])) {                   // group_idx[sqrdists > r**2] = N  (:102)
                     if (cnt[k] == 0) fst[k] = t0 + i;
                     ++cnt[k];
+                    ucnt[k] += u;
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < NS; ++k) { cnt_s[seg][k][lane] = cnt[k]; first_s[seg][k][lane] = fst[k]; }
+        for (int k = 0; k < NS; ++k) { cnt_s[seg][k][lane] = cnt[k]; first_s[seg][k][lane] = fst[k]; ucnt_s[seg][k][lane] = ucnt[k]; }
         __syncthreads();
 
         // offsets of this range, and the tile's totals
-        int off[NS], tile_total[NS];
+        // (the unique-hit offsets ignore the K cut-off: hits are emitted in index order, so those that make
+        // the cut are a prefix of the unique sequence and their positions are unaffected by the ones that do not)
+        int off[NS], tile_total[NS], uoff[NS], utile[NS];
         bool any_room = false;
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            int o = total[k], tt = 0;
+            int o = total[k], tt = 0, uo = utotal[k], ut = 0;
             for (int g = 0; g < kBqSegs; ++g) {
-                const int c = cnt_s[g][k][lane];
-                if (g < seg) o += c;
-                tt += c;
+                const int c = cnt_s[g][k][lane], uc = ucnt_s[g][k][lane];
+                if (g < seg) { o += c; uo += uc; }
+                tt += c; ut += uc;
                 if (first[k] == N && first_s[g][k][lane] != N) first[k] = first_s[g][k][lane];
             }
-            off[k] = o; tile_total[k] = tt;
+            off[k] = o; tile_total[k] = tt; uoff[k] = uo; utile[k] = ut;
             any_room = any_room || (cnt[k] > 0 && o < prm.K[k]);
         }
 
@@ -115,16 +132,30 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     if (!(d > prm.r2[k])) {
-                        if (off[k] < prm.K[k]) row[prm.k_off[k] + off[k]] = t0 + i;
+                        if (off[k] < prm.K[k]) {
+                            row[prm.k_off[k] + off[k]] = t0 + i;
+                            if (dedup && flag_s[i]) { urow[prm.k_off[k] + uoff[k]] = t0 + i; ++emitted[k]; }
+                        }
                         ++off[k];
+                        uoff[k] += flag_s[i];
                     }
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < NS; ++k) total[k] += tile_total[k];
+        for (int k = 0; k < NS; ++k) { total[k] += tile_total[k]; utotal[k] += utile[k]; }
     }
+    if (dedup) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            if (emitted[k]) atomicAdd(&uemit_s[k][lane], emitted[k]);
+    }
+    __syncthreads();
     if (!live) return;
+    if (ucnt_out != nullptr && seg == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) ucnt_out[(int64_t)k * gridDim.y * S + (int64_t)b * S + s] = uemit_s[k][lane];
+    }
     if (cnt_out != nullptr && seg == 0) {                // real (unpadded) neighbours per scale, for the row compaction
 #pragma unroll
         for (int k = 0; k < NS; ++k) cnt_out[(int64_t)k * gridDim.y * S + (int64_t)b * S + s] = min(total[k], prm.K[k]);   // [scale][b*S+s]
@@ -187,14 +218,15 @@ extern "C" int ev2h_index_rows_f32(const float *table_rows, const int32_t *idx, 
 static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                            const float *centres_rows, int B, int N, int S, int n_scales,
                            const float *radius_sq_host, const int32_t *nsample_host,
-                           int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream);
+                           int32_t *out_idx, int32_t *out_cnt, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
+                           ev2h_stream_t stream);
 
 extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                                    const float *centres_rows, int B, int N, int S, int n_scales,
                                    const float *radius_sq_host, const int32_t *nsample_host,
                                    int32_t *out_idx, ev2h_stream_t stream) {
     return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
-                           out_idx, nullptr, stream);
+                           out_idx, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
@@ -202,13 +234,25 @@ extern "C" int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64
                                        const float *radius_sq_host, const int32_t *nsample_host,
                                        int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream) {
     return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
-                           out_idx, out_cnt, stream);
+                           out_idx, out_cnt, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int ev2h_ball_query_uniq_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                        const float *centres_rows, int B, int N, int S, int n_scales,
+                                        const float *radius_sq_host, const int32_t *nsample_host,
+                                        int32_t *out_idx, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
+                                        ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(first_flag && out_uniq && out_ucnt, "ev2h_ball_query_uniq_f32: null argument");
+    return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
+                           out_idx, nullptr, first_flag, out_uniq, out_ucnt, stream);
 }
 
 static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                            const float *centres_rows, int B, int N, int S, int n_scales,
                            const float *radius_sq_host, const int32_t *nsample_host,
-                           int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream) {
+                           int32_t *out_idx, int32_t *out_cnt, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
+                           ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(xyz && centres_rows && out_idx && radius_sq_host && nsample_host, "ev2h_ball_query_f32: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0, "ev2h_ball_query_f32: B, N, S must be positive");
@@ -235,10 +279,10 @@ static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c,
     constexpr int kBqThreads = kBqCentres * kBqSegs;
     cudaStream_t st = as_stream(stream);
     switch (n_scales) {
-        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
-        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
-        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
-        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt); break;
+        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
+        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
+        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
+        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
     }
     return check_launch("ev2h_ball_query_f32");
 }

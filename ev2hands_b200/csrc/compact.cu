@@ -91,7 +91,7 @@ compact_fill_kernel(const int32_t *__restrict__ idx, int idx_ld, const int32_t *
     const int64_t b = g / S;
     int32_t *rm = prm.rowmap[sc], *bg = prm.blockgroup[sc];
     for (int k = lane; k < rows; k += lpg) {
-        const int pt = src[k < real ? k : 0];
+        const int pt = c < 1 ? -1 : src[k < real ? k : 0];             // c == 0: empty ball, the list holds nothing
         rm[off + k] = (pt >= 0 && pt < N) ? (int32_t)(b * N + pt) : -1;
         if ((k & 7) == 0) bg[(off + k) >> 3] = g;
     }
@@ -138,4 +138,65 @@ extern "C" int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int3
     compact_fill_kernel<<<dim3((unsigned)((G + 7) / 8), (unsigned)n_scales), 256, 0, st>>>(idx, idx_ld, cnt, G, N, S,
                                                                                             offs_scratch, n_rows_dev, prm);
     return check_launch("ev2h_group_compact_i32 (fill)");
+}
+
+// ---- exact-duplicate points ------------------------------------------------------------------------------
+// Event windows are drawn WITH replacement from the per-pixel aggregates (reference dataset code, SURVEY.md 8d:
+// ~40 % of a window's 2048 points are exact copies of an earlier point).  Two neighbours with identical records
+// give identical MLP rows, which the max-pool cannot tell apart, so the compacted row list keeps only the first
+// occurrence.  first[b,n] = 1 iff no point m < n of window b has the same 32-byte record.
+namespace ev2h {
+
+constexpr int kUniqSlots = 8192;          // open-addressing table per window, >= 2 x the points hashed at once
+constexpr int kUniqThreads = 1024;
+
+__device__ __forceinline__ bool same_record(const uint4 *rec, int a, int b) {
+    const uint4 a0 = rec[2 * a], a1 = rec[2 * a + 1], b0 = rec[2 * b], b1 = rec[2 * b + 1];
+    return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
+}
+
+__global__ void __launch_bounds__(kUniqThreads)
+first_occurrence_kernel(const float *__restrict__ pts8, int N, uint8_t *__restrict__ first) {
+    __shared__ int table[kUniqSlots];
+    const uint4 *rec = reinterpret_cast<const uint4 *>(pts8 + (int64_t)blockIdx.x * N * 8);
+    uint8_t *out = first + (int64_t)blockIdx.x * N;
+    for (int i = threadIdx.x; i < kUniqSlots; i += kUniqThreads) table[i] = 0x7fffffff;
+    __syncthreads();
+    auto slot_of = [&](int n) {
+        const uint4 a = rec[2 * n], b = rec[2 * n + 1];
+        uint32_t h = a.x * 0x9E3779B1u ^ a.y * 0x85EBCA77u ^ a.z * 0xC2B2AE3Du ^ a.w * 0x27D4EB2Fu ^ b.x * 0x165667B1u;
+        h ^= h >> 15;
+        return (int)(h & (kUniqSlots - 1));
+    };
+    // phase 1: every record ends up in exactly one slot holding the smallest index that carries it
+    for (int n = threadIdx.x; n < N; n += kUniqThreads) {
+        int h = slot_of(n);
+        for (;;) {
+            const int cur = atomicCAS(&table[h], 0x7fffffff, n);
+            if (cur == 0x7fffffff) break;                                 // claimed an empty slot
+            if (same_record(rec, cur, n)) { atomicMin(&table[h], n); break; }
+            h = (h + 1) & (kUniqSlots - 1);
+        }
+    }
+    __syncthreads();
+    // phase 2: look the record up again; the slot now holds its first occurrence
+    for (int n = threadIdx.x; n < N; n += kUniqThreads) {
+        int h = slot_of(n);
+        for (;;) {
+            const int cur = table[h];
+            if (same_record(rec, cur, n)) { out[n] = cur == n ? 1 : 0; break; }
+            h = (h + 1) & (kUniqSlots - 1);
+        }
+    }
+}
+
+}  // namespace ev2h
+
+extern "C" int ev2h_first_occurrence_u8(const float *pts8, int B, int N, uint8_t *first, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(pts8 && first, "ev2h_first_occurrence_u8: null argument");
+    EV2H_REQUIRE(B > 0 && N > 0 && ((uintptr_t)pts8 & 15) == 0, "ev2h_first_occurrence_u8: bad sizes or misaligned records");
+    if (2 * N > kUniqSlots) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_first_occurrence_u8: N=%d exceeds %d points per window", N, kUniqSlots / 2);
+    first_occurrence_kernel<<<(unsigned)B, kUniqThreads, 0, as_stream(stream)>>>(pts8, N, first);
+    return check_launch("ev2h_first_occurrence_u8");
 }

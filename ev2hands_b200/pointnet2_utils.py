@@ -49,6 +49,8 @@ _FUSED_ENABLED = os.environ.get("EV2H_FUSED", "1") != "0"
 _TF32X3_PURE = os.environ.get("EV2H_TF32X3_PURE", "0") == "1"
 # Run the fused kernel over compacted rows (padded duplicate neighbours skipped; bit-identical results).
 _COMPACT = os.environ.get("EV2H_COMPACT", "1") != "0"
+# ... and over exact-duplicate points only once (event windows are sampled with replacement).
+_DEDUP = os.environ.get("EV2H_DEDUP", "1") != "0"
 # Evaluate layer 1 per point (instead of per gathered row) also for narrow inputs; experiment switch.
 _PER_POINT_ALWAYS = os.environ.get("EV2H_PER_POINT", "0") == "1"
 
@@ -297,7 +299,17 @@ class PointNetSetAbstractionMsg(nn.Module):
         self._folded = [_FoldedMLP() for _ in mlp_list]
 
     # ---- shared front end: FPS + ball query -----------------------------------------
-    def _sample(self, xyz, fps_start):
+    def _pts8(self, xyz, points, strides):
+        """[features | xyz | 0] per point, 32 bytes: one sector per gathered neighbour (gather mode of the fused kernel)."""
+        B, _, N = xyz.shape
+        D = 0 if points is None else points.shape[1]
+        pts8 = torch.zeros((B, N, 8), dtype=torch.float32, device=xyz.device)
+        if points is not None:
+            _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, pts8, N * 8, 8, 0)
+        _capi.transpose(xyz, strides, B, 3, N, pts8, N * 8, 8, D)
+        return pts8
+
+    def _sample(self, xyz, fps_start, points=None, fused=False):
         B, _, N = xyz.shape
         S = self.npoint
         if fps_start is None:
@@ -305,16 +317,29 @@ class PointNetSetAbstractionMsg(nn.Module):
             fps_start = torch.randint(0, N, (B,), dtype=torch.long)
         strides = _capi.cf_strides(xyz)
         fps_idx, centres_rows, new_xyz = _capi.fps(xyz, strides, fps_start, B, N, S)
-        ball, self._ball_cnt = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list, with_counts=True)
+        D = 0 if points is None else points.shape[1]
+        self._pts8_cache = None
+        if (fused and _COMPACT and _DEDUP and _FUSED_ENABLED and _mlp_precision in ("tf32x3", "bf16")
+                and not (D + 3 > 8 or _PER_POINT_ALWAYS) and N <= 4096 and all(k % 8 == 0 for k in self.nsample_list)):
+            # gather mode: neighbours whose 32-byte record repeats an earlier point give identical rows; list them once
+            self._pts8_cache = self._pts8(xyz, points, strides)
+            first = _capi.first_occurrence(self._pts8_cache)
+            ball, uniq, ucnt = _capi.ball_query_uniq(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list, first)
+            self._compact_src = (uniq, ucnt)
+        else:
+            ball, cnt = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list, with_counts=True)
+            self._compact_src = (ball, cnt)
         return strides, fps_idx, centres_rows, new_xyz, ball
 
     def forward(self, xyz, points, fps_start=None):
         """xyz [B,3,N], points [B,D,N] or None -> (new_xyz [B,3,S], new_points [B,sum D',S])."""
         _check_inputs(xyz, points)
+        autograd = _wants_autograd(self, points)
         with torch.no_grad():
-            strides, fps_idx, centres_rows, new_xyz, ball = self._sample(xyz.detach(), fps_start)
+            strides, fps_idx, centres_rows, new_xyz, ball = self._sample(xyz.detach(), fps_start, None if autograd else points,
+                                                                          fused=not autograd)
         self.last_fps_idx, self.last_ball_idx = fps_idx, ball        # exposed for parity tests
-        if _wants_autograd(self, points):
+        if autograd:
             return new_xyz, self._forward_autograd(xyz, points, strides, centres_rows, ball)
         with torch.no_grad():
             return new_xyz, self._forward_fused(xyz, points, strides, centres_rows, ball)
@@ -338,11 +363,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         pts8 = P = C = None
         p_cols = []
         if any(fused) and not per_point:
-            # [features | xyz | 0] per point, 32 bytes: one sector per gathered neighbour
-            pts8 = torch.zeros((B, N, 8), dtype=torch.float32, device=xyz.device)
-            if points is not None:
-                _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, pts8, N * 8, 8, 0)
-            _capi.transpose(xyz, strides, B, 3, N, pts8, N * 8, 8, D)
+            pts8 = self._pts8_cache if self._pts8_cache is not None else self._pts8(xyz, points, strides)
         elif any(fused):
             # layer 1 once per point: P = W1'[f; xyz] + b1' for every fused scale side by side,
             # C = W1'_xyz centre per centre (see sa_fused_tc.cu)
@@ -380,7 +401,7 @@ class PointNetSetAbstractionMsg(nn.Module):
 
         compact = None
         if any(fused) and _COMPACT and all(k % 8 == 0 for k in self.nsample_list):
-            compact = _capi.group_compact(ball, self._ball_cnt, N, self.nsample_list)
+            compact = _capi.group_compact(self._compact_src[0], self._compact_src[1], N, self.nsample_list)
         self.last_compact_rows = None if compact is None else compact[2]     # int32 [n_scales] on the device (diagnostics)
 
         feats_rows = None

@@ -98,6 +98,19 @@ EV2H_API int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64_t
                         int n_scales, const float *radius_sq_host, const int32_t *nsample_host,
                         int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream);
 
+/* first[b,n] = 1 iff no point m < n of window b has the same 32-byte record pts8[b,m,:] (bitwise).  Event
+ * windows are sampled with replacement, so ~40 % of the points are exact copies of an earlier one; copies give
+ * identical MLP rows and the compacted row list keeps only the first.  N <= 4096. */
+EV2H_API int ev2h_first_occurrence_u8(const float *pts8, int B, int N, uint8_t *first, ev2h_stream_t stream);
+/* Ball query that also emits, per centre and scale, the first-K hit list WITHOUT the hits whose first flag is 0
+ * (out_uniq int32 [B,S,sum K], only the first out_ucnt[scale,b,s] entries of each block are written;
+ * out_ucnt int32 [n_scales,B,S]).  out_idx is the reference's padded list as in ev2h_ball_query_f32. */
+EV2H_API int ev2h_ball_query_uniq_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                        const float *centres_rows, int B, int N, int S,
+                        int n_scales, const float *radius_sq_host, const int32_t *nsample_host,
+                        int32_t *out_idx, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
+                        ev2h_stream_t stream);
+
 /* Row compaction for the fused kernel.  query_ball_point pads every group to K neighbours with copies of
  * the first one (pointnet2_utils.py:104-106); the max-pool cannot see those copies, so the shared MLP need
  * not evaluate them.  For every scale i of a layer this builds the list of rows actually needed - per group
@@ -106,7 +119,8 @@ EV2H_API int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64_t
  *   blockgroup_host[i]  int32 [B*S*K_i/8 + 16] global group b*S + centre of every 8-row block (-1 past the end)
  *   n_rows_dev          int32 [n_scales]       compact rows per scale
  * (device buffers; the two pointer tables live on the host).  offs_scratch: int32 [n_scales * B*S].
- * idx / cnt come from ev2h_ball_query_cnt_f32; every K_i must be a multiple of 8. */
+ * idx / cnt come from ev2h_ball_query_cnt_f32, or (out_uniq, out_ucnt) from ev2h_ball_query_uniq_f32 to drop
+ * exact-duplicate points as well; every K_i must be a multiple of 8. */
 EV2H_API int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int32_t *cnt, int B, int N, int S, int n_scales,
                                     const int32_t *nsample_host, int32_t *offs_scratch,
                                     int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,

@@ -526,17 +526,55 @@ def test_compacted_rows_are_bit_identical_to_dense(precision):
     ev = dev(synth.make_windows(5, 2048, seed=77))
     starts = (torch.from_numpy(synth.make_start_indices(5, 2048, 8)), torch.from_numpy(synth.make_start_indices(5, 512, 9)))
     outs = {}
-    old = pu._COMPACT
+    old = (pu._COMPACT, pu._DEDUP)
     try:
-        for flag in (False, True):
-            pu._COMPACT = flag
+        for flags in ((False, False), (True, False), (True, True)):       # dense / compacted / compacted + duplicate points once
+            pu._COMPACT, pu._DEDUP = flags
             with torch.no_grad():
                 l3, lv = enc(ev, fps_starts=starts, return_levels=True)
-            outs[flag] = (l3.cpu().numpy(), lv["l1_points"].cpu().numpy(), lv["l2_points"].cpu().numpy())
+            outs[flags] = (l3.cpu().numpy(), lv["l1_points"].cpu().numpy(), lv["l2_points"].cpu().numpy())
     finally:
-        pu._COMPACT = old
-    for a, b in zip(outs[False], outs[True]):
-        assert np.array_equal(a, b)
+        pu._COMPACT, pu._DEDUP = old
+    for flags in ((True, False), (True, True)):
+        for a, b in zip(outs[(False, False)], outs[flags]):
+            assert np.array_equal(a, b)
+
+
+def test_first_occurrence_and_deduplicated_ball_query():
+    rs = np.random.RandomState(9)
+    B, N, S = 3, 900, 40
+    base = rs.rand(B, 300, 8).astype(np.float32)
+    base[:, :, 7] = 0
+    pick = rs.randint(0, 300, size=(B, N))
+    pts8 = np.stack([base[b][pick[b]] for b in range(B)])                 # sampling with replacement: many exact copies
+    first = _capi.first_occurrence(dev(pts8)).cpu().numpy()
+    want_first = np.zeros((B, N), dtype=np.uint8)
+    for b in range(B):
+        seen = set()
+        for n in range(N):
+            key = pts8[b, n].tobytes()
+            if key not in seen:
+                seen.add(key); want_first[b, n] = 1
+    assert np.array_equal(first, want_first)
+    xyz = np.ascontiguousarray(pts8[:, :, 4:7].transpose(0, 2, 1))
+    centres = np.ascontiguousarray(pts8[:, :S, 4:7])
+    Ks, radii = [8, 32], [0.2, 0.45]
+    xd = dev(xyz)
+    idx, uniq, ucnt = _capi.ball_query_uniq(xd, _capi.cf_strides(xd), dev(centres), N, radii, Ks, dev(first))
+    idx2 = _capi.ball_query(xd, _capi.cf_strides(xd), dev(centres), N, radii, Ks)
+    assert torch.equal(idx, idx2)                                       # the reference list is unchanged
+    idx_h, uniq_h, ucnt_h = idx.cpu().numpy(), uniq.cpu().numpy(), ucnt.cpu().numpy()
+    k_off = 0
+    for i, K in enumerate(Ks):
+        for b in range(B):
+            for s in range(S):
+                blk = idx_h[b, s, k_off:k_off + K]
+                real = len(np.unique(blk))                               # ascending + padded with the first: distinct = real hits
+                hits = blk[:real]
+                want = [int(h) for h in hits if want_first[b, h]]
+                assert ucnt_h[i, b, s] == len(want)
+                assert list(uniq_h[b, s, k_off:k_off + len(want)]) == want
+        k_off += K
 
 
 def test_compaction_tables_match_a_numpy_restatement():
