@@ -205,9 +205,24 @@ def run_ours(args):
     ev_dev = ev_host.to(device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
 
-    def step_resident():
+    def forward_resident(ev, a, b):
         with torch.no_grad():
-            return enc(ev_dev, fps_starts=(s1, s2))
+            return enc(ev, fps_starts=(a, b))
+
+    graphed = None
+    if args.graph:
+        # the ~35 launches of a step replayed as one CUDA graph (inputs resident, shapes fixed); eager if capture fails
+        try:
+            from ev2hands_b200.encoder import GraphedForward
+            graphed = GraphedForward(forward_resident, ev_dev, s1, s2)
+        except Exception as exc:      # noqa: BLE001
+            print("bench.py: CUDA graph capture failed (%s); timing the eager path" % exc, file=sys.stderr)
+            graphed = None
+
+    def step_resident():
+        if graphed is not None and not _capi.LOG.timing:
+            return graphed(ev_dev, s1, s2)
+        return forward_resident(ev_dev, s1, s2)
 
     def barrier():
         torch.cuda.synchronize()
@@ -219,10 +234,21 @@ def run_ours(args):
         step_resident()
     barrier()
 
+    # ---- instrumented pass (eager): per-kernel device time from CUDA events around every launch, same K steps,
+    # same L2 flush; feeds the roofline (time of the MLP kernels) and the launch count
+    _capi.LOG.reset(timing=True)
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        forward_resident(ev_dev, s1, s2)
+    barrier()
+    launches = _capi.LOG.count
+    kern = _capi.LOG.totals_ms()
+    _capi.LOG.reset(timing=False)
+
     # ---- timed region: K steps, device time per step from CUDA events, L2 flushed between steps
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
-    _capi.LOG.reset(timing=True)
     evs = []
     barrier()
     wall0 = time.perf_counter()
@@ -238,9 +264,6 @@ def run_ours(args):
     clocks = sampler.finish()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
-    launches = _capi.LOG.count
-    kern = _capi.LOG.totals_ms()
-    _capi.LOG.reset(timing=False)
 
     # ---- end to end through the module API with host buffers (H2D + forward + D2H per step)
     out_host = torch.empty((B, 1024), dtype=torch.float32).pin_memory()
@@ -329,7 +352,9 @@ def run_ours(args):
                    "windows_per_gpu": B, "global_windows": B * world,
                    "mlp_path": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 3-product split x=hi+lo, w=hi+lo: tf32 hi*hi + two bf16 correction products (fp32-level accuracy)",
                                 "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate"}[args.mlp],
-                   "l2": "256 MiB buffer written between timed steps (L2 flush)"},
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                   "launch": "one CUDA graph replay per step" if graphed is not None else "eager launches through the module API",
+                   "kernel_times": "separate eager pass of the same K steps with CUDA events around every launch"},
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": (achieved_tflops / peak_tflops) if achieved_tflops else None, "traffic": traffic,
                      "kernel": "%s (shared MLP, %d launches/step)" % ("linear_relu_kernel" if args.mlp == "fp32" else "sa_fused_tc_kernel + linear_tc_kernel", mlp_n // max(args.steps, 1)),
@@ -375,6 +400,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--with-decoder", action="store_true", help="also time encoder + feature-propagation decoder (secondary number)")
     ap.add_argument("--points", type=int, default=N_POINTS, help="events per window (2048 = the model's default; 16384 = config 5)")
     ap.add_argument("--mlp", choices=["fp32", "tf32x3", "bf16"], default=os.environ.get("EV2H_MLP", "tf32x3"),

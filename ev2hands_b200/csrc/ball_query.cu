@@ -42,8 +42,8 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
                   const uint8_t *__restrict__ first_flag, int32_t *__restrict__ uniq_out, int32_t *__restrict__ ucnt_out) {
     // Optional second list (first_flag != nullptr): the same first-K hits without exact duplicates of an earlier
     // point (first_flag[b,n] = 0), in index order, for the row compaction; ucnt_out = its length.
+    // The flag travels in the sign bit of the staged |p|^2 (a sum of squares is never negative), read back with fabsf.
     __shared__ float4 pts[kBqTile];
-    __shared__ uint8_t flag_s[kBqTile];
     __shared__ int ucnt_s[kBqSegs][NS][kBqCentres];
     __shared__ int uemit_s[NS][kBqCentres];              // unique hits written (i.e. within the first K hits), summed over ranges
     __shared__ int cnt_s[kBqSegs][NS][kBqCentres];      // hits of this tile per (range, radius, centre)
@@ -78,8 +78,9 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
         for (int i = threadIdx.x; i < n_tile; i += kBqCentres * kBqSegs) {
             const int64_t g = (int64_t)(t0 + i) * sn;
             const float x = base[g], y = base[sc + g], z = base[2 * sc + g];
-            pts[i] = make_float4(x, y, z, sq_norm3(x, y, z));
-            flag_s[i] = dedup ? first_flag[(int64_t)b * N + t0 + i] : 1;
+            const float nn = sq_norm3(x, y, z);
+            const bool dup = dedup && first_flag[(int64_t)b * N + t0 + i] == 0;
+            pts[i] = make_float4(x, y, z, dup ? __uint_as_float(__float_as_uint(nn) | 0x80000000u) : nn);
         }
         __syncthreads();
         const int per = (n_tile + kBqSegs - 1) / kBqSegs;
@@ -90,9 +91,11 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
 #pragma unroll
         for (int k = 0; k < NS; ++k) { cnt[k] = 0; fst[k] = N; ucnt[k] = 0; }
         for (int i = i0; i < i1; ++i) {
-            const float d = sqdist_expanded(qx, qy, qz, qn, pts[i]);
+            float4 pw = pts[i];
+            const int u = (int)(__float_as_uint(pw.w) >> 31) ^ 1;
+            pw.w = fabsf(pw.w);
+            const float d = sqdist_expanded(qx, qy, qz, qn, pw);
             if (d > prm.r2_max) continue;                // outside every radius
-            const int u = flag_s[i];
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
                 if (!(d > prm.r2[k])) {                   // group_idx[sqrdists > r**2] = N  (:102)
@@ -127,17 +130,20 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
         // pass 2: write the hits of this range at their final positions
         if (live && any_room) {
             for (int i = i0; i < i1; ++i) {
-                const float d = sqdist_expanded(qx, qy, qz, qn, pts[i]);
+                float4 pw = pts[i];
+                const int u = (int)(__float_as_uint(pw.w) >> 31) ^ 1;
+                pw.w = fabsf(pw.w);
+                const float d = sqdist_expanded(qx, qy, qz, qn, pw);
                 if (d > prm.r2_max) continue;
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     if (!(d > prm.r2[k])) {
                         if (off[k] < prm.K[k]) {
                             row[prm.k_off[k] + off[k]] = t0 + i;
-                            if (dedup && flag_s[i]) { urow[prm.k_off[k] + uoff[k]] = t0 + i; ++emitted[k]; }
+                            if (dedup && u) { urow[prm.k_off[k] + uoff[k]] = t0 + i; ++emitted[k]; }
                         }
                         ++off[k];
-                        uoff[k] += flag_s[i];
+                        uoff[k] += u;
                     }
                 }
             }
