@@ -116,24 +116,35 @@ def oracle_states():
     return {n: synth.random_state_for(synth.ENCODER_SPECS[n], seed=100 + i) for i, n in enumerate(("sa1", "sa2", "sa3"))}
 
 
-def time_cpu_oracle(n_windows: int, reps: int, warmup: int):
-    """Reference algorithm (oracle port) on the host: returns (windows/s, threads, seconds per rep)."""
+def time_cpu_oracle(n_windows: int, reps: int, warmup: int, device: str = "cpu"):
+    """Reference algorithm (oracle port) on the host - or, device="cuda", the same stock-PyTorch ops on the GPU,
+    the comparator SURVEY.md 8d asks for since the reference ships no kernels: returns (windows/s, threads, seconds per rep)."""
     from ev2hands_b200 import synth
     from oracle import sa_oracle
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     states = oracle_states()
-    ev = torch.from_numpy(synth.make_windows(n_windows, N_POINTS, seed=1234 + 1))
-    starts = {"sa1": torch.from_numpy(synth.make_start_indices(n_windows, N_POINTS, 0)),
-              "sa2": torch.from_numpy(synth.make_start_indices(n_windows, 512, 1))}
+    ev = torch.from_numpy(synth.make_windows(n_windows, N_POINTS, seed=1234 + 1)).to(device)
+    starts = {"sa1": torch.from_numpy(synth.make_start_indices(n_windows, N_POINTS, 0)).to(device),
+              "sa2": torch.from_numpy(synth.make_start_indices(n_windows, 512, 1)).to(device)}
+    cuda = device != "cpu"
+    old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    if cuda:                                     # fp32 arithmetic, like the reference on its own hardware
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     times = []
     with torch.no_grad():
         for i in range(warmup + reps):
+            if cuda:
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
             sa_oracle.encoder_forward(states, synth.ENCODER_SPECS, ev, starts)
+            if cuda:
+                torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
     return n_windows / (sum(times) / len(times)), threads, times
 
 
@@ -386,6 +397,13 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": threads, "kind": "port",
                                 "sample": "4 windows per run, 1 warm-up + 3 timed runs of oracle/sa_oracle.py (torch CPU, "
                                           "the reference's algorithm op for op)"}
+        try:      # the same stock-PyTorch ops on this GPU (the reference ships no kernels): informational comparator
+            gwps, _, _ = time_cpu_oracle(WINDOWS_PER_GPU, 2, 1, device="cuda")
+            line["torch_gpu_baseline"] = {"value": gwps, "unit": "windows/s", "kind": "port",
+                                          "sample": "64 windows per run (the workload's batch), 1 warm-up + 2 timed runs of oracle/sa_oracle.py on cuda:0 "
+                                                    "(stock PyTorch fp32 ops, Python FPS loop, materialised distance matrices)"}
+        except Exception as exc:      # noqa: BLE001
+            line["torch_gpu_baseline"] = {"unavailable": str(exc)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

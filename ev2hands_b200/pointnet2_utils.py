@@ -376,28 +376,36 @@ class PointNetSetAbstractionMsg(nn.Module):
             C = torch.empty((B * S, c1_total), dtype=torch.float32, device=xyz.device)
             ctr4 = torch.zeros((B * S, 4), dtype=torch.float32, device=xyz.device)
             ctr4[:, :3] = centres_rows.reshape(B * S, 3)
+            # every fused scale's first layer in ONE GEMM: the folded weights side by side (same input rows)
+            firsts = [layers[0] for layers, f in zip(all_layers, fused) if f]
+            key = tuple(L0["wt"].data_ptr() for L0 in firsts)
+            cat = getattr(self, "_first_cat", None)
+            if cat is None or cat["key"] != key:
+                rows = firsts[0]["wt"].shape[0]
+                wt = torch.zeros((rows, (c1_total + 127) // 128 * 128), dtype=torch.float32, device=xyz.device)
+                bias = torch.zeros((wt.shape[1],), dtype=torch.float32, device=xyz.device)
+                c = 0
+                for L0 in firsts:
+                    wt[:, c:c + L0["cout"]] = L0["wt"][:, :L0["cout"]]
+                    bias[c:c + L0["cout"]] = L0["bias"][:L0["cout"]]
+                    c += L0["cout"]
+                wx = torch.zeros((16, wt.shape[1]), dtype=torch.float32, device=xyz.device)
+                wx[:3] = wt[D:D + 3]
+                cat = self._first_cat = {"key": key, "wt": wt, "bias": bias, "wt_xyz": wx, "zero_bias": torch.zeros_like(bias), "packed": {}}
+            if mode == _capi.TC_TF32X3 and _capi.tc_supported(c1_total, 0):
+                # the wide per-point layer on the tensor cores (fp32-level accuracy); bf16 mode keeps it
+                # in exact fp32 so that only the two tensor-core layers carry bf16 rounding
+                if mode not in cat["packed"]:
+                    cat["packed"][mode] = _capi.tc_pack(cat["wt"], D + 3, c1_total, mode)
+                _capi.linear_tc_no_relu(x_pts, B * N, ld_pts, D + 3, cat["packed"][mode], cat["bias"], c1_total, P, c1_total, 0, mode)
+            else:
+                _capi.linear_no_relu(x_pts, B * N, ld_pts, D + 3, cat["wt"], cat["bias"], c1_total, P, c1_total, 0)
+            _capi.linear_no_relu(ctr4, B * S, 4, 3, cat["wt_xyz"], cat["zero_bias"], c1_total, C, c1_total, 0)
             col = 0
             for layers, f in zip(all_layers, fused):
-                if not f:
-                    p_cols.append(None)
-                    continue
-                L0 = layers[0]
-                if "wt_xyz" not in L0:
-                    wx = torch.zeros((16, L0["wt"].shape[1]), dtype=torch.float32, device=xyz.device)
-                    wx[:3] = L0["wt"][D:D + 3]
-                    L0["wt_xyz"], L0["zero_bias"] = wx, torch.zeros_like(L0["bias"])
-                if mode == _capi.TC_TF32X3 and _capi.tc_supported(L0["cout"], 0):
-                    # the wide per-point layer on the tensor cores (fp32-level accuracy); bf16 mode keeps it
-                    # in exact fp32 so that only the two tensor-core layers carry bf16 rounding
-                    key = (mode, 32, 16)
-                    if key not in L0["packed"]:
-                        L0["packed"][key] = _capi.tc_pack(L0["wt"], L0["cin"], L0["cout"], mode)
-                    _capi.linear_tc_no_relu(x_pts, B * N, ld_pts, D + 3, L0["packed"][key], L0["bias"], L0["cout"], P, c1_total, col, mode)
-                else:
-                    _capi.linear_no_relu(x_pts, B * N, ld_pts, D + 3, L0["wt"], L0["bias"], L0["cout"], P, c1_total, col)
-                _capi.linear_no_relu(ctr4, B * S, 4, 3, L0["wt_xyz"], L0["zero_bias"], L0["cout"], C, c1_total, col)
-                p_cols.append(col)
-                col += L0["cout"]
+                p_cols.append(col if f else None)
+                if f:
+                    col += layers[0]["cout"]
 
         compact = None
         if any(fused) and _COMPACT and all(k % 8 == 0 for k in self.nsample_list):

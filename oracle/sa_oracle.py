@@ -52,7 +52,7 @@ def pairwise_sqdist(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
 
 def take_rows(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """table [B,N,C], idx [B,...] int64 -> [B,...,C]."""
-    b = torch.arange(table.shape[0]).view(-1, *([1] * (idx.dim() - 1)))
+    b = torch.arange(table.shape[0], device=table.device).view(-1, *([1] * (idx.dim() - 1)))
     return table[b.expand_as(idx), idx]
 
 
@@ -64,10 +64,11 @@ def fps(xyz: torch.Tensor, n_sample: int, start: torch.Tensor | None = None) -> 
     B, N, _ = xyz.shape
     if start is None:
         start = torch.randint(0, N, (B,), dtype=torch.long)
-    picked = torch.zeros(B, n_sample, dtype=torch.long)
-    best = torch.full((B, N), 1e10)
-    cur = start.clone()
-    rows = torch.arange(B)
+    dev = xyz.device                                    # (runs on any device; the reference timing uses the CPU)
+    picked = torch.zeros(B, n_sample, dtype=torch.long, device=dev)
+    best = torch.full((B, N), 1e10, device=dev)
+    cur = start.clone().to(dev)
+    rows = torch.arange(B, device=dev)
     for i in range(n_sample):
         picked[:, i] = cur
         c = xyz[rows, cur].unsqueeze(1)
@@ -83,7 +84,7 @@ def ball_query(radius: float, n_neighbor: int, xyz: torch.Tensor, centres: torch
     with the first hit.  [B,N,3],[B,S,3] -> int64 [B,S,n_neighbor]."""
     B, N, _ = xyz.shape
     S = centres.shape[1]
-    ids = torch.arange(N, dtype=torch.long).expand(B, S, N).clone()
+    ids = torch.arange(N, dtype=torch.long, device=xyz.device).expand(B, S, N).clone()
     ids[pairwise_sqdist(centres, xyz) > radius ** 2] = N
     ids = ids.sort(dim=-1).values[:, :, :n_neighbor]
     first = ids[:, :, :1].expand(-1, -1, n_neighbor)
@@ -95,7 +96,7 @@ def ball_query(radius: float, n_neighbor: int, xyz: torch.Tensor, centres: torch
 def group_all(xyz: torch.Tensor, feats: torch.Tensor | None):
     """One group holding every point; channels [xyz(uncentred), feats]."""
     B, N, C = xyz.shape
-    centre = torch.zeros(B, 1, C)
+    centre = torch.zeros(B, 1, C, device=xyz.device)
     g = xyz.view(B, 1, N, C)
     if feats is not None:
         g = torch.cat([g, feats.view(B, 1, N, -1)], dim=-1)
@@ -105,7 +106,8 @@ def group_all(xyz: torch.Tensor, feats: torch.Tensor | None):
 def shared_mlp_max(x: torch.Tensor, layers) -> torch.Tensor:
     """x [B,C,K,S]; layers = [(W[Co,Ci,1,1], b, gamma, beta, mean, var)...];
     1x1 conv + eval-mode BatchNorm + ReLU per layer, then max over K."""
-    for (w, b, gamma, beta, mean, var) in layers:
+    for layer in layers:
+        w, b, gamma, beta, mean, var = (t.to(x.device) for t in layer)
         x = F.relu(F.batch_norm(F.conv2d(x, w, b), mean, var, gamma, beta, False, 0.1, BN_EPS))
     return x.max(dim=2).values
 
@@ -210,7 +212,8 @@ def fp_forward(state: dict, spec: dict, xyz1_cf: torch.Tensor, xyz2_cf: torch.Te
         up = torch.sum(take_rows(p2, idx) * w.view(B, N, 3, 1), dim=2)
     h = up if points1_cf is None else torch.cat([points1_cf.permute(0, 2, 1).contiguous(), up], dim=-1)
     h = h.permute(0, 2, 1).contiguous()
-    for (w_, b_, gamma, beta, mean, var) in _layers(state, "mlp_convs.{j}", "mlp_bns.{j}", len(spec["mlp"])):
+    for layer in _layers(state, "mlp_convs.{j}", "mlp_bns.{j}", len(spec["mlp"])):
+        w_, b_, gamma, beta, mean, var = (t.to(h.device) for t in layer)
         h = F.relu(F.batch_norm(F.conv1d(h, w_, b_), mean, var, gamma, beta, False, 0.1, BN_EPS))
     return (h, aux) if return_aux else h
 
