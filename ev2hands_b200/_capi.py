@@ -49,7 +49,10 @@ _SIGNATURES = {
     "ev2h_first_occurrence_u8": [c_vp, c_int, c_int, c_vp, c_vp],
     "ev2h_ball_query_uniq_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f),
                                  ctypes.POINTER(ctypes.c_int32), c_vp, c_vp, c_vp, c_vp, c_vp],
-    "ev2h_group_compact_i32": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32), c_vp,
+    "ev2h_ball_query_compact_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f),
+                                    ctypes.POINTER(ctypes.c_int32), c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                                    c_vp, c_vp],
+    "ev2h_group_compact_i32": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32),
                                ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp],
     "ev2h_sa_msg_fused_compact_tc": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                      c_vp, c_int, c_vp, c_int, c_vp,
@@ -95,7 +98,7 @@ def lib() -> ctypes.CDLL:
 
 class LaunchLog:
     """Counts kernel launches (every compute entry point of the ABI enqueues exactly one
-    kernel, ev2h_group_compact_i32 two) and, when ``timing`` is on, brackets each with CUDA events on its stream so
+    kernel) and, when ``timing`` is on, brackets each with CUDA events on its stream so
     bench.py can report per-kernel device time from inside the timed region."""
 
     def __init__(self):
@@ -242,6 +245,31 @@ def ball_query_uniq(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: i
     return out, uniq, ucnt
 
 
+def ball_query_compact(xyz: torch.Tensor, strides, centres_rows: torch.Tensor, N: int, radii, nsamples, first_flag=None):
+    """Ball query + compacted row lists in one kernel -> (idx, rowmaps, blockgroups, n_rows); first_flag (uint8 [B,N])
+    additionally lists exact-duplicate points once."""
+    _need_cuda_f32(xyz, "xyz")
+    _need_cuda_f32(centres_rows, "centres")
+    B, S, _ = centres_rows.shape
+    ns = len(radii)
+    dev = xyz.device
+    r2 = (c_f * ns)(*[radius_sq_f32(r) for r in radii])
+    ks = (ctypes.c_int32 * ns)(*[int(k) for k in nsamples])
+    out = torch.empty((B, S, int(sum(nsamples))), dtype=torch.int32, device=dev)
+    uniq = torch.empty_like(out) if first_flag is not None else None
+    rowmaps = [torch.empty((B * S * int(k),), dtype=torch.int32, device=dev) for k in nsamples]
+    blockgroups = [torch.empty((B * S * int(k) // 8,), dtype=torch.int32, device=dev) for k in nsamples]
+    n_rows = torch.empty((ns,), dtype=torch.int32, device=dev)
+    a_rm = (c_vp * ns)(*[t.data_ptr() for t in rowmaps])
+    a_bg = (c_vp * ns)(*[t.data_ptr() for t in blockgroups])
+    with torch.cuda.device(dev):
+        with _timed("ev2h_ball_query_f32"):
+            _check(lib().ev2h_ball_query_compact_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows.contiguous()),
+                                                     B, N, S, ns, r2, ks, _p(out), _p(first_flag), _p(uniq), a_rm, a_bg, _p(n_rows),
+                                                     _stream(xyz)), "ev2h_ball_query_compact_f32")
+    return out, rowmaps, blockgroups, n_rows
+
+
 def group_compact(idx: torch.Tensor, cnt: torch.Tensor, N: int, nsamples):
     """Compacted row lists of every scale of a layer (ev2h_group_compact_i32):
     -> (rowmaps, blockgroups, n_rows): two lists of int32 device tensors and the int32 [n_scales] row counts."""
@@ -249,15 +277,14 @@ def group_compact(idx: torch.Tensor, cnt: torch.Tensor, N: int, nsamples):
     ns = len(nsamples)
     dev = idx.device
     rowmaps = [torch.empty((B * S * int(k),), dtype=torch.int32, device=dev) for k in nsamples]
-    blockgroups = [torch.empty((B * S * int(k) // 8 + 16,), dtype=torch.int32, device=dev) for k in nsamples]
+    blockgroups = [torch.empty((B * S * int(k) // 8,), dtype=torch.int32, device=dev) for k in nsamples]
     n_rows = torch.empty((ns,), dtype=torch.int32, device=dev)
-    offs = torch.empty((ns * B * S,), dtype=torch.int32, device=dev)
     ks = (ctypes.c_int32 * ns)(*[int(k) for k in nsamples])
     a_rm = (c_vp * ns)(*[t.data_ptr() for t in rowmaps])
     a_bg = (c_vp * ns)(*[t.data_ptr() for t in blockgroups])
     with torch.cuda.device(dev):
-        with _timed("ev2h_group_compact_i32", launches=2):
-            _check(lib().ev2h_group_compact_i32(_p(idx), idx.shape[-1], _p(cnt), B, N, S, ns, ks, _p(offs), a_rm, a_bg, _p(n_rows),
+        with _timed("ev2h_group_compact_i32"):
+            _check(lib().ev2h_group_compact_i32(_p(idx), idx.shape[-1], _p(cnt), B, N, S, ns, ks, a_rm, a_bg, _p(n_rows),
                                                 _stream(idx)), "ev2h_group_compact_i32")
     return rowmaps, blockgroups, n_rows
 

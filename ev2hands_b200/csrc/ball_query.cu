@@ -10,6 +10,7 @@
 // Bit-exactness with the reference lives in sqdist_expanded(): same expression,
 // same rounding order as aten's  -2*matmul + |q|^2 + |p|^2  (see SURVEY.md 7.1).
 #include "common.cuh"
+#include <string.h>
 #include "geom.cuh"
 
 namespace ev2h {
@@ -18,6 +19,14 @@ constexpr int kMaxScales = 4;
 constexpr int kBqCentres = 32;    // centres per CTA (one per lane)
 constexpr int kBqSegs = 8;        // point ranges scanned in parallel (one per warp)
 constexpr int kBqTile = 2048;     // points staged per pass (32 KB of float4)
+
+// Optional in-kernel row compaction (see compact.cu for the format): per scale the list of rows the fused kernel
+// has to evaluate - every group's real (and, with first_flag, non-duplicate) neighbours rounded up to 8 rows.
+struct BallCompact {
+    int32_t *rowmap[kMaxScales];
+    int32_t *blockgroup[kMaxScales];
+    int32_t *n_rows;                  // [n_scales], zeroed before the launch; nullptr = no compaction
+};
 
 struct BallParams {
     float r2[kMaxScales];
@@ -39,7 +48,8 @@ __global__ void __launch_bounds__(kBqCentres * kBqSegs)
 ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
                   const float *__restrict__ centres, int N, int S, BallParams prm,
                   int32_t *__restrict__ out, int32_t *__restrict__ cnt_out,
-                  const uint8_t *__restrict__ first_flag, int32_t *__restrict__ uniq_out, int32_t *__restrict__ ucnt_out) {
+                  const uint8_t *__restrict__ first_flag, int32_t *__restrict__ uniq_out, int32_t *__restrict__ ucnt_out,
+                  BallCompact comp) {
     // Optional second list (first_flag != nullptr): the same first-K hits without exact duplicates of an earlier
     // point (first_flag[b,n] = 0), in index order, for the row compaction; ucnt_out = its length.
     // The flag travels in the sign bit of the staged |p|^2 (a sum of squares is never negative), read back with fabsf.
@@ -157,6 +167,46 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
             if (emitted[k]) atomicAdd(&uemit_s[k][lane], emitted[k]);
     }
     __syncthreads();
+    if (comp.n_rows != nullptr) {
+        // ---- row compaction in place: reserve this CTA's rows of every scale with one atomic add, then copy the
+        // hit lists (written above by all the warps; visible after the barrier) into the compact row list
+        __shared__ int coff_s[NS][kBqCentres], ccnt_s[NS][kBqCentres];
+        if (seg == 0) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int c = dedup ? uemit_s[k][lane] : min(total[k], prm.K[k]);
+                const int rows = live ? ((max(c, 1) + 7) & ~7) : 0;
+                int incl = rows;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                int base = 0;
+                if (lane == 31 && incl > 0) base = atomicAdd(comp.n_rows + k, incl);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                coff_s[k][lane] = base + incl - rows;
+                ccnt_s[k][lane] = c;
+            }
+        }
+        __syncthreads();
+        const int32_t *lists = dedup ? uniq_out : out;
+        for (int cidx = seg; cidx < kBqCentres; cidx += kBqSegs) {
+            const int sc_ = blockIdx.x * kBqCentres + cidx;
+            if (sc_ >= S) break;
+            const int64_t g = (int64_t)b * S + sc_;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int c = ccnt_s[k][cidx], real = max(c, 1), rows = (real + 7) & ~7, off = coff_s[k][cidx];
+                const int32_t *src = lists + g * prm.k_total + prm.k_off[k];
+                for (int j = lane; j < rows; j += 32) {
+                    const int pt = c < 1 ? -1 : src[j < real ? j : 0];        // c == 0: empty ball
+                    comp.rowmap[k][off + j] = (pt >= 0 && pt < N) ? (int32_t)((int64_t)b * N + pt) : -1;
+                    if ((j & 7) == 0) comp.blockgroup[k][(off + j) >> 3] = (int32_t)g;
+                }
+            }
+        }
+    }
     if (!live) return;
     if (ucnt_out != nullptr && seg == 0) {
 #pragma unroll
@@ -225,6 +275,7 @@ static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c,
                            const float *centres_rows, int B, int N, int S, int n_scales,
                            const float *radius_sq_host, const int32_t *nsample_host,
                            int32_t *out_idx, int32_t *out_cnt, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
+                           int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
                            ev2h_stream_t stream);
 
 extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
@@ -232,7 +283,7 @@ extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t s
                                    const float *radius_sq_host, const int32_t *nsample_host,
                                    int32_t *out_idx, ev2h_stream_t stream) {
     return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
-                           out_idx, nullptr, nullptr, nullptr, nullptr, stream);
+                           out_idx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
@@ -240,7 +291,7 @@ extern "C" int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64
                                        const float *radius_sq_host, const int32_t *nsample_host,
                                        int32_t *out_idx, int32_t *out_cnt, ev2h_stream_t stream) {
     return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
-                           out_idx, out_cnt, nullptr, nullptr, nullptr, stream);
+                           out_idx, out_cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int ev2h_ball_query_uniq_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
@@ -251,13 +302,28 @@ extern "C" int ev2h_ball_query_uniq_f32(const float *xyz, int64_t stride_b, int6
     using namespace ev2h;
     EV2H_REQUIRE(first_flag && out_uniq && out_ucnt, "ev2h_ball_query_uniq_f32: null argument");
     return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
-                           out_idx, nullptr, first_flag, out_uniq, out_ucnt, stream);
+                           out_idx, nullptr, first_flag, out_uniq, out_ucnt, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int ev2h_ball_query_compact_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                           const float *centres_rows, int B, int N, int S, int n_scales,
+                                           const float *radius_sq_host, const int32_t *nsample_host,
+                                           int32_t *out_idx, const uint8_t *first_flag, int32_t *uniq_scratch,
+                                           int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
+                                           ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(rowmap_host && blockgroup_host && n_rows_dev, "ev2h_ball_query_compact_f32: null argument");
+    EV2H_REQUIRE((first_flag == nullptr) == (uniq_scratch == nullptr), "ev2h_ball_query_compact_f32: first_flag and uniq_scratch go together");
+    EV2H_REQUIRE((int64_t)B * S * 128 < 2147483647LL, "ev2h_ball_query_compact_f32: too many groups for 32-bit row offsets");
+    return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
+                           out_idx, nullptr, first_flag, uniq_scratch, nullptr, rowmap_host, blockgroup_host, n_rows_dev, stream);
 }
 
 static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                            const float *centres_rows, int B, int N, int S, int n_scales,
                            const float *radius_sq_host, const int32_t *nsample_host,
                            int32_t *out_idx, int32_t *out_cnt, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
+                           int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
                            ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(xyz && centres_rows && out_idx && radius_sq_host && nsample_host, "ev2h_ball_query_f32: null argument");
@@ -281,14 +347,27 @@ static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c,
         }
     }
     prm.k_total = off;
+    BallCompact comp;
+    memset(&comp, 0, sizeof(comp));
+    if (n_rows_dev != nullptr) {
+        for (int i = 0; i < n_scales; ++i) {
+            EV2H_REQUIRE(rowmap_host[i] && blockgroup_host[i] && nsample_host[i] % 8 == 0,
+                         "ev2h_ball_query_compact_f32: scale %d: K must be a multiple of 8 and buffers non-null", i);
+            comp.rowmap[i] = rowmap_host[i];
+            comp.blockgroup[i] = blockgroup_host[i];
+        }
+        comp.n_rows = n_rows_dev;
+        cudaError_t e = cudaMemsetAsync(n_rows_dev, 0, sizeof(int32_t) * n_scales, as_stream(stream));
+        if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_ball_query_compact_f32: memset: %s", cudaGetErrorString(e));
+    }
     dim3 grid((S + kBqCentres - 1) / kBqCentres, B);
     constexpr int kBqThreads = kBqCentres * kBqSegs;
     cudaStream_t st = as_stream(stream);
     switch (n_scales) {
-        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
-        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
-        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
-        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt); break;
+        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
+        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
+        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
+        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
     }
     return check_launch("ev2h_ball_query_f32");
 }

@@ -9,13 +9,11 @@
 // of the pooled epilogue), groups back to back.  Results are bit-identical to the dense evaluation.
 //
 //   rowmap[r]        global point row (b*N + point) feeding compact row r, -1 for "no point" (empty ball)
-//   blockgroup[r/8]  global group (b*S + centre) the 8-row block belongs to, -1 past the end
+//   blockgroup[r/8]  global group (b*S + centre) the 8-row block belongs to (defined for r < n_rows)
 //   n_rows           total compact rows of the scale
 #include "common.cuh"
 
 namespace ev2h {
-
-constexpr int kCompactScanThreads = 1024;
 
 __device__ __forceinline__ int compact_rows(int cnt, int K) {
     cnt = cnt < 1 ? 1 : (cnt > K ? K : cnt);
@@ -28,65 +26,49 @@ struct CompactScales {
     int32_t *blockgroup[4];
 };
 
-// One CTA per scale: exclusive prefix sum of the rounded neighbour counts over all groups.  cnt is scale-major
-// [n_scales][G], so a thread's run of consecutive groups is one contiguous stretch of memory.
-__global__ void __launch_bounds__(kCompactScanThreads)
-compact_scan_kernel(const int32_t *__restrict__ cnt, int G, CompactScales prm,
-                    int32_t *__restrict__ offs, int32_t *__restrict__ n_rows) {
-    __shared__ int warp_sum[kCompactScanThreads / 32];
-    const int sc = blockIdx.x, K = prm.K[sc];
-    const int32_t *c = cnt + (int64_t)sc * G;
-    int32_t *o = offs + (int64_t)sc * G;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int base = 0;                                       // rows before the current stretch of 4 * 1024 groups
-    for (int g0 = 0; g0 < G; g0 += 4 * kCompactScanThreads) {
-        // four consecutive groups per thread: coalesced 16-byte accesses when G is a multiple of 4
-        const int g = g0 + 4 * threadIdx.x;
-        int r[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] = g + j < G ? compact_rows(c[g + j], K) : 0;
-        const int mine = r[0] + r[1] + r[2] + r[3];
-        int incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        __syncthreads();                                // warp_sum of the previous stretch has been consumed
-        if (lane == 31) warp_sum[warp] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kCompactScanThreads / 32; ++w) {
-            const int v = warp_sum[w];
-            if (w < warp) before += v;
-            total += v;
-        }
-        int run = base + before + incl - mine;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (g + j < G) o[g + j] = run;
-            run += r[j];
-        }
-        base += total;
-    }
-    if (threadIdx.x == 0) n_rows[sc] = base;
-}
-
-// lpg lanes per (group, scale) - 8, 16 or 32 for K <= 32, 64, 128 - write the group's compact rows and its
-// block -> group entries.
+// lpg lanes per (group, scale) - 8, 16 or 32 for K <= 32, 64, 128.  A CTA reserves the rows of its groups with one
+// atomic add on the scale's row counter, then every group writes its compact rows and block -> group entries.
+// CTAs therefore land in the list in no particular order, which nothing depends on: every group's rows are contiguous, the block table says
+// whose they are, and the pooled maximum does not care in which tile a group is evaluated.
 __global__ void __launch_bounds__(256)
 compact_fill_kernel(const int32_t *__restrict__ idx, int idx_ld, const int32_t *__restrict__ cnt, int G,
-                    int N, int S, const int32_t *__restrict__ offs, const int32_t *__restrict__ n_rows, CompactScales prm) {
+                    int N, int S, int32_t *__restrict__ n_rows, CompactScales prm) {
     const int sc = blockIdx.y;
     const int K = prm.K[sc];
     const int lpg = K <= 32 ? 8 : (K <= 64 ? 16 : 32);
     const int t = blockIdx.x * 256 + threadIdx.x;
     const int g = t / lpg, lane = t % lpg;
-    if (g >= G) return;
-    const int c = cnt[(int64_t)sc * G + g];
-    const int real = c < 1 ? 1 : (c > K ? K : c), rows = (real + 7) & ~7;
-    const int off = offs[(int64_t)sc * G + g];
+    const bool live = g < G;
+    int c = 0, rows = 0;
+    if (live) {
+        c = cnt[(int64_t)sc * G + g];
+        rows = compact_rows(c, K);
+    }
+    // one atomic add per CTA: block-wide exclusive scan of the group leaders' row counts
+    __shared__ int warp_tot[8];
+    __shared__ int cta_base;
+    const int wl = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int mine = (live && lane == 0) ? rows : 0;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (wl >= d) incl += v;
+    }
+    if (wl == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int v = warp_tot[w]; warp_tot[w] = tot; tot += v; }
+        cta_base = tot ? atomicAdd(n_rows + sc, tot) : 0;
+    }
+    __syncthreads();
+    int off = cta_base + warp_tot[wid] + incl - mine;            // valid in the leader lane
+    // the group's lanes are lpg consecutive lanes of one warp (lpg divides 32): broadcast the leader's offset
+    off = __shfl_sync(0xffffffffu, off, wl & ~(lpg - 1));
+    if (!live) return;
+    const int real = c < 1 ? 1 : (c > K ? K : c);
     const int32_t *src = idx + (int64_t)g * idx_ld + prm.k_off[sc];
     const int64_t b = g / S;
     int32_t *rm = prm.rowmap[sc], *bg = prm.blockgroup[sc];
@@ -95,21 +77,16 @@ compact_fill_kernel(const int32_t *__restrict__ idx, int idx_ld, const int32_t *
         rm[off + k] = (pt >= 0 && pt < N) ? (int32_t)(b * N + pt) : -1;
         if ((k & 7) == 0) bg[(off + k) >> 3] = g;
     }
-    if (g == G - 1) {                                   // blocks between the end of the rows and the end of the last tile
-        const int total = n_rows[sc];
-        const int first = total >> 3, last = ((total + 127) / 128) * 16;
-        for (int j = first + lane; j < last; j += lpg) bg[j] = -1;
-    }
 }
 
 }  // namespace ev2h
 
 extern "C" int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int32_t *cnt, int B, int N, int S, int n_scales,
-                                      const int32_t *nsample_host, int32_t *offs_scratch,
+                                      const int32_t *nsample_host,
                                       int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
                                       ev2h_stream_t stream) {
     using namespace ev2h;
-    EV2H_REQUIRE(idx && cnt && nsample_host && offs_scratch && rowmap_host && blockgroup_host && n_rows_dev,
+    EV2H_REQUIRE(idx && cnt && nsample_host && rowmap_host && blockgroup_host && n_rows_dev,
                  "ev2h_group_compact_i32: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0 && n_scales >= 1 && n_scales <= 4, "ev2h_group_compact_i32: bad sizes");
     const int64_t G64 = (int64_t)B * S;
@@ -131,13 +108,11 @@ extern "C" int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int3
     }
     EV2H_REQUIRE(off <= idx_ld, "ev2h_group_compact_i32: idx_ld smaller than the sum of K");
     cudaStream_t st = as_stream(stream);
-    compact_scan_kernel<<<n_scales, kCompactScanThreads, 0, st>>>(cnt, G, prm, offs_scratch, n_rows_dev);
-    int rc = check_launch("ev2h_group_compact_i32 (scan)");
-    if (rc) return rc;
+    cudaError_t e = cudaMemsetAsync(n_rows_dev, 0, sizeof(int32_t) * n_scales, st);
+    if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_group_compact_i32: memset: %s", cudaGetErrorString(e));
     // sized for 32 lanes per group; scales with fewer lanes per group leave the tail of their grid row idle
-    compact_fill_kernel<<<dim3((unsigned)((G + 7) / 8), (unsigned)n_scales), 256, 0, st>>>(idx, idx_ld, cnt, G, N, S,
-                                                                                            offs_scratch, n_rows_dev, prm);
-    return check_launch("ev2h_group_compact_i32 (fill)");
+    compact_fill_kernel<<<dim3((unsigned)((G + 7) / 8), (unsigned)n_scales), 256, 0, st>>>(idx, idx_ld, cnt, G, N, S, n_rows_dev, prm);
+    return check_launch("ev2h_group_compact_i32");
 }
 
 // ---- exact-duplicate points ------------------------------------------------------------------------------

@@ -66,7 +66,7 @@ struct FusedParams {
     const float *centres;                        // [B,S,3]
     // optional compacted row list (ev2h_group_compact_i32): padded duplicate neighbours skipped
     const int32_t *rowmap;                       // [n_rows] global point row per compact row, -1 = no point
-    const int32_t *blockgroup;                   // [ceil(n_rows/128)*16] global group of every 8-row block, -1 past the end
+    const int32_t *blockgroup;                   // [n_rows/8] global group of every 8-row block
     const int32_t *n_rows_dev;                   // device scalar: compact rows of this scale
     // layer 1
     int per_point;                               // 0 = gather + FFMA, 1 = relu(P - C)
@@ -616,7 +616,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                     // per lane fetched once per tile).  Groups may straddle tiles, so the first and the last group of
                     // a tile are merged into the (zero-initialised) output with an integer atomic max - pooled
                     // values are >= 0 after the ReLU, where float order equals integer order - the others stored.
-                    const int my_gid = lane < 16 ? __ldg(p.blockgroup + tile * 16 + lane) : -1;
+                    const int my_gid = (lane < 16 && (tile * 16 + lane) * 8 < M) ? __ldg(p.blockgroup + tile * 16 + lane) : -1;   // -1: past the end
                     for (int mb = 0; mb < p.mb3; ++mb) {
                         const int ch = mb * 128 + q * 32 + lane;
                         const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + (uint32_t)(mb * FZ_BLOCK_M) + ((uint32_t)(q * 32) << 16);

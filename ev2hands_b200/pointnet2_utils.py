@@ -318,17 +318,20 @@ class PointNetSetAbstractionMsg(nn.Module):
         strides = _capi.cf_strides(xyz)
         fps_idx, centres_rows, new_xyz = _capi.fps(xyz, strides, fps_start, B, N, S)
         D = 0 if points is None else points.shape[1]
-        self._pts8_cache = None
-        if (fused and _COMPACT and _DEDUP and _FUSED_ENABLED and _mlp_precision in ("tf32x3", "bf16")
-                and not (D + 3 > 8 or _PER_POINT_ALWAYS) and N <= 4096 and all(k % 8 == 0 for k in self.nsample_list)):
-            # gather mode: neighbours whose 32-byte record repeats an earlier point give identical rows; list them once
-            self._pts8_cache = self._pts8(xyz, points, strides)
-            first = _capi.first_occurrence(self._pts8_cache)
-            ball, uniq, ucnt = _capi.ball_query_uniq(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list, first)
-            self._compact_src = (uniq, ucnt)
+        self._pts8_cache = self._compact = None
+        want_fused = fused and _FUSED_ENABLED and _mlp_precision in ("tf32x3", "bf16")
+        if want_fused and _COMPACT and all(k % 8 == 0 for k in self.nsample_list):
+            # compacted row lists come out of the ball query itself; in gather mode (narrow inputs, N <= 4096) neighbours
+            # whose 32-byte record repeats an earlier point give identical rows and are listed once
+            first = None
+            if _DEDUP and not (D + 3 > 8 or _PER_POINT_ALWAYS) and N <= 4096:
+                self._pts8_cache = self._pts8(xyz, points, strides)
+                first = _capi.first_occurrence(self._pts8_cache)
+            ball, rowmaps, blockgroups, n_rows = _capi.ball_query_compact(xyz, strides, centres_rows, N, self.radius_list,
+                                                                          self.nsample_list, first)
+            self._compact = (rowmaps, blockgroups, n_rows)
         else:
-            ball, cnt = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list, with_counts=True)
-            self._compact_src = (ball, cnt)
+            ball = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list)
         return strides, fps_idx, centres_rows, new_xyz, ball
 
     def forward(self, xyz, points, fps_start=None):
@@ -407,9 +410,7 @@ class PointNetSetAbstractionMsg(nn.Module):
                 if f:
                     col += layers[0]["cout"]
 
-        compact = None
-        if any(fused) and _COMPACT and all(k % 8 == 0 for k in self.nsample_list):
-            compact = _capi.group_compact(self._compact_src[0], self._compact_src[1], N, self.nsample_list)
+        compact = self._compact if any(fused) else None
         self.last_compact_rows = None if compact is None else compact[2]     # int32 [n_scales] on the device (diagnostics)
 
         feats_rows = None

@@ -111,18 +111,29 @@ EV2H_API int ev2h_ball_query_uniq_f32(const float *xyz, int64_t stride_b, int64_
                         int32_t *out_idx, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
                         ev2h_stream_t stream);
 
+/* Ball query with the row compaction of ev2h_group_compact_i32 done in the same kernel (no second pass over the
+ * index lists): out_idx as in ev2h_ball_query_f32, plus rowmap / blockgroup / n_rows as described below.
+ * first_flag (optional, with uniq_scratch int32 [B,S,sum K]) also drops exact-duplicate points. */
+EV2H_API int ev2h_ball_query_compact_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                        const float *centres_rows, int B, int N, int S,
+                        int n_scales, const float *radius_sq_host, const int32_t *nsample_host,
+                        int32_t *out_idx, const uint8_t *first_flag, int32_t *uniq_scratch,
+                        int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
+                        ev2h_stream_t stream);
+
 /* Row compaction for the fused kernel.  query_ball_point pads every group to K neighbours with copies of
  * the first one (pointnet2_utils.py:104-106); the max-pool cannot see those copies, so the shared MLP need
  * not evaluate them.  For every scale i of a layer this builds the list of rows actually needed - per group
  * its out_cnt real neighbours, rounded up to a multiple of 8 with copies of the first, groups back to back:
  *   rowmap_host[i]      int32 [B*S*K_i]        global point row b*N + point of every compact row (-1: no point)
- *   blockgroup_host[i]  int32 [B*S*K_i/8 + 16] global group b*S + centre of every 8-row block (-1 past the end)
+ *   blockgroup_host[i]  int32 [B*S*K_i/8]      global group b*S + centre of every 8-row block
  *   n_rows_dev          int32 [n_scales]       compact rows per scale
- * (device buffers; the two pointer tables live on the host).  offs_scratch: int32 [n_scales * B*S].
+ * (device buffers; the two pointer tables live on the host).  Groups are appended in no particular order
+ * (one atomic add per group reserves its rows); nothing downstream depends on the order.
  * idx / cnt come from ev2h_ball_query_cnt_f32, or (out_uniq, out_ucnt) from ev2h_ball_query_uniq_f32 to drop
  * exact-duplicate points as well; every K_i must be a multiple of 8. */
 EV2H_API int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int32_t *cnt, int B, int N, int S, int n_scales,
-                                    const int32_t *nsample_host, int32_t *offs_scratch,
+                                    const int32_t *nsample_host,
                                     int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
                                     ev2h_stream_t stream);
 

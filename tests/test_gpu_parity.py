@@ -592,19 +592,60 @@ def test_compaction_tables_match_a_numpy_restatement():
     k_off = 0
     for i, K in enumerate(Ks):
         # counts: number of distinct leading entries before the padding (= entries != first after position 0, + 1)
-        blk = idx_h[:, :, k_off:k_off + K]
-        want_cnt = np.array([[len(np.unique(blk[b, s])) for s in range(S)] for b in range(B)])
+        blk_all = idx_h[:, :, k_off:k_off + K]
+        want_cnt = np.array([[len(np.unique(blk_all[b, s])) for s in range(S)] for b in range(B)])
         assert np.array_equal(cnt_h[i], want_cnt)
-        rm, bg = [], []
+        # groups are appended in no particular order: rebuild {group: rows} from the tables and compare per group
+        total = int(n_rows_h[i])
+        rm_h, bg_h = rowmaps[i].cpu().numpy()[:total], blockgroups[i].cpu().numpy()[:total // 8]
+        assert total % 8 == 0
+        got = {}
+        for blk, g in enumerate(bg_h):
+            got.setdefault(int(g), []).extend(rm_h[8 * blk:8 * blk + 8].tolist())
+        # every group's blocks are contiguous
+        changes = 1 + int((bg_h[1:] != bg_h[:-1]).sum())
+        assert changes == len(got) == B * S
+        want_total = 0
         for g in range(B * S):
             b, s = divmod(g, S)
             c = max(int(want_cnt[b, s]), 1)
             rows = (c + 7) // 8 * 8
-            rm += [b * N + int(blk[b, s, k if k < c else 0]) for k in range(rows)]
-            bg += [g] * (rows // 8)
-        assert int(n_rows_h[i]) == len(rm)
-        assert np.array_equal(rowmaps[i].cpu().numpy()[:len(rm)], np.array(rm, dtype=np.int32))
-        n_blk = (len(rm) + 127) // 128 * 16
-        want_bg = np.array(bg + [-1] * (n_blk - len(bg)), dtype=np.int32)
-        assert np.array_equal(blockgroups[i].cpu().numpy()[:n_blk], want_bg)
+            want_total += rows
+            assert got[g] == [b * N + int(blk_idx) for blk_idx in (blk_all[b, s, [k if k < c else 0 for k in range(rows)]])]
+        assert total == want_total
         k_off += K
+
+
+def test_ball_query_with_in_kernel_compaction_matches_the_two_step_tables():
+    """ev2h_ball_query_compact_f32 = ball query + ev2h_group_compact_i32 in one kernel: same index lists, and the same
+    set of rows per group (groups land in the list in no particular order in both)."""
+    rs = np.random.RandomState(12)
+    B, N, S = 2, 1500, 70
+    base = rs.rand(B, 500, 8).astype(np.float32)
+    base[:, :, 7] = 0
+    pts8 = np.stack([base[b][rs.randint(0, 500, size=N)] for b in range(B)])
+    xyz = np.ascontiguousarray(pts8[:, :, 4:7].transpose(0, 2, 1))
+    centres = np.ascontiguousarray(pts8[:, :S, 4:7])
+    Ks, radii = [16, 64, 128], [0.1, 0.3, 0.6]
+    xd, cd = dev(xyz), dev(centres)
+    strides = _capi.cf_strides(xd)
+    for dedup in (False, True):
+        first = _capi.first_occurrence(dev(pts8)) if dedup else None
+        idx, rowmaps, blockgroups, n_rows = _capi.ball_query_compact(xd, strides, cd, N, radii, Ks, first)
+        if dedup:
+            idx2, lists, cnt = _capi.ball_query_uniq(xd, strides, cd, N, radii, Ks, first)
+        else:
+            idx2, cnt = _capi.ball_query(xd, strides, cd, N, radii, Ks, with_counts=True)
+            lists = idx2
+        assert torch.equal(idx, idx2)
+        rm2, bg2, n2 = _capi.group_compact(lists, cnt, N, Ks)
+        assert torch.equal(n_rows, n2)
+        for i in range(len(Ks)):
+            total = int(n_rows[i])
+            def per_group(rm, bg):
+                rm, bg = rm.cpu().numpy()[:total], bg.cpu().numpy()[:total // 8]
+                d = {}
+                for blk, g in enumerate(bg):
+                    d.setdefault(int(g), []).extend(rm[8 * blk:8 * blk + 8].tolist())
+                return d
+            assert per_group(rowmaps[i], blockgroups[i]) == per_group(rm2[i], bg2[i])
