@@ -18,7 +18,7 @@ namespace ev2h {
 constexpr int kMaxScales = 4;
 constexpr int kBqCentres = 32;    // centres per CTA (one per lane)
 constexpr int kBqSegs = 8;        // point ranges scanned in parallel (one per warp)
-constexpr int kBqTile = 2048;     // points staged per pass (32 KB of float4)
+constexpr int kBqTile = 1024;     // points staged per pass (16 KB of float4: six CTAs per SM, one wave for sa1 at B = 64)
 
 // Optional in-kernel row compaction (see compact.cu for the format): per scale the list of rows the fused kernel
 // has to evaluate - every group's real (and, with first_flag, non-duplicate) neighbours rounded up to 8 rows.
