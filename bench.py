@@ -357,7 +357,7 @@ def run_ours(args):
     line = {
         "metric": "encoder event-windows/s", "value": value, "unit": "windows/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xtf32)", "bf16": "bf16"}[args.mlp], "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (split tf32 + bf16 corrections, fp32 accumulate)", "bf16": "bf16"}[args.mlp], "data": "synthetic",
         "config": {"workload": "encoder forward sa1->sa2->sa3 (TEHNet.py:172-181), %d windows per GPU, "
                                "N=%d points/window, 5 channels, random-init weights, eval mode" % (B, args.points),
                    "windows_per_gpu": B, "global_windows": B * world,
