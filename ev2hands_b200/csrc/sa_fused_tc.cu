@@ -90,7 +90,7 @@ struct FusedParams {
     float *out; int ld_out, out_col, c_out;
     // rings
     int sa, sb, a_slot_bytes, b_slot_bytes;
-    long long *dbg;     // optional [gridDim.x][8] issuer wait-cycle counters (debug/profiling only)
+    long long *dbg;     // optional trace buffer (EV2H_FUSED_TRACE builds only, tools/fused_trace.py)
 };
 
 struct Ring {
@@ -562,7 +562,7 @@ sa_fused_tc_kernel(const FusedParams p) {
         uint64_t *my_grants = a_grant + LG * FZ_MAX_RING;
         uint32_t bits = 0;
         uint32_t it = 0;
-        const bool eprof = warp == EPI_WARP0 && lane == 0;    // traces only
+        const bool eprof = warp == EPI_WARP0 && lane == 0;    // the thread that writes this role's trace events
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int64_t m0 = tile * FZ_BLOCK_M;
             {

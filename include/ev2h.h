@@ -285,8 +285,8 @@ EV2H_API int ev2h_sa_msg_fused_compact_tc(
  * to pack their weights with; -1 if the pair is not supported. */
 EV2H_API int ev2h_sa_msg_fused_kc(int mode, const int32_t *cout_host);
 
-/* Debug/profiling only: device buffer [512][16] int64 (one row per CTA) receiving the UMMA issuer's wait-cycle counters
- * of the next fused launches (NULL turns it off). */
+/* Debug/profiling only: device buffer of 512 x 16 int64 receiving the timeline trace of CTA 0 of the next fused
+ * launches (only in builds with -DEV2H_FUSED_TRACE, see tools/fused_trace.py; NULL turns it off). */
 EV2H_API int ev2h_fused_set_debug_buffer(void *buf);
 /* Debug only: bit 0 swaps the leading/stride byte offsets of the UMMA shared-memory descriptors. */
 EV2H_API int ev2h_tc_set_debug(int flags);

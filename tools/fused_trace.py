@@ -20,17 +20,18 @@ orig = _capi.sa_msg_fused
 buf = torch.zeros(512, 16, dtype=torch.int64, device=dev)
 ROLE = {1: "load", 2: "strm", 3: "issu", 4: "epil"}
 EV = {(1, 1): "chunk computed", (1, 2): "slot granted", (1, 3): "arrived a_full",
-      (2, 1): "b_empty ok -> copy", (3, 1): "acc_empty ok", (3, 2): "a_full ok", (3, 3): "b_full ok", (3, 4): "after syncwarp", (3, 5): "elected: start", (3, 6): "elected: mmas issued", (3, 7): "elected: commits issued",
+      (2, 1): "b_empty ok -> copy", (3, 1): "acc_empty ok", (3, 2): "a_full ok", (3, 3): "b_full ok", (3, 6): "mmas issued", (3, 7): "commits issued",
       (4, 1): "acc_full0 seen", (4, 2): "chunk converted", (4, 3): "slot granted", (4, 4): "arrived a_full",
       (4, 5): "acc_full1 seen", (4, 6): "pool done"}
 def wrapped(*a, **k):
     buf.zero_(); _capi.lib().ev2h_fused_set_debug_buffer(buf.data_ptr())
-    orig(*a, **k); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); orig(*a, **k); e1.record(); torch.cuda.synchronize()
     _capi.lib().ev2h_fused_set_debug_buffer(None)
     d = buf.cpu().numpy().reshape(-1)
     tr = np.concatenate([d[4800 + r * 800 + 1: 4800 + r * 800 + 1 + int(d[4800 + r * 800])] for r in range(4)]); n = len(tr)
     evs = sorted(((int(x) & 0xFFFFFFFFFF, int(x) >> 40) for x in tr))
-    print("==== %s K=%d widths=%s: %d events" % (prec, a[6], a[18], n))
+    print("==== %s K=%d widths=%s: %.3f ms, %d events" % (prec, a[6], a[18], e0.elapsed_time(e1), n))
     if not evs: return
     t0 = evs[0][0]
     for t, tag in evs:
