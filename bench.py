@@ -276,29 +276,47 @@ def run_ours(args):
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
 
-    # ---- end to end through the module API with host buffers (H2D + forward + D2H per step)
-    out_host = torch.empty((B, 1024), dtype=torch.float32).pin_memory()
-    ev_stage = torch.empty_like(ev_dev)
+    # ---- end to end through the module API with host buffers: every step copies its windows from pinned host
+    # memory, runs the public forward (FPS start indices drawn on the host like the reference does) and reads the
+    # per-window features back.  The copies run on their own stream, double buffered, so step i+1's upload overlaps
+    # step i's kernels - as a serving loop would; the timed region is the whole loop (uploads, L2 flushes, kernels,
+    # read-backs), one event pair around K steps.
+    out_host = [torch.empty((B, 1024), dtype=torch.float32).pin_memory() for _ in range(2)]
+    ev_stage = [torch.empty_like(ev_dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
 
-    def step_e2e():
-        ev_stage.copy_(ev_host, non_blocking=True)
-        with torch.no_grad():
-            o = enc(ev_stage)              # FPS start indices drawn on the host like the reference does
-        out_host.copy_(o, non_blocking=True)
+    def run_e2e(k):
+        main = torch.cuda.current_stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
 
-    for _ in range(2):
-        step_e2e()
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(freed[i % 2])      # the step that last read this buffer is done
+                ev_stage[i % 2].copy_(ev_host, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        copy_stream.wait_stream(main)
+        upload(0)
+        for i in range(k):
+            flush.zero_()
+            if i + 1 < k:
+                upload(i + 1)
+            main.wait_event(ready[i % 2])
+            with torch.no_grad():
+                o = enc(ev_stage[i % 2])
+            out_host[i % 2].copy_(o, non_blocking=True)
+            freed[i % 2].record(main)
+
+    run_e2e(2)
     barrier()
-    e_evs = []
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step_e2e()
-        b.record()
-        e_evs.append((a, b))
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    run_e2e(args.steps)
+    eb.record()
     barrier()
-    e2e_ms = float(sum(a.elapsed_time(b) for a, b in e_evs))
+    e2e_ms = float(ea.elapsed_time(eb))
 
     # ---- optional secondary number: encoder + feature-propagation decoder, same timing rules
     dec_ms = 0.0
@@ -376,7 +394,8 @@ def run_ours(args):
                                   "peak_gbs": peaks["hbm_gbs"]}},
         "kernels": {k: {"launches_per_step": n / args.steps, "ms_per_step": ms / args.steps} for k, (n, ms) in sorted(kern.items())},
         "e2e": {"value": windows / (e2e_ms / 1e3), "unit": "windows/s", "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": int(ev_host.numel() * 4 + 2 * B * 8), "d2h_bytes_per_step": int(out_host.numel() * 4)},
+                "h2d_bytes_per_step": int(ev_host.numel() * 4 + 2 * B * 8), "d2h_bytes_per_step": int(out_host[0].numel() * 4),
+                "timed": "one event pair around K steps incl. uploads (own stream, double buffered), L2 flushes, eager forwards, read-backs"},
         "gpu_launches": launches, "clocks": clocks, "wall_s": wall,
         "checksum": float(out.double().sum().item()),
     }

@@ -179,7 +179,12 @@ def fps(xyz: torch.Tensor, strides, start: torch.Tensor, B: int, N: int, S: int,
     """-> (idx int32 [B,S], centres_rows [B,S,3] | None, centres_cf [B,3,S] | None)"""
     _need_cuda_f32(xyz, "xyz")
     dev = xyz.device
-    start = start.to(device=dev, dtype=torch.int64).contiguous()
+    if not start.is_cuda:
+        # host-drawn start indices (the reference's torch.randint on the CPU generator): upload from pinned memory
+        # without blocking, so the host keeps running ahead of the device instead of syncing with it twice per step
+        start = start.to(dtype=torch.int64).contiguous().pin_memory().to(dev, non_blocking=True)
+    else:
+        start = start.to(device=dev, dtype=torch.int64).contiguous()
     idx = torch.empty((B, S), dtype=torch.int32, device=dev)
     rows = torch.empty((B, S, 3), dtype=torch.float32, device=dev) if want_rows else None
     cf = torch.empty((B, 3, S), dtype=torch.float32, device=dev) if want_cf else None
