@@ -93,26 +93,41 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
             pts[i] = make_float4(x, y, z, dup ? __uint_as_float(__float_as_uint(nn) | 0x80000000u) : nn);
         }
         __syncthreads();
-        const int per = (n_tile + kBqSegs - 1) / kBqSegs;
+        const int per = (n_tile + kBqSegs - 1) / kBqSegs;              // <= kBqTile / kBqSegs = 32 * WORDS points
         const int i0 = min(seg * per, n_tile), i1 = min(i0 + per, n_tile);
 
-        // pass 1: count
+        // pass 1: one distance evaluation per (centre, point); the hits of this range are kept as bit masks
+        // (bit j of word w = point i0 + 32 w + j), so placing them later needs no second evaluation
+        constexpr int WORDS = kBqTile / kBqSegs / 32;
+        uint32_t hit[NS][WORDS], fl[WORDS];
         int cnt[NS], fst[NS], ucnt[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) { cnt[k] = 0; fst[k] = N; ucnt[k] = 0; }
-        for (int i = i0; i < i1; ++i) {
-            float4 pw = pts[i];
-            const int u = (int)(__float_as_uint(pw.w) >> 31) ^ 1;
-            pw.w = fabsf(pw.w);
-            const float d = sqdist_expanded(qx, qy, qz, qn, pw);
-            if (d > prm.r2_max) continue;                // outside every radius
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+            // first-occurrence flags of the word's 32 points: the point is the same for every lane, so each lane
+            // looks at one point and a ballot assembles the word
+            const int ip = i0 + 32 * w + lane;
+            fl[w] = __ballot_sync(0xffffffffu, ip < i1 && (__float_as_uint(pts[ip].w) >> 31) == 0u);
+            uint32_t m[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) m[k] = 0u;
+            const int nb = min(32, i1 - (i0 + 32 * w));
+            for (int j = 0; j < nb; ++j) {
+                float4 pw = pts[i0 + 32 * w + j];
+                pw.w = fabsf(pw.w);
+                const float d = sqdist_expanded(qx, qy, qz, qn, pw);
+                if (d > prm.r2_max) continue;            // outside every radius
+#pragma unroll
+                for (int k = 0; k < NS; ++k)
+                    if (!(d > prm.r2[k])) m[k] |= 1u << j;    // group_idx[sqrdists > r**2] = N  (:102)
+            }
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-                if (!(d > prm.r2[k])) {                   // group_idx[sqrdists > r**2] = N  (:102)
-                    if (cnt[k] == 0) fst[k] = t0 + i;
-                    ++cnt[k];
-                    ucnt[k] += u;
-                }
+                hit[k][w] = m[k];
+                if (m[k] != 0u && cnt[k] == 0) fst[k] = t0 + i0 + 32 * w + __ffs(m[k]) - 1;
+                cnt[k] += __popc(m[k]);
+                ucnt[k] += __popc(m[k] & fl[w]);
             }
         }
 #pragma unroll
@@ -137,23 +152,21 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
             any_room = any_room || (cnt[k] > 0 && o < prm.K[k]);
         }
 
-        // pass 2: write the hits of this range at their final positions
+        // pass 2: walk the set bits and write the hits of this range at their final positions
         if (live && any_room) {
-            for (int i = i0; i < i1; ++i) {
-                float4 pw = pts[i];
-                const int u = (int)(__float_as_uint(pw.w) >> 31) ^ 1;
-                pw.w = fabsf(pw.w);
-                const float d = sqdist_expanded(qx, qy, qz, qn, pw);
-                if (d > prm.r2_max) continue;
 #pragma unroll
-                for (int k = 0; k < NS; ++k) {
-                    if (!(d > prm.r2[k])) {
-                        if (off[k] < prm.K[k]) {
-                            row[prm.k_off[k] + off[k]] = t0 + i;
-                            if (dedup && u) { urow[prm.k_off[k] + uoff[k]] = t0 + i; ++emitted[k]; }
-                        }
-                        ++off[k];
-                        uoff[k] += u;
+            for (int k = 0; k < NS; ++k) {
+                int o = off[k], uo = uoff[k];
+#pragma unroll
+                for (int w = 0; w < WORDS; ++w) {
+                    uint32_t m = hit[k][w];
+                    while (m != 0u && o < prm.K[k]) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1u;
+                        const int pt = t0 + i0 + 32 * w + j;
+                        row[prm.k_off[k] + o] = pt;
+                        if (dedup && ((fl[w] >> j) & 1u)) { urow[prm.k_off[k] + uo] = pt; ++uo; ++emitted[k]; }
+                        ++o;
                     }
                 }
             }
