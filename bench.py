@@ -276,6 +276,30 @@ def run_ours(args):
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
 
+    # ---- transparency: the same K steps with the row compaction switched off (every padded / duplicate neighbour
+    # evaluated like the reference does; identical output bits), eager launches
+    import ev2hands_b200.pointnet2_utils as _pu
+    dense_ms = 0.0
+    if _pu._COMPACT:
+        _pu._COMPACT = False
+        try:
+            for _ in range(2):
+                forward_resident(ev_dev, s1, s2)
+            barrier()
+            d_evs = []
+            for _ in range(args.steps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out_dense = forward_resident(ev_dev, s1, s2)
+                b.record()
+                d_evs.append((a, b))
+            barrier()
+            dense_ms = float(sum(a.elapsed_time(b) for a, b in d_evs))
+            dense_equal = bool(torch.equal(out_dense, out))
+        finally:
+            _pu._COMPACT = True
+
     # ---- end to end through the module API with host buffers: every step copies its windows from pinned host
     # memory, runs the public forward (FPS start indices drawn on the host like the reference does) and reads the
     # per-window features back.  The copies run on their own stream, double buffered, so step i+1's upload overlaps
@@ -348,7 +372,7 @@ def run_ours(args):
         dec_ms = float(sum(a.elapsed_time(b) for a, b in d_evs))
 
     # ---- max over ranks
-    total_ms, e2e_ms, dec_ms = sharding.max_over_ranks([total_ms, e2e_ms, dec_ms], device=device)
+    total_ms, e2e_ms, dec_ms, dense_ms = sharding.max_over_ranks([total_ms, e2e_ms, dec_ms, dense_ms], device=device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -382,6 +406,7 @@ def run_ours(args):
                    "mlp_path": {"fp32": "fp32 FFMA (CUDA cores)", "tf32x3": "tcgen05 3-product split x=hi+lo, w=hi+lo: tf32 hi*hi + two bf16 correction products (fp32-level accuracy)",
                                 "bf16": "tcgen05 kind::f16 bf16 operands, fp32 accumulate"}[args.mlp],
                    "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                   "rows": "compacted: padded and exact-duplicate neighbours are evaluated once (bit-identical pooled features; EV2H_COMPACT=0 evaluates the dense groups, timed under compaction.dense_rows_eager)",
                    "launch": "one CUDA graph replay per step" if graphed is not None else "eager launches through the module API",
                    "kernel_times": "separate eager pass of the same K steps with CUDA events around every launch"},
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
@@ -408,6 +433,9 @@ def run_ours(args):
     # rows the fused kernel evaluates / dense B*S*K rows per scale: padded duplicate neighbours are skipped
     # (bit-identical pooled features); roofline.achieved counts the dense algorithmic FLOPs
     line["compaction"] = {"rows_evaluated_fraction": comp} if comp else None
+    if comp and dense_ms > 0:
+        line["compaction"]["dense_rows_eager"] = {"value": windows / (dense_ms / 1e3), "unit": "windows/s", "ms_per_step": dense_ms / args.steps,
+                                                  "output_bits_equal": dense_equal}
     if args.with_decoder:
         line["secondary"] = {"metric": "encoder + fp3/fp2/fp1 decoder event-windows/s (TEHNet.py:172-186)",
                              "value": windows / (dec_ms / 1e3), "unit": "windows/s", "ms_per_step": dec_ms / args.steps}
