@@ -368,7 +368,9 @@ sa_fused_tc_kernel(const FusedParams p) {
                         v[i] = make_float4(fmaxf(v[i].x - c.x, 0.f), fmaxf(v[i].y - c.y, 0.f), fmaxf(v[i].z - c.z, 0.f), fmaxf(v[i].w - c.w, 0.f));
                     }
                 }
+                if (tid == 0) FZ_TRACE(1, 1, it, kc);
                 const int slot = acquire_slot(my_grants, it * Q + (uint32_t)kc, p.sa, bits, 11);
+                if (tid == 0) FZ_TRACE(1, 2, it, kc);
                 uint8_t *st = a_ring + (size_t)slot * p.a_slot_bytes;
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
@@ -397,6 +399,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                 }
                 tc::fence_proxy_async();
                 tc::mbar_arrive(a_full + slot);
+                if (tid == 0) FZ_TRACE(1, 3, it, kc);
             };
 
             int64_t p_cur[4], c_cur[4], p_nxt[4], c_nxt[4];
