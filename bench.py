@@ -247,6 +247,11 @@ def run_ours(args):
 
     # ---- instrumented pass (eager): per-kernel device time from CUDA events around every launch, same K steps,
     # same L2 flush; feeds the roofline (time of the MLP kernels) and the launch count
+    # (one stream here, so that a kernel's bracket holds that kernel alone: the headline steps run sa2's FPS and
+    # ball query on a second stream beside sa1's MLP kernels)
+    import ev2hands_b200.encoder as _enc_mod
+    geom_stream = _enc_mod._GEOM_STREAM
+    _enc_mod._GEOM_STREAM = False
     _capi.LOG.reset(timing=True)
     barrier()
     for _ in range(args.steps):
@@ -256,6 +261,7 @@ def run_ours(args):
     launches = _capi.LOG.count
     kern = _capi.LOG.totals_ms()
     _capi.LOG.reset(timing=False)
+    _enc_mod._GEOM_STREAM = geom_stream
 
     # ---- timed region: K steps, device time per step from CUDA events, L2 flushed between steps
     sampler = ClockSampler(physical_gpu_index(local_rank))
@@ -408,7 +414,9 @@ def run_ours(args):
                    "l2": "256 MiB buffer written between timed steps (L2 flush)",
                    "rows": "compacted: padded and exact-duplicate neighbours are evaluated once (bit-identical pooled features; EV2H_COMPACT=0 evaluates the dense groups, timed under compaction.dense_rows_eager)",
                    "launch": "one CUDA graph replay per step" if graphed is not None else "eager launches through the module API",
-                   "kernel_times": "separate eager pass of the same K steps with CUDA events around every launch"},
+                   "kernel_times": "separate eager single-stream pass of the same K steps with CUDA events around every launch",
+                   "streams": "sa2's FPS + ball query on a second stream beside sa1's MLP kernels" if geom_stream else "one stream",
+                   "layout": "levels stay in point-major rows between layers; channel-first copies only on request"},
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": (achieved_tflops / peak_tflops) if achieved_tflops else None, "traffic": traffic,
                      "kernel": "%s (shared MLP, %d launches/step)" % ("linear_relu_kernel" if args.mlp == "fp32" else "sa_fused_tc_kernel + linear_tc_kernel", mlp_n // max(args.steps, 1)),

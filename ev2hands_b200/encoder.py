@@ -11,7 +11,20 @@ import os
 import torch
 import torch.nn as nn
 
-from .pointnet2_utils import PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg
+from .pointnet2_utils import (PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg,
+                              _check_inputs, _wants_autograd)
+
+# Inference: sa2's FPS and ball query need only sa1's centres, so they run on a second stream beside sa1's
+# grouping + MLP kernels (EV2H_GEOM_STREAM=0 keeps everything on one stream).
+_GEOM_STREAM = os.environ.get("EV2H_GEOM_STREAM", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(device):
+    st = _side_streams.get(device)
+    if st is None:
+        st = _side_streams[device] = torch.cuda.Stream(device=device)
+    return st
 
 
 class SetAbstractionEncoder(nn.Module):
@@ -36,12 +49,51 @@ class SetAbstractionEncoder(nn.Module):
         ``torch.randint`` draws the reference makes (in this order) per forward."""
         s1, s2 = fps_starts if fps_starts is not None else (None, None)
         l0_xyz = events[:, :3, :]
+        if events.is_cuda and not _wants_autograd(self, events):
+            return self._forward_inference(l0_xyz, events, s1, s2, return_levels)
         l1_xyz, l1_points = self.sa1(l0_xyz, events, fps_start=s1)
         l2_xyz, l2_points = self.sa2(l1_xyz, l1_points, fps_start=s2)
         _, l3_points = self.sa3(l2_xyz, l2_points)
         out = l3_points.squeeze(-1)
         if return_levels:
             return out, {"l1_xyz": l1_xyz, "l1_points": l1_points, "l2_xyz": l2_xyz, "l2_points": l2_points}
+        return out
+
+
+    def _forward_inference(self, l0_xyz, events, s1, s2, return_levels):
+        """The same data flow on the kernels' point-major rows (``forward_rows``): each layer's pooled rows
+        [features | centre xyz] are the next layer's input rows as they are, and the channel-first tensors of the
+        reference's API are only materialised for ``return_levels``.  sa2's FPS + ball query run on a side stream
+        as soon as sa1's centres exist."""
+        _check_inputs(l0_xyz, events)
+        B, _, N = events.shape
+        # the reference draws sa1's start indices, then sa2's, from the CPU generator (pointnet2_utils.py:75)
+        if s1 is None:
+            s1 = torch.randint(0, N, (B,), dtype=torch.long)
+        if s2 is None:
+            s2 = torch.randint(0, self.sa1.npoint, (B,), dtype=torch.long)
+        with torch.no_grad():
+            g1 = self.sa1._fps(l0_xyz, s1)
+            l1_xyz = g1["new_xyz"]
+            d1 = sum(convs[-1].out_channels for convs in self.sa1.conv_blocks)
+            if _GEOM_STREAM:
+                main, side = torch.cuda.current_stream(events.device), _side_stream(events.device)
+                # tensors allocated on the side stream stay referenced (g2) until main has waited for it below;
+                # the side stream starts every forward behind main, which orders any reuse of their memory
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    g2 = self.sa2._ball(self.sa2._fps(l1_xyz, s2), l1_xyz, None, d1, fused=True)
+                self.sa1._ball(g1, l0_xyz, events, events.shape[1], fused=True)
+                _, r1 = self.sa1.forward_rows(l0_xyz, events, geom=g1)
+                main.wait_stream(side)
+            else:
+                self.sa1._ball(g1, l0_xyz, events, events.shape[1], fused=True)
+                _, r1 = self.sa1.forward_rows(l0_xyz, events, geom=g1)
+                g2 = self.sa2._ball(self.sa2._fps(l1_xyz, s2), l1_xyz, None, d1, fused=True)
+            l2_xyz, r2 = self.sa2.forward_rows(l1_xyz, r1, geom=g2)
+            out = self.sa3.forward_rows(l2_xyz, r2).squeeze(-1)
+        if return_levels:
+            return out, {"l1_xyz": l1_xyz, "l1_points": r1.cf(), "l2_xyz": l2_xyz, "l2_points": r2.cf()}
         return out
 
 

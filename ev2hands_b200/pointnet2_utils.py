@@ -24,6 +24,7 @@ query, grouping (with scatter-add backward) and max-pool (with arg-max backward)
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -204,7 +205,7 @@ class _FoldedMLP:
             for j, (conv, bn) in enumerate(zip(convs, bns)):
                 w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels)
                 if j == 0 and in_perm is not None:
-                    w = w[:, in_perm]
+                    w = w[:, in_perm if torch.is_tensor(in_perm) else torch.tensor(list(in_perm), device=w.device)]
                 wt, bias = _capi.fold_conv_bn(w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
                 layers.append({"wt": wt, "bias": bias, "cin": conv.in_channels, "cout": conv.out_channels, "packed": {}})
             self.by_device[dev] = (key, layers)
@@ -267,6 +268,47 @@ def _rows_to_cf(rows):
     return cf
 
 
+class _LevelRows:
+    """Point-major copy of one level of the encoder, the layout the kernels work in:
+    ``rows`` [B, S, ld] float32 = [features (c channels) | centre xyz (3) | zero padding].
+
+    A set-abstraction layer's fused path produces it; the channel-first tensor the reference's API returns is a
+    transpose of it, made on demand.  The record rides on that tensor (attribute ``_ev2h_rows``) so that the next
+    layer reads the rows it needs - [features | xyz] is exactly the input row of its per-point first layer -
+    instead of transposing the channel-first tensor back.  ``matches`` guards the shortcut: same tensor objects'
+    storage, not modified in place since."""
+
+    def __init__(self, rows, c, new_xyz):
+        self.rows, self.c = rows, c
+        self.B, self.S, self.ld = rows.shape
+        self.xyz_cf = new_xyz
+        self._xyz_key = (new_xyz.data_ptr(), new_xyz._version)
+        self._cf = None          # weak reference: the tensor owns the record, not the other way round
+        self._cf_key = None
+
+    def cf(self):
+        """contiguous channel-first features [B, c, S] (transpose kernel); the same tensor while it is alive."""
+        cf = self._cf() if self._cf is not None else None
+        if cf is None:
+            cf = torch.empty((self.B, self.c, self.S), dtype=torch.float32, device=self.rows.device)
+            _capi.transpose(self.rows, (self.S * self.ld, self.ld, 1), self.B, self.S, self.c, cf, self.c * self.S, self.S, 0)
+            cf._ev2h_rows = self
+            self._cf, self._cf_key = weakref.ref(cf), (cf.data_ptr(), cf._version)
+        return cf
+
+    def matches(self, xyz, points):
+        return (self._cf is not None and points is self._cf() and (points.data_ptr(), points._version) == self._cf_key
+                and (xyz.data_ptr(), xyz._version) == self._xyz_key and tuple(xyz.shape) == (self.B, 3, self.S))
+
+
+def _level_rows_of(xyz, points):
+    """The _LevelRows record behind ``points`` (itself, or the one riding on a channel-first tensor), or None."""
+    if isinstance(points, _LevelRows):
+        return points
+    rec = getattr(points, "_ev2h_rows", None)
+    return rec if rec is not None and rec.matches(xyz, points) else None
+
+
 def _wants_autograd(module, *tensors):
     if module.training:
         return True
@@ -309,50 +351,75 @@ class PointNetSetAbstractionMsg(nn.Module):
         _capi.transpose(xyz, strides, B, 3, N, pts8, N * 8, 8, D)
         return pts8
 
-    def _sample(self, xyz, fps_start, points=None, fused=False):
+    def _fps(self, xyz, fps_start):
+        """FPS of this layer on the current stream -> geometry record (dict)."""
         B, _, N = xyz.shape
-        S = self.npoint
         if fps_start is None:
             # same draw, from the same (CPU) generator, as pointnet2_utils.py:75
             fps_start = torch.randint(0, N, (B,), dtype=torch.long)
         strides = _capi.cf_strides(xyz)
-        fps_idx, centres_rows, new_xyz = _capi.fps(xyz, strides, fps_start, B, N, S)
-        D = 0 if points is None else points.shape[1]
-        self._pts8_cache = self._compact = None
+        fps_idx, centres_rows, new_xyz = _capi.fps(xyz, strides, fps_start, B, N, self.npoint)
+        return {"strides": strides, "fps_idx": fps_idx, "centres_rows": centres_rows, "new_xyz": new_xyz}
+
+    def _ball(self, geom, xyz, points, D, fused):
+        """Ball query of every scale (plus the compacted row lists of the fused path) on the current stream;
+        ``points`` is only needed for narrow inputs (the 32-byte gather records), ``D`` = feature channels."""
+        B, _, N = xyz.shape
+        strides, centres_rows = geom["strides"], geom["centres_rows"]
+        geom["pts8"] = geom["compact"] = None
         want_fused = fused and _FUSED_ENABLED and _mlp_precision in ("tf32x3", "bf16")
         if want_fused and _COMPACT and all(k % 8 == 0 for k in self.nsample_list):
             # compacted row lists come out of the ball query itself; in gather mode (narrow inputs, N <= 4096) neighbours
             # whose 32-byte record repeats an earlier point give identical rows and are listed once
             first = None
             if _DEDUP and not (D + 3 > 8 or _PER_POINT_ALWAYS) and N <= 4096:
-                self._pts8_cache = self._pts8(xyz, points, strides)
-                first = _capi.first_occurrence(self._pts8_cache)
+                geom["pts8"] = self._pts8(xyz, points, strides)
+                first = _capi.first_occurrence(geom["pts8"])
             ball, rowmaps, blockgroups, n_rows = _capi.ball_query_compact(xyz, strides, centres_rows, N, self.radius_list,
                                                                           self.nsample_list, first)
-            self._compact = (rowmaps, blockgroups, n_rows)
+            geom["compact"] = (rowmaps, blockgroups, n_rows)
         else:
             ball = _capi.ball_query(xyz, strides, centres_rows, N, self.radius_list, self.nsample_list)
-        return strides, fps_idx, centres_rows, new_xyz, ball
+        geom["ball"] = ball
+        return geom
 
     def forward(self, xyz, points, fps_start=None):
         """xyz [B,3,N], points [B,D,N] or None -> (new_xyz [B,3,S], new_points [B,sum D',S])."""
         _check_inputs(xyz, points)
-        autograd = _wants_autograd(self, points)
-        with torch.no_grad():
-            strides, fps_idx, centres_rows, new_xyz, ball = self._sample(xyz.detach(), fps_start, None if autograd else points,
-                                                                          fused=not autograd)
-        self.last_fps_idx, self.last_ball_idx = fps_idx, ball        # exposed for parity tests
-        if autograd:
-            return new_xyz, self._forward_autograd(xyz, points, strides, centres_rows, ball)
-        with torch.no_grad():
-            return new_xyz, self._forward_fused(xyz, points, strides, centres_rows, ball)
+        if _wants_autograd(self, points):
+            with torch.no_grad():
+                geom = self._ball(self._fps(xyz.detach(), fps_start), xyz.detach(), None, 0, fused=False)
+            self.last_fps_idx, self.last_ball_idx = geom["fps_idx"], geom["ball"]        # exposed for parity tests
+            return geom["new_xyz"], self._forward_autograd(xyz, points, geom["strides"], geom["centres_rows"], geom["ball"])
+        new_xyz, rec = self.forward_rows(xyz, points, fps_start)
+        return new_xyz, rec.cf()
 
-    def _forward_fused(self, xyz, points, strides, centres_rows, ball):
+    def forward_rows(self, xyz, points, fps_start=None, geom=None):
+        """The inference path in the kernels' own layout: like ``forward`` but returns the level as a ``_LevelRows``
+        record (point-major rows; ``.cf()`` gives the reference's channel-first tensor).  ``points`` may be such a
+        record from the previous layer; ``geom`` = this layer's FPS + ball query if the caller already ran them
+        (``_fps`` / ``_ball``, e.g. on another stream)."""
+        with torch.no_grad():
+            rows_in = _level_rows_of(xyz, points)
+            D = rows_in.c if rows_in is not None else (0 if points is None else points.shape[1])
+            if isinstance(points, _LevelRows):
+                # wide inputs are consumed as rows; narrow ones (gather records) want the channel-first tensor
+                points = None if (D + 3 > 8 or _PER_POINT_ALWAYS) else rows_in.cf()
+            if geom is None:
+                geom = self._ball(self._fps(xyz, fps_start), xyz, points, D, fused=True)
+            self.last_fps_idx, self.last_ball_idx = geom["fps_idx"], geom["ball"]        # exposed for parity tests
+            return geom["new_xyz"], self._forward_fused(xyz, points, rows_in, D, geom)
+
+    def _forward_fused(self, xyz, points, rows_in, D, geom):
+        """``points`` [B,D,N] channel-first, or ``rows_in`` (the previous layer's _LevelRows: [features | xyz] rows)."""
         B, _, N = xyz.shape
         S = self.npoint
-        D = 0 if points is None else points.shape[1]
+        strides, centres_rows, ball = geom["strides"], geom["centres_rows"], geom["ball"]
         c_total = sum(convs[-1].out_channels for convs in self.conv_blocks)
-        out_rows = torch.zeros((B, S, c_total), dtype=torch.float32, device=xyz.device)
+        # pooled features, then the centres: [features | xyz | 0] is the next layer's per-point input row
+        ld_out = _pad4(c_total + 3)
+        out_rows = torch.zeros((B, S, ld_out), dtype=torch.float32, device=xyz.device)
+        out_rows[:, :, c_total:c_total + 3] = centres_rows
         mode = {"tf32x3": _capi.TC_TF32X3, "bf16": _capi.TC_BF16}.get(_mlp_precision)
         fmode = _capi.TC_TF32_BF16C if (mode == _capi.TC_TF32X3 and not _TF32X3_PURE) else mode   # fused kernel's mode
         all_layers = [self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]) for i in range(len(self.nsample_list))]
@@ -366,14 +433,17 @@ class PointNetSetAbstractionMsg(nn.Module):
         pts8 = P = C = None
         p_cols = []
         if any(fused) and not per_point:
-            pts8 = self._pts8_cache if self._pts8_cache is not None else self._pts8(xyz, points, strides)
+            pts8 = geom["pts8"] if geom["pts8"] is not None else self._pts8(xyz, points, strides)
         elif any(fused):
             # layer 1 once per point: P = W1'[f; xyz] + b1' for every fused scale side by side,
             # C = W1'_xyz centre per centre (see sa_fused_tc.cu)
-            ld_pts = _pad4(D + 3)
-            x_pts = torch.zeros((B * N, ld_pts), dtype=torch.float32, device=xyz.device)
-            _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, x_pts, N * ld_pts, ld_pts, 0)
-            _capi.transpose(xyz, strides, B, 3, N, x_pts, N * ld_pts, ld_pts, D)
+            if rows_in is not None:
+                x_pts, ld_pts = rows_in.rows.view(B * N, rows_in.ld), rows_in.ld      # the previous layer left them ready
+            else:
+                ld_pts = _pad4(D + 3)
+                x_pts = torch.zeros((B * N, ld_pts), dtype=torch.float32, device=xyz.device)
+                _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, x_pts, N * ld_pts, ld_pts, 0)
+                _capi.transpose(xyz, strides, B, 3, N, x_pts, N * ld_pts, ld_pts, D)
             c1_total = sum(w[0] for w, f in zip(widths, fused) if f)
             P = torch.empty((B * N, c1_total), dtype=torch.float32, device=xyz.device)
             C = torch.empty((B * S, c1_total), dtype=torch.float32, device=xyz.device)
@@ -410,7 +480,7 @@ class PointNetSetAbstractionMsg(nn.Module):
                 if f:
                     col += layers[0]["cout"]
 
-        compact = self._compact if any(fused) else None
+        compact = geom["compact"] if any(fused) else None
         self.last_compact_rows = None if compact is None else compact[2]     # int32 [n_scales] on the device (diagnostics)
 
         feats_rows = None
@@ -433,10 +503,12 @@ class PointNetSetAbstractionMsg(nn.Module):
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
                                    C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
                                    layers[0]["cout"], [L["cout"] for L in use], packed, [L["bias"] for L in use],
-                                   out_rows, c_total, col, fmode,
+                                   out_rows, ld_out, col, fmode,
                                    compact=None if compact is None else (compact[0][i], compact[1][i], compact[2][i:i + 1]))
             else:
-                if feats_rows is None and points is not None:
+                if feats_rows is None and rows_in is not None:
+                    feats_rows = rows_in.rows[:, :, :D].contiguous()
+                elif feats_rows is None and points is not None:
                     feats_rows = _to_rows(points)
                 per_window = S * K * 4 * (ld_x + sum(_pad4(l["cout"]) for l in layers[:-1]))
                 chunk = max(1, min(B, _WORKSPACE_BYTES // per_window))
@@ -446,10 +518,10 @@ class PointNetSetAbstractionMsg(nn.Module):
                     x = torch.empty((M, ld_x), dtype=torch.float32, device=xyz.device)
                     _capi.group_gather(xyz[b0:b0 + nb], strides, None if feats_rows is None else feats_rows[b0:b0 + nb], D,
                                        centres_rows[b0:b0 + nb], ball[b0:b0 + nb], k_off, nb, N, S, K, x, ld_x)
-                    _mlp_rows(x, M, ld_x, layers, K, out_rows[b0:b0 + nb], c_total, col)
+                    _mlp_rows(x, M, ld_x, layers, K, out_rows[b0:b0 + nb], ld_out, col)
             k_off += K
             col += layers[-1]["cout"]
-        return _rows_to_cf(out_rows)
+        return _LevelRows(out_rows, c_total, geom["new_xyz"])
 
     def _forward_autograd(self, xyz, points, strides, centres_rows, ball):
         B, _, N = xyz.shape
@@ -484,6 +556,7 @@ class PointNetSetAbstraction(nn.Module):
             last = w
         self.group_all = group_all
         self._folded = _FoldedMLP()
+        self._folded_rows = _FoldedMLP()       # first layer's input channels in [points | xyz] order (see _group_all_rows)
 
     def forward(self, xyz, points, fps_start=None):
         """xyz [B,3,N], points [B,D,N] or None -> (new_xyz [B,3,S], new_points [B,D',S])."""
@@ -495,10 +568,30 @@ class PointNetSetAbstraction(nn.Module):
             if autograd:
                 return new_xyz, self._group_all_autograd(xyz, points)
             with torch.no_grad():
+                rows_in = _level_rows_of(xyz, points)
+                if rows_in is not None:
+                    return new_xyz, self._group_all_rows(rows_in)
                 return new_xyz, self._group_all_fused(xyz, points)
         return self._forward_sampled(xyz, points, fps_start, autograd)
 
+    def forward_rows(self, xyz, points):
+        """group_all inference on the previous layer's ``_LevelRows`` record -> pooled features [B, D', 1]."""
+        if not self.group_all or not isinstance(points, _LevelRows):
+            raise RuntimeError("forward_rows: group_all layers fed with a _LevelRows record only")
+        with torch.no_grad():
+            return self._group_all_rows(points)
+
     # ---- group_all ---------------------------------------------------------------------
+    def _group_all_rows(self, rec):
+        """group_all over the previous layer's rows [points | xyz | 0] as they are: the reference's channel order
+        is [xyz, points] (:141-158), so the first layer's input channels are permuted instead of the data."""
+        B, N, D = rec.B, rec.S, rec.c
+        layers = self._folded_rows.get(self.mlp_convs, self.mlp_bns, in_perm=list(range(3, 3 + D)) + [0, 1, 2])
+        c_out = layers[-1]["cout"]
+        out = torch.zeros((B, c_out), dtype=torch.float32, device=rec.rows.device)
+        _mlp_rows(rec.rows.view(B * N, rec.ld), B * N, rec.ld, layers, N, out, c_out, 0)
+        return out.view(B, c_out, 1)
+
     def _group_all_fused(self, xyz, points):
         B, _, N = xyz.shape
         D = 0 if points is None else points.shape[1]

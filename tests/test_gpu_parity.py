@@ -306,6 +306,43 @@ def test_results_do_not_depend_on_sharding_or_chunking(monkeypatch):
     assert torch.equal(whole, chunked)
 
 
+def test_row_chaining_between_layers_and_side_stream(monkeypatch, precision):
+    """The encoder's inference path hands each layer's point-major rows to the next and runs sa2's FPS + ball
+    query on a second stream; the module-by-module calls of the reference's API take the same shortcut through
+    the record riding on the returned tensor.  All of it must give the same results as feeding plain
+    channel-first tensors, and an in-place edit of the tensor must drop the shortcut."""
+    from ev2hands_b200 import encoder as enc_mod
+    tol = PRECISION_TOL[precision]
+    enc = _encoder_with((7, 8, 9))
+    ev = dev(synth.make_windows(3, 2048, seed=99))
+    s1 = torch.from_numpy(synth.make_start_indices(3, 2048, 3))
+    s2 = torch.from_numpy(synth.make_start_indices(3, 512, 4))
+    with torch.no_grad():
+        fast, lv = enc(ev, fps_starts=(s1, s2), return_levels=True)
+        monkeypatch.setattr(enc_mod, "_GEOM_STREAM", False)
+        one_stream = enc(ev, fps_starts=(s1, s2))
+        assert torch.equal(fast, one_stream)
+        # module by module, the way TEHNet.forward calls them (TEHNet.py:172-181): shortcut through the riding record
+        l1_xyz, l1_points = enc.sa1(ev[:, :3, :], ev, fps_start=s1)
+        assert getattr(l1_points, "_ev2h_rows", None) is not None
+        l2_xyz, l2_points = enc.sa2(l1_xyz, l1_points, fps_start=s2)
+        _, l3 = enc.sa3(l2_xyz, l2_points)
+        assert torch.equal(l1_points, lv["l1_points"]) and torch.equal(l2_points, lv["l2_points"])
+        assert torch.equal(l3.squeeze(-1), fast)
+        # plain tensors (no record): the layers transpose them themselves; same values up to the summation order
+        # of sa3's first layer (its input channels arrive as [xyz | points] instead of [points | xyz])
+        p1 = l1_points.clone()
+        l2_xyz_b, l2_points_b = enc.sa2(l1_xyz.clone(), p1, fps_start=s2)
+        assert torch.equal(l2_xyz_b, l2_xyz) and torch.equal(l2_points_b, l2_points)
+        _, l3_b = enc.sa3(l2_xyz_b, l2_points_b.clone())
+        assert rel_err(l3_b, l3) <= tol
+        # an in-place edit makes the record stale: the edited tensor is what must be consumed
+        l1_points.mul_(0.5)
+        _, l2_half = enc.sa2(l1_xyz, l1_points, fps_start=s2)
+        _, l2_want = enc.sa2(l1_xyz, l1_points.clone(), fps_start=s2)
+        assert torch.equal(l2_half, l2_want) and not torch.equal(l2_half, l2_points)
+
+
 def test_full_size_properties_batch64():
     """BASELINE config 2 (B=64, N=2048): size-independent properties instead of an oracle run."""
     B, N = 64, 2048
