@@ -61,6 +61,8 @@ _SIGNATURES = {
                                      c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_three_nn_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_three_interp_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp],
+    "ev2h_window_aggregate_f64": [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "ev2h_window_sample_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_group_max_bwd_f32": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
 }
@@ -496,3 +498,41 @@ def three_interp(feats_rows, ld_f, idx, weight, B, N, S, D, out_rows, ld_out, co
         with _timed("ev2h_three_interp_f32"):
             _check(lib().ev2h_three_interp_f32(_p(feats_rows), ld_f, _p(idx), _p(weight), B, N, S, D, _p(out_rows), ld_out, col,
                                                _stream(out_rows)), "ev2h_three_interp_f32")
+
+
+WINDOW_STREAM, WINDOW_ERPC = 0, 1
+
+
+def window_aggregate(events: torch.Tensor, win_start: torch.Tensor, win_count: torch.Tensor, max_count: int,
+                     width: int, height: int, mode: int):
+    """events float64 [n, >=4] (CUDA), win_start int64 [B], win_count int32 [B] (CUDA)
+    -> (records fp32 [B, max_count, 5], n_pixels int32 [B], n_bad int32 [B])."""
+    if not events.is_cuda or events.dtype != torch.float64 or events.dim() != 2 or events.stride(1) != 1:
+        raise RuntimeError("events must be a CUDA float64 [n, >=4] tensor with contiguous rows (there is no CPU path)")
+    dev = events.device
+    B = win_start.shape[0]
+    win_start = win_start.to(device=dev, dtype=torch.int64).contiguous()
+    win_count = win_count.to(device=dev, dtype=torch.int32).contiguous()
+    records = torch.empty((B, max_count, 5), dtype=torch.float32, device=dev)
+    n_pixels = torch.empty((B,), dtype=torch.int32, device=dev)
+    n_bad = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        with _timed("ev2h_window_aggregate_f64"):
+            _check(lib().ev2h_window_aggregate_f64(_p(events), events.stride(0), _p(win_start), _p(win_count), B, max_count,
+                                                   width, height, mode, _p(records), _p(n_pixels), _p(n_bad), _stream(events)),
+                   "ev2h_window_aggregate_f64")
+    return records, n_pixels, n_bad
+
+
+def window_sample(records: torch.Tensor, n_pixels: torch.Tensor, sample_idx: torch.Tensor, width: int, height: int,
+                  n_bad: torch.Tensor):
+    """records [B, max_count, 5], sample_idx int64 [B, N] -> windows fp32 [B, 5, N] (channel-first, the encoder's input)."""
+    B, max_count, _ = records.shape
+    N = sample_idx.shape[1]
+    out = torch.empty((B, 5, N), dtype=torch.float32, device=records.device)
+    sample_idx = sample_idx.to(device=records.device, dtype=torch.int64).contiguous()
+    with torch.cuda.device(records.device):
+        with _timed("ev2h_window_sample_f32"):
+            _check(lib().ev2h_window_sample_f32(_p(records), max_count, _p(n_pixels), _p(sample_idx), B, N, width, height,
+                                                _p(out), _p(n_bad), _stream(records)), "ev2h_window_sample_f32")
+    return out

@@ -159,3 +159,31 @@ def random_state_for(spec: dict, seed: int) -> dict:
                                spec["mlp_list"], cins, seed)
     return random_sa_state("mlp_convs.{j}", "mlp_bns.{j}", [spec["mlp"]],
                            [spec["in_channel"]], seed)
+
+
+def make_raw_events(n_events: int, seed: int = 0, t0: float = 0.0, duration: float = 5.0e6,
+                    extra_columns: int = 0, unique_times: bool = False) -> np.ndarray:
+    """A raw event stream, float64 ``[n_events, 4 + extra_columns]`` = (x, y, t, polarity, ...), time ordered:
+    the rows the reference's window builders consume (``dataset/erpc.py:170-176`` reads x, y, t [ns], p and two
+    bookkeeping columns from the HDF5 table; ``dataset/evaluation_stream.py:108-127`` rows of x, y, t [ms], p).
+    Same spatial recipe as ``make_windows``: two Gaussian blobs plus 1/32 uniform noise on the 346x260 sensor."""
+    rs = np.random.RandomState(seed)
+    n_noise = max(1, n_events // 32)
+    n_sig = n_events - n_noise
+    n_a = n_sig // 2
+    centres = np.stack([rs.uniform(60, SENSOR_W - 60, size=2), rs.uniform(50, SENSOR_H - 50, size=2)], axis=1)
+    sigma = rs.uniform(18.0, 32.0, size=2)
+    xs = np.concatenate([rs.normal(centres[0, 0], sigma[0], n_a), rs.normal(centres[1, 0], sigma[1], n_sig - n_a),
+                         rs.uniform(0, SENSOR_W, n_noise)])
+    ys = np.concatenate([rs.normal(centres[0, 1], sigma[0], n_a), rs.normal(centres[1, 1], sigma[1], n_sig - n_a),
+                         rs.uniform(0, SENSOR_H, n_noise)])
+    order = rs.permutation(n_events)
+    out = np.zeros((n_events, 4 + extra_columns), dtype=np.float64)
+    out[:, 0] = np.clip(xs, 0, SENSOR_W - 1).astype(np.int64)[order]
+    out[:, 1] = np.clip(ys, 0, SENSOR_H - 1).astype(np.int64)[order]
+    if unique_times:      # no two events share a timestamp (integer ticks drawn without replacement)
+        out[:, 2] = t0 + np.sort(rs.choice(int(duration), size=n_events, replace=False)).astype(np.float64)
+    else:
+        out[:, 2] = t0 + np.sort(np.floor(rs.uniform(0.0, duration, n_events)))
+    out[:, 3] = (rs.rand(n_events) < 0.5).astype(np.float64)
+    return out

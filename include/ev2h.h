@@ -318,6 +318,36 @@ EV2H_API int ev2h_three_interp_f32(const float *feats_rows, int ld_f, const int3
                                    int B, int N, int S, int D, float *out_rows, int ld_out, int col,
                                    ev2h_stream_t stream);
 
+/* ---- event-window construction -------------------------------------
+ * The step in front of the encoder: raw camera events -> the [5, N] point set (x, y, t, n_pos, n_neg).
+ * Replaces the per-window numpy code of the reference's two dataset classes:
+ *   EV2H_WINDOW_STREAM  ERPCParser.__getitem__, src/Ev2Hands/dataset/evaluation_stream.py:188-215
+ *   EV2H_WINDOW_ERPC    Ev2HandSDataset.__getitem__, src/Ev2Hands/dataset/erpc.py:178-218 and :249
+ * (np.add.at into 346x260 float32 grids, np.nonzero, mean time, [ERPC: * 1e-6, argsort by time, rebase,]
+ * np.random.choice(M, N), pc_normalize).  Two calls, because the reference draws the N indices from numpy's
+ * global generator with M, the number of occupied pixels, as the bound - the caller reads n_pixels back,
+ * draws exactly like the reference, and passes the indices in (the same convention as the FPS start indices).
+ *
+ * events: float64 rows of row_stride doubles, columns 0..3 = x, y, t, polarity (any further columns are
+ * ignored: the ERPC table carries two more); window b = rows [win_start[b], win_start[b] + win_count[b]),
+ * win_count[b] <= max_count <= 16384 (STREAM) / 4096 (ERPC).  Every per-pixel sum is taken the way np.add.at
+ * takes it: in double, rounded to the float32 cell, in stream order.  STREAM subtracts the window's first
+ * timestamp from every t first (:188).  records: fp32 [B, max_count, 5] = (x, y, t_mean, n_pos, n_neg) of the
+ * n_pixels[b] occupied pixels, in the reference's order right before the draw: np.nonzero (row-major) order
+ * for STREAM, ascending mean time (pixel order among equal means, where the reference's unstable argsort may
+ * return any order) with the earliest subtracted for ERPC.  Events outside the sensor are dropped and counted
+ * in n_bad[b] (numpy would raise IndexError, or wrap negative indices). */
+enum { EV2H_WINDOW_STREAM = 0, EV2H_WINDOW_ERPC = 1 };
+EV2H_API int ev2h_window_aggregate_f64(const double *events, int64_t row_stride, const int64_t *win_start,
+                                       const int32_t *win_count, int B, int max_count, int width, int height, int mode,
+                                       float *records, int32_t *n_pixels, int32_t *n_bad, ev2h_stream_t stream);
+/* out[b] = pc_normalize(records[b][sample_idx[b]]) transposed: fp32 [B, 5, N]; x -> 2 (x / width) - 1,
+ * y -> 2 (y / height) - 1, t -> 2 ((t - t_min) / (t_max - t_min)) - 1 over the N drawn points (IEEE divisions in
+ * the reference's operation order; a window whose drawn points share one time gives NaN like the reference).
+ * sample_idx int64 [B, N], each in [0, n_pixels[b]); violations are counted into n_bad[b] (added to it). */
+EV2H_API int ev2h_window_sample_f32(const float *records, int max_count, const int32_t *n_pixels, const int64_t *sample_idx,
+                                    int B, int N, int width, int height, float *out, int32_t *n_bad, ev2h_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -686,3 +686,105 @@ def test_ball_query_with_in_kernel_compaction_matches_the_two_step_tables():
                     d.setdefault(int(g), []).extend(rm[8 * blk:8 * blk + 8].tolist())
                 return d
             assert per_group(rowmaps[i], blockgroups[i]) == per_group(rm2[i], bg2[i])
+
+
+# ------------------------------------------------------------------ event windows ----
+def _window_case(golden, case):
+    g = golden("windows")
+    return (g[case + "_events"], g[case + "_starts"], g[case + "_counts"], g[case + "_idx"], g[case + "_windows"], g[case + "_M"])
+
+
+@pytest.mark.parametrize("case,mode", [("stream", "stream"), ("erpc", "erpc"), ("erpct", "erpc")])
+def test_event_windows_golden(golden, case, mode):
+    """ev2h_window_aggregate_f64 + ev2h_window_sample_f32 against what the reference's own dataset classes
+    produced from the same raw events and the same draw: bit for bit ("erpct": where equal mean times leave
+    the reference's unstable argsort a choice, time and every untied point)."""
+    from oracle import window_oracle as wo
+    ev, starts, counts, idx, want, M = _window_case(golden, case)
+    wb = e2h.EventWindowBuilder(mode)
+    got = wb(torch.from_numpy(ev).to(DEV), starts, counts, sample_idx=torch.from_numpy(idx), check=True)
+    assert np.array_equal(wb.last_n_pixels.cpu().numpy(), M)
+    got = got.cpu().numpy()
+    assert got.shape == want.shape
+    if case == "erpct":
+        for b, (s, c) in enumerate(zip(starts, counts)):
+            rec = wo.aggregate(ev[s:s + c], mode)
+            tt = rec[:, 2]
+            u, cn = np.unique(tt, return_counts=True)
+            keep = ~np.isin(tt, u[cn > 1])[idx[b]]
+            assert np.array_equal(got[b, 2], want[b, 2]) and np.array_equal(got[b][:, keep], want[b][:, keep])
+        # and all of it against the oracle, whose sort is stable like the kernel's
+        assert np.array_equal(got, wo.build_windows(ev, starts, counts, idx, mode))
+    else:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_event_windows_draw_like_the_reference(golden):
+    """without explicit indices the builder draws np.random.choice(M, N) per window from numpy's global generator"""
+    ev, starts, counts, idx, want, M = _window_case(golden, "stream")
+    wb = e2h.EventWindowBuilder("stream")
+    np.random.seed(5)                     # the seed tests/golden/make_window_golden.py used
+    got = wb(torch.from_numpy(ev).to(DEV), starts, counts)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode,n_max", [("stream", 16384), ("stream", 700), ("erpc", 4096), ("erpc", 33)])
+def test_event_windows_ragged_vs_oracle(mode, n_max):
+    """ragged batches up to the largest supported window, overlapping windows, hot pixels (long runs), a single
+    event, negative and huge timestamps - records and windows against the oracle, bit for bit"""
+    from oracle import window_oracle as wo
+    rs = np.random.RandomState(n_max)
+    ev = synth.make_raw_events(3 * n_max + 50, seed=n_max, t0=-2.5e5 if mode == "stream" else 7.0e9, duration=6.0e5,
+                               extra_columns=2 if mode == "erpc" else 0)
+    ev[10:10 + n_max // 3, :2] = (17, 200)                  # a hot pixel: one long run
+    ev[5, 3] = 2.0                                          # polarity that is neither 0 nor 1 counts as negative
+    starts = np.array([0, 7, n_max, 2 * n_max + 49, 3])
+    counts = np.array([n_max, max(1, n_max // 2), n_max - 1, 1, 2])
+    wb = e2h.EventWindowBuilder(mode, n_events=777)
+    rec, n_pix, n_bad = wb.aggregate(torch.from_numpy(ev).to(DEV), starts, counts)
+    want_rec = [wo.aggregate(ev[s:s + c], mode) for s, c in zip(starts, counts)]
+    assert n_pix.cpu().tolist() == [r.shape[0] for r in want_rec] and int(n_bad.sum()) == 0
+    for b, r in enumerate(want_rec):
+        assert np.array_equal(rec[b, :r.shape[0]].cpu().numpy().view(np.uint32), r.view(np.uint32)), b
+    idx = np.stack([rs.randint(0, r.shape[0], size=777) for r in want_rec])
+    got = wb.sample(rec, n_pix, n_bad, torch.from_numpy(idx)).cpu().numpy()
+    want = wo.build_windows(ev, starts, counts, idx, mode)
+    assert np.array_equal(got, want, equal_nan=True)        # the 1-event window is NaN in t (0/0) there too
+    assert np.isnan(got[3, 2]).all() and not np.isnan(got[[0, 1, 2]]).any()
+    if mode == "stream":        # ("erpc" at 7e9 ns: the two events' mean times are one float32, NaN like the reference)
+        assert not np.isnan(got[4]).any()
+
+
+def test_event_windows_errors_and_out_of_sensor_events():
+    ev = synth.make_raw_events(300, seed=3)
+    ev[7, 0] = 346.0          # one column past the sensor
+    ev[9, 1] = -1.0
+    wb = e2h.EventWindowBuilder("stream", n_events=64)
+    d = torch.from_numpy(ev).to(DEV)
+    rec, n_pix, n_bad = wb.aggregate(d, [0], [300])
+    assert n_bad.cpu().tolist() == [2]
+    with pytest.raises(IndexError):
+        wb(d, [0], [300], check=True)
+    with pytest.raises(IndexError):
+        wb.aggregate(d, [200], [101])
+    with pytest.raises(RuntimeError):
+        wb.aggregate(torch.from_numpy(ev), [0], [300])              # host tensor: no CPU path
+    with pytest.raises(RuntimeError, match="exceed"):
+        e2h.EventWindowBuilder("erpc").aggregate(torch.zeros((5000, 4), dtype=torch.float64, device=DEV), [0], [5000])
+    bad_idx = torch.full((1, 64), 10 ** 6, dtype=torch.int64)
+    wb.sample(rec, n_pix, n_bad, bad_idx)
+    assert int(n_bad[0]) == 2 + 64
+
+
+def test_event_windows_feed_the_encoder(golden):
+    """raw events -> windows -> encoder, all on the device: same features as the encoder on the reference's window"""
+    ev, starts, counts, idx, want, M = _window_case(golden, "stream")
+    enc = _encoder_with((1, 2, 3))
+    wb = e2h.EventWindowBuilder("stream")
+    wins = wb(torch.from_numpy(ev).to(DEV), starts, counts, sample_idx=torch.from_numpy(idx))
+    s1 = torch.from_numpy(synth.make_start_indices(3, 2048, 0))
+    s2 = torch.from_numpy(synth.make_start_indices(3, 512, 1))
+    with torch.no_grad():
+        a = enc(wins, fps_starts=(s1, s2))
+        b = enc(dev(want), fps_starts=(s1, s2))
+    assert torch.equal(a, b)
