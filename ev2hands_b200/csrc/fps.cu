@@ -124,7 +124,7 @@ extern "C" int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c
     if (N <= 256) EV2H_FPS(64, 4, true);
     if (N <= 512) EV2H_FPS(128, 4, true);
     if (N <= 1024) EV2H_FPS(256, 4, true);
-    if (N <= 2048) EV2H_FPS(256, 8, true);
+    if (N <= 2048) EV2H_FPS(256, 8, true);      // 128 / 512 / 1024 threads per window measured 0.173 / 0.197 / 0.235 ms vs 0.179 ms (B = 64)
     if (N <= 4096) EV2H_FPS(512, 8, true);
     if (N <= 8192) EV2H_FPS(1024, 8, true);
     EV2H_FPS(1024, 16, false);

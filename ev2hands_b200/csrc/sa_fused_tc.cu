@@ -513,9 +513,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                         mma(true, d, x, w + (b_part_d >> 1), 1u);            // x_hi * w_lo
                     };
                     for (uint32_t c = 0; c < nch[g]; ++c) {
-                        tc::mbar_wait_u32(a_full_u + 8 * a_slot, a_phase, 40 + g);
-                        FZ_TRACE(3, 2, it, g * 50 + c);
-                        tc::mbar_wait_u32(b_full_u + 8 * b_slot, b_phase, 50 + g);
+                        tc::mbar_wait2_u32(a_full_u + 8 * a_slot, a_phase, b_full_u + 8 * b_slot, b_phase, 40 + g, 50 + g);
                         FZ_TRACE(3, 3, it, g * 50 + c);
                         tc::tc_fence_after();
                         const uint32_t x0 = a_base + a_slot * a_slot_d, w0 = b_base + b_slot * b_slot_d;

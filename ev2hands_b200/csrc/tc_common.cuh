@@ -90,6 +90,18 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity, int
         if ((++spins & 15u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(tag, parity);   // ~2 s
     }
 }
+// Two barriers at once: both probes are in flight together (a probe costs ~80 cycles even when the phase is already
+// complete, profiles/r01_umma_handshake_microbench.txt), then whichever is still pending is waited for.
+__device__ __forceinline__ void mbar_wait2_u32(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b, int tag_a, int tag_b) {
+    uint32_t ok_a, ok_b;
+    asm volatile("{\n.reg .pred p, q;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n"
+                 "selp.u32 %0, 1, 0, p;\nselp.u32 %1, 1, 0, q;\n}\n"
+                 : "=r"(ok_a), "=r"(ok_b) : "r"(bar_a), "r"(parity_a), "r"(bar_b), "r"(parity_b) : "memory");
+    if (!ok_a) mbar_wait_u32(bar_a, parity_a, tag_a);
+    if (!ok_b) mbar_wait_u32(bar_b, parity_b, tag_b);
+}
 __device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
