@@ -55,7 +55,11 @@ constexpr int FZ_MAX_PRODUCERS = 3;       // up to two loader groups + the epilo
 //   KC  channels per K chunk (32, or 16 to halve the ring footprint so two CTAs share an SM)
 //   LG  loader groups of 4 warps;  threads = 32 * (6 + 4 LG): loaders, weight streamer, issuer, 4 epilogue warps
 //   OCC CTAs per SM the instance is built for (launch bound; TMEM share is 512 / OCC columns)
-__host__ __device__ constexpr int fz_threads(int lg) { return 32 * (6 + 4 * lg); }
+// With one CTA per SM nothing else fills the tensor pipe while the issuing thread waits, commits and sets up the
+// next chunk (about half of its time per chunk), so those instances run TWO issuer warps that take alternate K
+// chunks of a layer: one thread's hand-shakes overlap the other's UMMAs.  (Two CTAs per SM overlap each other.)
+__host__ __device__ constexpr int fz_issuers(int occ) { return occ == 1 ? 2 : 1; }
+__host__ __device__ constexpr int fz_threads(int lg, int occ) { return 32 * (5 + 4 * lg + fz_issuers(occ)); }
 
 enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1, FZ_MODE_MIXED = 2 };
 
@@ -112,7 +116,7 @@ struct Ring {
 // lifetime) and, for n >= ring size, the wait for the issuer's grant of that slot.  `bits` holds one
 // phase bit per slot, toggled every time this producer consumes a grant.
 __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs, int ring, uint32_t &bits, int tag) {
-    const int slot = (int)(ring == 2 ? (n_abs & 1u) : (n_abs % 3u));          // the operand ring has 2 or 3 slots
+    const int slot = (int)(ring == 2 ? (n_abs & 1u) : ring == 4 ? (n_abs & 3u) : (n_abs % 3u));          // the operand ring has 2, 3 or 4 slots
     if (n_abs >= (uint32_t)ring) {
         tc::mbar_wait(my_grants + slot, (bits >> slot) & 1u, tag);
         bits ^= 1u << slot;
@@ -121,10 +125,11 @@ __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs,
 }
 
 template <int MODE, int KC, int LG, int OCC>
-__global__ void __launch_bounds__(fz_threads(LG), OCC)
+__global__ void __launch_bounds__(fz_threads(LG, OCC), OCC)
 sa_fused_tc_kernel(const FusedParams p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
-    constexpr int THREADS = fz_threads(LG);
+    constexpr int THREADS = fz_threads(LG, OCC);
+    constexpr int NI = fz_issuers(OCC);
     constexpr int EB = MODE == FZ_MODE_BF16 ? 2 : 4;
     constexpr int PARTS = MODE == FZ_MODE_BF16 ? 1 : 2;
     constexpr int A_PART = FZ_BLOCK_M * KC * EB;         // per precision part: 16 KB (tf32, KC 32) ... 8 KB
@@ -149,8 +154,10 @@ sa_fused_tc_kernel(const FusedParams p) {
     uint64_t *b_empty = b_full + FZ_MAX_RING;
     uint64_t *acc_full = b_empty + FZ_MAX_RING;          // [2]
     uint64_t *acc_empty = acc_full + FZ_GEMMS;           // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + FZ_GEMMS);
-    float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);          // [n0 + n1]; tail offset 432, 16-byte aligned
+    uint64_t *init_done = acc_empty + FZ_GEMMS;          // [2] two issuers: chunk 0 of a layer (the accumulator's overwrite) has completed
+    uint64_t *turn = init_done + FZ_GEMMS;               // [2] two issuers: turn[i] = issuer i has ISSUED another of its chunks
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(turn + FZ_GEMMS);
+    float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);          // [n0 + n1]; tail offset 464, 16-byte aligned
     float *w1s = bias_s + p.n[0] + p.n[1];                             // [c1_pad][8] layer-1 weights (gather mode)
     float *b1s = w1s + (p.per_point ? 0 : p.n_chunks[0] * KC * 8);     // [c1_pad]
 
@@ -170,7 +177,10 @@ sa_fused_tc_kernel(const FusedParams p) {
             for (int pr = 0; pr < FZ_MAX_PRODUCERS; ++pr) tc::mbar_init(a_grant + pr * FZ_MAX_RING + s, 1);
         }
         for (int s = 0; s < p.sb; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
-        for (int g = 0; g < FZ_GEMMS; ++g) { tc::mbar_init(acc_full + g, 1); tc::mbar_init(acc_empty + g, 128); }
+        for (int g = 0; g < FZ_GEMMS; ++g) {
+            tc::mbar_init(acc_full + g, NI); tc::mbar_init(acc_empty + g, 128); tc::mbar_init(init_done + g, 1);
+            tc::mbar_init(turn + g, 1);
+        }
         tc::fence_mbar_init();
     }
     for (int g = 0; g < FZ_GEMMS; ++g)
@@ -186,7 +196,7 @@ sa_fused_tc_kernel(const FusedParams p) {
     }
     // Warp roles, lowest to highest warp id = lowest to highest scheduler priority: loaders (work with
     // slack), weight streamer, UMMA issuer, and the epilogue warps, which are the serial bottleneck of a tile.
-    constexpr int STREAMER_WARP = 4 * LG, ISSUER_WARP = 4 * LG + 1, EPI_WARP0 = 4 * LG + 2;
+    constexpr int STREAMER_WARP = 4 * LG, ISSUER_WARP = 4 * LG + 1, EPI_WARP0 = 4 * LG + 1 + NI;
     const int loader_idx = warp;
     const bool is_loader = warp < STREAMER_WARP;
     if (warp == ISSUER_WARP) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -449,15 +459,28 @@ sa_fused_tc_kernel(const FusedParams p) {
             }
         }
         __syncwarp();
-    } else if (warp == ISSUER_WARP) {
-        // =============================== UMMA issuer ===============================
-        // ONE thread walks the chunk sequence; its per-chunk latency bounds the whole kernel (every chunk of
-        // every tile passes through it), so everything loop invariant is hoisted into registers, barriers are
-        // addressed in the shared window directly and the K steps of a full chunk are straight-line code.
+    } else if (warp >= ISSUER_WARP && warp < ISSUER_WARP + NI) {
+        // =============================== UMMA issuer(s) ===============================
+        // One thread walks the chunk sequence; its per-chunk latency bounds the kernel (every chunk of every tile
+        // passes through it), so everything loop invariant is hoisted into registers, barriers are addressed in
+        // the shared window directly and the K steps of a full chunk are straight-line code.
+        // NI == 2: issuer `me` takes the chunks whose absolute number (over the CTA's lifetime) is me mod 2.  Both
+        // rings have an even number of slots there (host side), so a slot - and every phase of its barriers -
+        // belongs to one issuer: the two are independent pipelines sharing the tensor pipe, and no parity wait can
+        // be a phase off.  The chunks are still ISSUED in sequence - an issuer passes the turn on (turn[me], a plain
+        // arrive behind tcgen05.fence::before_thread_sync) once its chunk's UMMAs are issued, and takes it before
+        // its next chunk - so the accumulation order, and with it every output bit, is that of one issuer; what
+        // overlaps the other's UMMAs is everything else (operand waits, commits, descriptor set-up).  Chunk 0 of a
+        // layer overwrites the accumulator: the owner of chunk 1 additionally waits until chunk 0 has COMPLETED
+        // (tcgen05.commit -> init_done), and the accumulator goes to the epilogue after both issuers' commits
+        // (acc_full counts NI).  Both wait for acc_empty at the start of every layer.
+        const uint32_t me = (uint32_t)(warp - ISSUER_WARP);
         if (lane == 0) {
             const uint32_t sa = (uint32_t)p.sa, sb = (uint32_t)p.sb, mb3 = (uint32_t)p.mb3;
             const uint32_t a_full_u = tc::smem_u32(a_full), a_grant_u = tc::smem_u32(a_grant), b_full_u = tc::smem_u32(b_full),
-                           b_empty_u = tc::smem_u32(b_empty), acc_full_u = tc::smem_u32(acc_full), acc_empty_u = tc::smem_u32(acc_empty);
+                           b_empty_u = tc::smem_u32(b_empty), acc_full_u = tc::smem_u32(acc_full), acc_empty_u = tc::smem_u32(acc_empty),
+                           init_done_u = tc::smem_u32(init_done), turn_u = tc::smem_u32(turn);
+            uint32_t own = 0;                                    // chunks this issuer has issued (NI == 2)
             const uint32_t desc_hi = tc::smem_desc_hi(128);
             const uint32_t a_slot_d = (uint32_t)p.a_slot_bytes >> 4, b_slot_d = (uint32_t)p.b_slot_bytes >> 4;
             const uint32_t a_base = tc::smem_desc_lo(tc::smem_u32(a_ring), CHUNK_ROWS_BYTES);
@@ -467,7 +490,7 @@ sa_fused_tc_kernel(const FusedParams p) {
             const uint32_t nch[2] = {(uint32_t)nc0, (uint32_t)nc1}, ksl[2] = {(uint32_t)p.k_steps_last[0], (uint32_t)p.k_steps_last[1]};
             const uint32_t wr[2] = {(uint32_t)p.n[0], 128u * mb3};
             const uint32_t dt[2] = {tmem_base + (uint32_t)p.tmem_col[0], tmem_base + (uint32_t)p.tmem_col[1]};
-            uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+            uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, par = 0;      // par: parity of the chunk's absolute number
             // (tile iteration, position in tile) of the chunk that will reuse the slot being freed: sa chunks ahead
             uint32_t g_it = sa / Q, g_q = sa % Q;
             uint32_t it = 0;
@@ -485,7 +508,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                     const uint32_t b_base = b_ring_d | (b_lbo_d << 16);
                     const uint32_t n_mb = g == 0 ? 1u : mb3;
                     tc::mbar_wait_u32(acc_empty_u + 8 * g, (it & 1) ^ 1, 30 + g);      // previous tile's epilogue drained this accumulator
-                    FZ_TRACE(3, 1, it, g * 50);
+                    if (me == 0) FZ_TRACE(3, 1, it, g * 50);
                     tc::tc_fence_after();
                     // one product: x = activation operand, w = weight operand (descriptor low words)
                     auto mma = [&](bool k16, uint32_t d, uint32_t x, uint32_t w, uint32_t acc) {
@@ -513,8 +536,15 @@ sa_fused_tc_kernel(const FusedParams p) {
                         mma(true, d, x, w + (b_part_d >> 1), 1u);            // x_hi * w_lo
                     };
                     for (uint32_t c = 0; c < nch[g]; ++c) {
+                        if (NI == 1 || par == me) {
                         tc::mbar_wait2_u32(a_full_u + 8 * a_slot, a_phase, b_full_u + 8 * b_slot, b_phase, 40 + g, 50 + g);
-                        FZ_TRACE(3, 3, it, g * 50 + c);
+                        if (me == 0) FZ_TRACE(3, 3, it, g * 50 + c);
+                        if (NI == 2) {
+                            // my chunk is number 2 * own + me: the other issuer must have issued number 2 * own + me - 1
+                            if (me == 1) tc::mbar_wait_u32(turn_u, own & 1u, 37);
+                            else if (own > 0) tc::mbar_wait_u32(turn_u + 8, (own - 1u) & 1u, 38);
+                            if (c == 1) tc::mbar_wait_u32(init_done_u + 8 * g, it & 1, 35 + g);
+                        }
                         tc::tc_fence_after();
                         const uint32_t x0 = a_base + a_slot * a_slot_d, w0 = b_base + b_slot * b_slot_d;
                         const uint32_t acc0 = c > 0 ? 1u : 0u;
@@ -541,17 +571,25 @@ sa_fused_tc_kernel(const FusedParams p) {
                                 }
                             }
                         }
-                        FZ_TRACE(3, 6, it, g * 50 + c);
+                        if (NI == 2) {
+                            tc::tc_fence_before();
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(turn_u + 8 * me) : "memory");
+                            ++own;
+                        }
+                        if (me == 0) FZ_TRACE(3, 6, it, g * 50 + c);
                         // the producer that fills this operand slot next: a loader group or the epilogue warps
                         const uint32_t next_prod = g_q < (uint32_t)nc0 ? (LG == 1 ? 0u : (g_it * (uint32_t)nc0 + g_q) % LG) : (uint32_t)LG;
                         tc::umma_commit_u32(a_grant_u + 8 * (next_prod * FZ_MAX_RING + a_slot));
                         tc::umma_commit_u32(b_empty_u + 8 * b_slot);
-                        if (c + 1 == nch[g]) tc::umma_commit_u32(acc_full_u + 8 * g);
-                        FZ_TRACE(3, 7, it, g * 50 + c);
+                        if (NI == 2 && c == 0) tc::umma_commit_u32(init_done_u + 8 * g);
+                        if (me == 0) FZ_TRACE(3, 7, it, g * 50 + c);
+                        }
                         if (++a_slot == sa) { a_slot = 0; a_phase ^= 1; }
                         if (++b_slot == sb) { b_slot = 0; b_phase ^= 1; }
                         if (++g_q == Q) { g_q = 0; ++g_it; }
+                        par ^= 1u;
                     }
+                    tc::umma_commit_u32(acc_full_u + 8 * g);      // this issuer's UMMAs into accumulator g are done (all of them with NI == 1)
                 }
             }
         }
@@ -734,7 +772,7 @@ static int launch_fused(const FusedParams &p, size_t smem, unsigned grid, cudaSt
     auto k = sa_fused_tc_kernel<MODE, KC, LG, OCC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_sa_msg_fused_tc: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
-    k<<<grid, fz_threads(LG), smem, st>>>(p);
+    k<<<grid, fz_threads(LG, OCC), smem, st>>>(p);
     return check_launch("ev2h_sa_msg_fused_tc");
 }
 
@@ -837,7 +875,7 @@ static int sa_msg_fused_impl(
 
     p.a_slot_bytes = PARTS * FZ_BLOCK_M * KC * EB;
     p.b_slot_bytes = PARTS * max_n * KC * EB;
-    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 2 * FZ_GEMMS) * 8 + 16 + boff * 4 +
+    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 4 * FZ_GEMMS) * 8 + 16 + boff * 4 +
                      (per_point ? 0 : p.n_chunks[0] * KC * 9 * 4);
     int occ = pl.occ;
     int budget = (occ == 2 ? 113 : 227) * 1024 - tail - 512;
@@ -845,8 +883,10 @@ static int sa_msg_fused_impl(
     // at least 2 slots each; a third operand slot when affordable; weights get the rest (prefetched furthest ahead)
     p.sa = 2;
     if (budget - 3 * p.a_slot_bytes >= 3 * p.b_slot_bytes) p.sa = 3;
+    if (fz_issuers(occ) == 2) p.sa = budget - 4 * p.a_slot_bytes >= 4 * p.b_slot_bytes ? 4 : 2;      // a slot belongs to one issuer
     p.sb = (budget - p.sa * p.a_slot_bytes) / p.b_slot_bytes;
     if (p.sb > FZ_MAX_RING) p.sb = FZ_MAX_RING;
+    if (fz_issuers(occ) == 2) p.sb &= ~1;
     if (p.sb < 2) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: rings do not fit in shared memory");
     const size_t smem = (size_t)p.sa * p.a_slot_bytes + (size_t)p.sb * p.b_slot_bytes + tail;
 
