@@ -372,7 +372,7 @@ class PointNetSetAbstractionMsg(nn.Module):
             # compacted row lists come out of the ball query itself; in gather mode (narrow inputs, N <= 4096) neighbours
             # whose 32-byte record repeats an earlier point give identical rows and are listed once
             first = None
-            if _DEDUP and not (D + 3 > 8 or _PER_POINT_ALWAYS) and N <= 4096:
+            if _DEDUP and D + 3 <= 8 and N <= 4096:
                 geom["pts8"] = self._pts8(xyz, points, strides)
                 first = _capi.first_occurrence(geom["pts8"])
             ball, rowmaps, blockgroups, n_rows = _capi.ball_query_compact(xyz, strides, centres_rows, N, self.radius_list,
