@@ -21,3 +21,14 @@ for prec in ("tf32x3", "bf16", "fp32"):
         d0 = dec(ev[:, :3, :], lv["l1_xyz"], lv["l2_xyz"], torch.zeros(2, 3, 1, device=dev), lv["l1_points"], lv["l2_points"], l3.unsqueeze(-1))
     torch.cuda.synchronize()
     print(prec, float(l3.abs().sum()), float(d0.abs().sum()), flush=True)
+
+# event-window construction (both modes, ragged counts, a hot pixel)
+import numpy as np
+for mode, cols in (("stream", 0), ("erpc", 2)):
+    raw = synth.make_raw_events(5000, seed=5, t0=1.0e6, duration=5.0e6, extra_columns=cols)
+    raw[100:400, :2] = (40, 50)
+    wb = e2h.EventWindowBuilder(mode, n_events=2048)
+    np.random.seed(1)
+    w = wb(torch.from_numpy(raw).to(dev), [0, 1000, 2900, 4999], [2048, 1500, 2100 if mode == "stream" else 2048, 1], check=True)
+    torch.cuda.synchronize()
+    print(mode, float(w[:3].abs().sum()), int(wb.last_n_pixels.sum()), flush=True)
