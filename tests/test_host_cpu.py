@@ -97,3 +97,39 @@ def test_synthetic_windows_are_deterministic_and_event_like():
     uniq = len({tuple(p) for p in a[0, :3].T})
     assert uniq < 0.8 * 2048
     assert (a[:, 3:] >= 0).all() and (a[:, 3:] == np.round(a[:, 3:])).all()
+
+
+def test_event_window_builder_host_logic_and_no_cpu_path():
+    """EventWindowBuilder: argument checks happen on the host, nothing is computed without a GPU,
+    and the C ABI rejects bad arguments with a status instead of crashing."""
+    raw = torch.from_numpy(synth.make_raw_events(300, seed=3))
+    wb = e2h.EventWindowBuilder("stream", n_events=64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        wb(raw, [0], [300])
+    with pytest.raises(IndexError):
+        wb.aggregate(raw, [200], [101])
+    with pytest.raises(RuntimeError, match="at least one event"):
+        wb.aggregate(raw, [0], [0])
+    with pytest.raises(RuntimeError, match="equally long"):
+        wb.aggregate(raw, [0, 1], [10])
+    with pytest.raises(ValueError):
+        e2h.EventWindowBuilder("frames")
+    L = _capi.lib()
+    assert L.ev2h_window_aggregate_f64(None, 4, None, None, 1, 16, 346, 260, 0, None, None, None, None) == 1
+    p = ctypes.c_void_p(64)
+    assert L.ev2h_window_aggregate_f64(p, 4, p, p, 1, 5000, 346, 260, 1, p, p, p, None) == 2      # erpc: <= 4096 events
+    assert b"exceed" in L.ev2h_last_error()
+    assert L.ev2h_window_aggregate_f64(p, 4, p, p, 1, 16, 346, 260, 7, p, p, p, None) == 1 and b"mode" in L.ev2h_last_error()
+    assert L.ev2h_window_aggregate_f64(p, 4, p, p, 1, 16, 4096, 4096, 0, p, p, p, None) == 1      # pixel number must fit the sort key
+    assert L.ev2h_window_sample_f32(p, 16, p, p, 0, 64, 346, 260, p, p, None) == 1
+
+
+def test_raw_event_stream_is_deterministic_and_sensor_shaped():
+    a = synth.make_raw_events(4096, seed=9, t0=5.0, duration=1.0e4, extra_columns=2)
+    b = synth.make_raw_events(4096, seed=9, t0=5.0, duration=1.0e4, extra_columns=2)
+    assert np.array_equal(a, b) and a.shape == (4096, 6) and a.dtype == np.float64
+    assert (np.diff(a[:, 2]) >= 0).all() and a[0, 2] >= 5.0
+    assert (a[:, 0] >= 0).all() and (a[:, 0] < synth.SENSOR_W).all() and (a[:, 1] < synth.SENSOR_H).all()
+    assert set(np.unique(a[:, 3])) <= {0.0, 1.0}
+    u = synth.make_raw_events(2000, seed=1, duration=1.0e5, unique_times=True)
+    assert np.unique(u[:, 2]).size == 2000
