@@ -162,7 +162,7 @@ linear_tc_kernel(const TcParams p) {
             for (int kc = 0; kc < p.n_kc; ++kc, ++n) {
                 if ((int)(n % TC_LOADER_GROUPS) == grp) {
                     float4 v[8];
-                    if (MODE == TC_MODE_TF32X3) {
+                    if (MODE == TC_MODE_TF32X3) {                     // (MIXED uses the 8-channels-per-lane mapping below)
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int row = 32 * wq + (i >> 1) * 8 + l8;
@@ -201,6 +201,27 @@ linear_tc_kernel(const TcParams p) {
                             *reinterpret_cast<float4 *>(st + c * (TC_BLOCK_M * 16) + row * 16) = hi;
                             *reinterpret_cast<float4 *>(st + A_PART + c * (TC_BLOCK_M * 16) + row * 16) = lo;
                         }
+                    } else if (MODE == TC_MODE_MIXED) {
+                        // [x_hi as tf32 | x as bf16 | x_lo as bf16] (the layout of tc_pack_kernel<MIXED> and of
+                        // sa_fused_tc.cu): 8 channels of a row = two tf32 chunks and one chunk of each bf16 copy
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = 32 * wq + i * 8 + l8;
+                            float4 h0, l0, h1, l1;
+                            tc::split_tf32(v[2 * i].x, h0.x, l0.x); tc::split_tf32(v[2 * i].y, h0.y, l0.y);
+                            tc::split_tf32(v[2 * i].z, h0.z, l0.z); tc::split_tf32(v[2 * i].w, h0.w, l0.w);
+                            tc::split_tf32(v[2 * i + 1].x, h1.x, l1.x); tc::split_tf32(v[2 * i + 1].y, h1.y, l1.y);
+                            tc::split_tf32(v[2 * i + 1].z, h1.z, l1.z); tc::split_tf32(v[2 * i + 1].w, h1.w, l1.w);
+                            *reinterpret_cast<float4 *>(st + (2 * oct) * (TC_BLOCK_M * 16) + row * 16) = h0;
+                            *reinterpret_cast<float4 *>(st + (2 * oct + 1) * (TC_BLOCK_M * 16) + row * 16) = h1;
+                            uint4 xb, lb;
+                            xb.x = tc::bf16x2(v[2 * i].x, v[2 * i].y); xb.y = tc::bf16x2(v[2 * i].z, v[2 * i].w);
+                            xb.z = tc::bf16x2(v[2 * i + 1].x, v[2 * i + 1].y); xb.w = tc::bf16x2(v[2 * i + 1].z, v[2 * i + 1].w);
+                            lb.x = tc::bf16x2(l0.x, l0.y); lb.y = tc::bf16x2(l0.z, l0.w);
+                            lb.z = tc::bf16x2(l1.x, l1.y); lb.w = tc::bf16x2(l1.z, l1.w);
+                            *reinterpret_cast<uint4 *>(st + A_PART + oct * (TC_BLOCK_M * 16) + row * 16) = xb;
+                            *reinterpret_cast<uint4 *>(st + A_PART + A_PART / 2 + oct * (TC_BLOCK_M * 16) + row * 16) = lb;
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -229,6 +250,7 @@ linear_tc_kernel(const TcParams p) {
         // ================================ UMMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = tc::instr_desc(MODE == TC_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_BLOCK_M, (uint32_t)n_blk);
+            const uint32_t idesc16 = tc::instr_desc(tc::FMT_BF16, TC_BLOCK_M, (uint32_t)n_blk);      // MIXED: the correction products
             const uint32_t a_lbo = TC_BLOCK_M * 16, b_lbo = (uint32_t)n_blk * 16, sbo = 128;
             const bool swap = p.debug & 1;       // debug: exchange the roles of the two descriptor offsets
             auto desc = [&](uint32_t addr, uint32_t lbo) {
@@ -258,8 +280,20 @@ linear_tc_kernel(const TcParams p) {
                             tc::umma_tf32(d_tmem, a_lo, b_hi, idesc, first);     // small terms first
                             tc::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
                             tc::umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                        } else if (MODE == TC_MODE_MIXED) {
+                            tc::umma_tf32(d_tmem, desc(a0 + a_off, a_lbo), desc(b0 + b_off, b_lbo), idesc, first);      // x_hi * w_hi
                         } else {
                             tc::umma_f16(d_tmem, desc(a0 + a_off, a_lbo), desc(b0 + b_off, b_lbo), idesc, first);
+                        }
+                    }
+                    if (MODE == TC_MODE_MIXED) {
+                        // the two correction products on the bf16 copies, 16 channels per UMMA: x_lo * w + x * w_lo
+                        const uint32_t ax = a0 + A_PART, al = ax + A_PART / 2, bw = b0 + b_part, bl = bw + b_part / 2;
+#pragma unroll
+                        for (int j = 0; j < K_STEPS / 2; ++j) {
+                            const uint32_t a_off = (uint32_t)j * 2 * a_lbo, b_off = (uint32_t)j * 2 * b_lbo;
+                            tc::umma_f16(d_tmem, desc(al + a_off, a_lbo), desc(bw + b_off, b_lbo), idesc16, 1u);
+                            tc::umma_f16(d_tmem, desc(ax + a_off, a_lbo), desc(bl + b_off, b_lbo), idesc16, 1u);
                         }
                     }
                     tc::umma_commit(empty_bar + stage);             // stage reusable once these UMMAs retire
@@ -437,7 +471,7 @@ static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const vo
     using namespace ev2h;
     EV2H_REQUIRE(x && w_packed && bias && y, "ev2h_linear_relu_tc: null argument");
     EV2H_REQUIRE(M > 0 && Cin > 0 && Cout > 0, "ev2h_linear_relu_tc: bad sizes");
-    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3, "ev2h_linear_relu_tc: unknown mode %d", mode);
+    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3 || mode == TC_MODE_MIXED, "ev2h_linear_relu_tc: unknown mode %d", mode);
     EV2H_REQUIRE(ld_x % 4 == 0 && ld_x >= Cin, "ev2h_linear_relu_tc: ld_x=%d must be a multiple of 4 and >= Cin=%d", ld_x, Cin);
     EV2H_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "ev2h_linear_relu_tc: x and w_packed must be 16-byte aligned");
     EV2H_REQUIRE(pool_rows >= 0 && (pool_rows == 0 || M % pool_rows == 0), "ev2h_linear_relu_tc: M must be a multiple of pool_rows");
@@ -477,6 +511,9 @@ static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const vo
     if (mode == TC_MODE_BF16) {
         e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) linear_tc_kernel<TC_MODE_BF16><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);
+    } else if (mode == TC_MODE_MIXED) {
+        e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) linear_tc_kernel<TC_MODE_MIXED><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);
     } else {
         e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) linear_tc_kernel<TC_MODE_TF32X3><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);

@@ -52,6 +52,9 @@ _TF32X3_PURE = os.environ.get("EV2H_TF32X3_PURE", "0") == "1"
 _COMPACT = os.environ.get("EV2H_COMPACT", "1") != "0"
 # ... and over exact-duplicate points only once (event windows are sampled with replacement).
 _DEDUP = os.environ.get("EV2H_DEDUP", "1") != "0"
+# The per-layer tensor-core kernel (sa3, the decoder, sa2's per-point first layer) uses the same split products as the
+# fused kernel for "tf32x3"; EV2H_LINEAR_MIXED=0 keeps three tf32 products there.
+_LINEAR_MIXED = os.environ.get("EV2H_LINEAR_MIXED", "1") != "0"
 # Evaluate layer 1 per point (instead of per gathered row) also for narrow inputs; experiment switch.
 _PER_POINT_ALWAYS = os.environ.get("EV2H_PER_POINT", "0") == "1"
 
@@ -213,11 +216,20 @@ class _FoldedMLP:
         return hit[1]
 
 
+def _layer_mode(mode):
+    """arithmetic of the per-layer tensor-core kernel for the selected precision: fp32-level = tf32 hi*hi + two bf16
+    correction products (4 UMMA time units per 16 channels instead of the 6 of three tf32 products)"""
+    if mode == _capi.TC_TF32X3 and _LINEAR_MIXED and not _TF32X3_PURE:
+        return _capi.TC_TF32_BF16C
+    return mode
+
+
 def _mlp_rows(x, M, ld_x, layers, pool_rows, out, ld_out, out_col):
     """Run the folded MLP over M rows of x; the last layer max-pools runs of pool_rows rows
     into out[:, out_col : out_col + C_last]."""
     cur, ld = x, ld_x
     mode = {"tf32x3": _capi.TC_TF32X3, "bf16": _capi.TC_BF16}.get(_mlp_precision)
+    lmode = _layer_mode(mode)
     for j, L in enumerate(layers):
         last = j == len(layers) - 1
         cin, cout = L["cin"], L["cout"]
@@ -232,10 +244,10 @@ def _mlp_rows(x, M, ld_x, layers, pool_rows, out, ld_out, out_col):
         # the layer on the CUDA cores in exact fp32 (only fp3's first layer, 1536 channels, is that long).
         too_long = mode == _capi.TC_TF32X3 and cin > 1024
         if mode is not None and not too_long and _capi.tc_supported(cout, pool):
-            packed = L["packed"].get(mode)
+            packed = L["packed"].get(lmode)
             if packed is None:
-                packed = L["packed"][mode] = _capi.tc_pack(L["wt"], cin, cout, mode)
-            _capi.linear_relu_tc(cur, M, ld, cin, packed, L["bias"], cout, pool, y, ld_y, col, mode)
+                packed = L["packed"][lmode] = _capi.tc_pack(L["wt"], cin, cout, lmode)
+            _capi.linear_relu_tc(cur, M, ld, cin, packed, L["bias"], cout, pool, y, ld_y, col, lmode)
         else:
             _capi.linear_relu(cur, M, ld, cin, L["wt"], L["bias"], cout, pool, y, ld_y, col)
         cur, ld = y, ld_y
@@ -468,9 +480,10 @@ class PointNetSetAbstractionMsg(nn.Module):
             if mode == _capi.TC_TF32X3 and _capi.tc_supported(c1_total, 0):
                 # the wide per-point layer on the tensor cores (fp32-level accuracy); bf16 mode keeps it
                 # in exact fp32 so that only the two tensor-core layers carry bf16 rounding
-                if mode not in cat["packed"]:
-                    cat["packed"][mode] = _capi.tc_pack(cat["wt"], D + 3, c1_total, mode)
-                _capi.linear_tc_no_relu(x_pts, B * N, ld_pts, D + 3, cat["packed"][mode], cat["bias"], c1_total, P, c1_total, 0, mode)
+                lmode = _layer_mode(mode)
+                if lmode not in cat["packed"]:
+                    cat["packed"][lmode] = _capi.tc_pack(cat["wt"], D + 3, c1_total, lmode)
+                _capi.linear_tc_no_relu(x_pts, B * N, ld_pts, D + 3, cat["packed"][lmode], cat["bias"], c1_total, P, c1_total, 0, lmode)
             else:
                 _capi.linear_no_relu(x_pts, B * N, ld_pts, D + 3, cat["wt"], cat["bias"], c1_total, P, c1_total, 0)
             _capi.linear_no_relu(ctr4, B * S, 4, 3, cat["wt_xyz"], cat["zero_bias"], c1_total, C, c1_total, 0)
