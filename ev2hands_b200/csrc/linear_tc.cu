@@ -154,34 +154,48 @@ linear_tc_kernel(const TcParams p) {
         // warp-wide load covers 8 rows x 64 contiguous bytes (full 32-byte sectors).
         const int lw = warp - 5, grp = lw >> 2, wq = lw & 3;
         const int l8 = lane & 7, oct = lane >> 3;
-        int stage = 0;
-        uint32_t phase = 0, n = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // The group's NEXT chunk is loaded into registers before the current one is converted and stored, so
+        // the global-load latency of a stage overlaps the previous stage's wait / store / arrive.
+        const uint32_t my_tiles = (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+        const uint32_t total = my_tiles * (uint32_t)p.n_kc;                 // chunks this CTA walks
+        auto issue_loads = [&](uint32_t n, float4 (&v)[8]) {
+            const int64_t tile = blockIdx.x + (int64_t)(n / (uint32_t)p.n_kc) * gridDim.x;
+            const int kc = (int)(n % (uint32_t)p.n_kc);
             const int64_t m0 = (tile / p.n_blocks) * TC_BLOCK_M;
-            const int nb = (int)(tile % p.n_blocks);
-            for (int kc = 0; kc < p.n_kc; ++kc, ++n) {
+            if (MODE == TC_MODE_TF32X3) {                     // (MIXED uses the 8-channels-per-lane mapping below)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 32 * wq + (i >> 1) * 8 + l8;
+                    const int k = kc * TC_KC + 4 * (oct + 4 * (i & 1));
+                    v[i] = ((m0 + row) < p.M && k < p.ld_x)
+                               ? __ldg(reinterpret_cast<const float4 *>(p.x + (m0 + row) * (int64_t)p.ld_x + k))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = 32 * wq + i * 8 + l8;
+                    const int k = kc * TC_KC + 8 * oct;
+                    const float *src = p.x + (m0 + row) * (int64_t)p.ld_x + k;
+                    const bool ok = (m0 + row) < p.M;
+                    v[2 * i] = (ok && k < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[2 * i + 1] = (ok && k + 4 < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        float4 v[8];
+        if ((uint32_t)grp < total) issue_loads((uint32_t)grp, v);
+        for (uint32_t n = 0; n < total; ++n) {
+            {
                 if ((int)(n % TC_LOADER_GROUPS) == grp) {
-                    float4 v[8];
-                    if (MODE == TC_MODE_TF32X3) {                     // (MIXED uses the 8-channels-per-lane mapping below)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = 32 * wq + (i >> 1) * 8 + l8;
-                            const int k = kc * TC_KC + 4 * (oct + 4 * (i & 1));
-                            v[i] = ((m0 + row) < p.M && k < p.ld_x)
-                                       ? __ldg(reinterpret_cast<const float4 *>(p.x + (m0 + row) * (int64_t)p.ld_x + k))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int row = 32 * wq + i * 8 + l8;
-                            const int k = kc * TC_KC + 8 * oct;
-                            const float *src = p.x + (m0 + row) * (int64_t)p.ld_x + k;
-                            const bool ok = (m0 + row) < p.M;
-                            v[2 * i] = (ok && k < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            v[2 * i + 1] = (ok && k + 4 < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
+                    const int64_t tile = blockIdx.x + (int64_t)(n / (uint32_t)p.n_kc) * gridDim.x;
+                    const int kc = (int)(n % (uint32_t)p.n_kc);
+                    const int nb = (int)(tile % p.n_blocks);
+                    float4 vn[8];
+                    const bool has_next = n + TC_LOADER_GROUPS < total;
+                    if (has_next) issue_loads(n + TC_LOADER_GROUPS, vn);
                     tc::mbar_wait(empty_bar + stage, phase ^ 1);
                     uint8_t *st = ring + (size_t)stage * stage_bytes;
                     if (wq == 0 && lane == 0) {
@@ -238,6 +252,10 @@ linear_tc_kernel(const TcParams p) {
                     }
                     tc::fence_proxy_async();
                     tc::mbar_arrive(full_bar + stage);
+                    if (has_next) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = vn[i];
+                    }
                 } else {
                     // walk the other group's chunks too: a parity wait is only meaningful while the
                     // waiter is at most one phase ahead of the barrier
