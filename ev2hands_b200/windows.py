@@ -35,10 +35,14 @@ class EventWindowBuilder:
                 ``dataset[index : index + 2048]`` of erpc.py:173-174 does).
     """
 
-    def __init__(self, mode: str = "stream", n_events: int = 2048, width: int = SENSOR_W, height: int = SENSOR_H):
+    def __init__(self, mode: str = "stream", n_events: int = 2048, width: int = SENSOR_W, height: int = SENSOR_H,
+                 sampling: bool = True):
+        """``sampling`` mirrors ``Ev2HandSDataset(sampling=...)`` (erpc.py:106, :216-226): True draws all ``n_events``
+        points with replacement; False keeps every occupied pixel once and draws only the missing ``n_events - M``."""
         if mode not in _MODES:
             raise ValueError("mode must be 'stream' or 'erpc'")
         self.mode, self.n_events, self.width, self.height = mode, int(n_events), int(width), int(height)
+        self.sampling = bool(sampling)
         self.last_n_pixels = self.last_n_bad = None
 
     def aggregate(self, events: torch.Tensor, starts, counts):
@@ -61,7 +65,15 @@ class EventWindowBuilder:
         m = n_pixels.cpu().numpy()
         if (m < 1).any():
             raise RuntimeError("a window has no event inside the sensor")
-        idx = np.stack([np.random.choice(int(mb), self.n_events) for mb in m]).astype(np.int64)
+        if self.sampling:
+            idx = np.stack([np.random.choice(int(mb), self.n_events) for mb in m]).astype(np.int64)
+        else:
+            # erpc.py:219-226: the pixels themselves, then n_events - M of them again (a window with more occupied
+            # pixels than n_events would keep them all there; a fixed-size batch cannot)
+            if (m > self.n_events).any():
+                raise RuntimeError("sampling=False needs at most n_events occupied pixels per window")
+            idx = np.stack([np.concatenate([np.arange(int(mb)), np.random.choice(int(mb), self.n_events - int(mb))]) if mb < self.n_events
+                            else np.arange(int(mb)) for mb in m]).astype(np.int64)
         return torch.from_numpy(idx).pin_memory()
 
     def sample(self, records, n_pixels, n_bad, sample_idx=None) -> torch.Tensor:

@@ -150,6 +150,29 @@ def main():
         out.update({tag + "_events": rows, tag + "_starts": np.array(e_starts), tag + "_counts": np.array([2048] * 3),
                     tag + "_windows": np.stack(e_wins), tag + "_M": np.array(e_M), tag + "_idx": np.stack(e_idx)})
 
+    # ---- "erpcpad": the same class with sampling=False (erpc.py:219-226): every occupied pixel once, in time order,
+    # then n_events - M more drawn with replacement ------------------------------------------------------------------
+    rows = synth.make_raw_events(6000, seed=13, extra_columns=2, t0=0.0, duration=1.2e7, unique_times=True)
+    rows[:, 5] = np.random.RandomState(2).randint(0, 4, size=rows.shape[0])
+    ds = object.__new__(erpc_mod.Ev2HandSDataset)
+    ds.dataset = rows
+    ds.annotations = {0: {'left': dict(hand), 'right': dict(hand)}}
+    ds.augment = False
+    ds.sampling = False
+    ds.demo = False
+    np.random.seed(8)
+    p_starts, p_wins, p_M, p_idx = [10, 2500], [], [], []
+    for s in p_starts:
+        n0 = len(rec.calls)
+        item = ds[s]
+        assert len(rec.calls) == n0 + 1
+        m, extra = rec.calls[-1]
+        p_wins.append(item["events"].numpy())
+        p_M.append(m)
+        p_idx.append(np.concatenate([np.arange(m), extra]))
+    out.update({"erpcpad_events": rows, "erpcpad_starts": np.array(p_starts), "erpcpad_counts": np.array([2048] * 2),
+                "erpcpad_windows": np.stack(p_wins), "erpcpad_M": np.array(p_M), "erpcpad_idx": np.stack(p_idx)})
+
     np.random.choice = rec.orig
     path = os.path.join(HERE, "windows.npz")
     np.savez_compressed(path, **out)

@@ -694,7 +694,7 @@ def _window_case(golden, case):
     return (g[case + "_events"], g[case + "_starts"], g[case + "_counts"], g[case + "_idx"], g[case + "_windows"], g[case + "_M"])
 
 
-@pytest.mark.parametrize("case,mode", [("stream", "stream"), ("erpc", "erpc"), ("erpct", "erpc")])
+@pytest.mark.parametrize("case,mode", [("stream", "stream"), ("erpc", "erpc"), ("erpct", "erpc"), ("erpcpad", "erpc")])
 def test_event_windows_golden(golden, case, mode):
     """ev2h_window_aggregate_f64 + ev2h_window_sample_f32 against what the reference's own dataset classes
     produced from the same raw events and the same draw: bit for bit ("erpct": where equal mean times leave
@@ -724,6 +724,12 @@ def test_event_windows_draw_like_the_reference(golden):
     ev, starts, counts, idx, want, M = _window_case(golden, "stream")
     wb = e2h.EventWindowBuilder("stream")
     np.random.seed(5)                     # the seed tests/golden/make_window_golden.py used
+    got = wb(torch.from_numpy(ev).to(DEV), starts, counts)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    # sampling=False (erpc.py:219-226): every pixel once, then the missing n_events - M drawn
+    ev, starts, counts, idx, want, M = _window_case(golden, "erpcpad")
+    wb = e2h.EventWindowBuilder("erpc", sampling=False)
+    np.random.seed(8)
     got = wb(torch.from_numpy(ev).to(DEV), starts, counts)
     assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
 

@@ -150,7 +150,7 @@ def _untied_columns(rec, idx):
     return ~np.isin(tt, u[c > 1])[idx]
 
 
-@pytest.mark.parametrize("case,mode", [("stream", "stream"), ("erpc", "erpc"), ("erpct", "erpc")])
+@pytest.mark.parametrize("case,mode", [("stream", "stream"), ("erpc", "erpc"), ("erpct", "erpc"), ("erpcpad", "erpc")])
 def test_window_oracle_matches_reference(golden, case, mode):
     """oracle/window_oracle.py against outputs of the reference's own __getitem__ methods
     (tests/golden/make_window_golden.py): bit for bit, except where equal mean times leave the reference's
