@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t orderable(float f) {
 }
 
 template <bool ERPC>
-__global__ void __launch_bounds__(WIN_THREADS, 1)
+__global__ void __launch_bounds__(WIN_THREADS, 2)      // 32 registers: two windows per SM (ncu: the erpc instance held one with 48)
 window_aggregate_kernel(const double *__restrict__ events, int64_t row_stride, const int64_t *__restrict__ win_start,
                         const int32_t *__restrict__ win_count, int max_count, int n_sort, int width, int height,
                         float *__restrict__ records, int32_t *__restrict__ n_pixels, int32_t *__restrict__ n_bad) {
