@@ -28,6 +28,27 @@ def shard(tensors, rank: int, world: int):
     return tuple(t[lo:hi] for t in tensors)
 
 
+def shard_windows(starts, counts, rank: int, world: int):
+    """Shard a batch of event windows (row ranges of one raw event table, ``EventWindowBuilder``'s input) over ranks.
+
+    -> ``(row_lo, row_hi, local_starts, local_counts, (lo, hi))``: the rank's contiguous share ``[lo, hi)`` of the
+    windows, the slice ``events[row_lo:row_hi]`` of the table it has to hold (windows may overlap, so slices of
+    neighbouring ranks may too) and the starts rebased to that slice.  Like the FPS start indices, the per-window
+    point draws are made for the global batch in batch order and sharded with the same bounds, so the union of the
+    ranks' windows equals the unsharded batch.  No collective."""
+    import numpy as np
+    starts = np.asarray(starts, dtype=np.int64)
+    counts = np.asarray(counts, dtype=np.int64)
+    if starts.shape != counts.shape or starts.ndim != 1:
+        raise ValueError("starts and counts must be equally long 1-d sequences")
+    lo, hi = shard_bounds(starts.shape[0], rank, world)
+    if hi == lo:
+        return 0, 0, starts[:0], counts[:0].astype(np.int32), (lo, hi)
+    s, c = starts[lo:hi], counts[lo:hi]
+    row_lo, row_hi = int(s.min()), int((s + c).max())
+    return row_lo, row_hi, s - row_lo, c.astype(np.int32), (lo, hi)
+
+
 def max_over_ranks(values, device=None) -> list:
     """Element-wise maximum of a list of floats over all ranks (identity without a process group)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

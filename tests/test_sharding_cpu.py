@@ -75,3 +75,29 @@ def test_two_rank_sharding_matches_unsharded(tmp_path):
     whole = c_oracle.fps(xyz, S, start)
     parts = np.concatenate([np.load(os.path.join(str(tmp_path), "fps_%d.npy" % r)) for r in range(world)])
     assert np.array_equal(whole, parts)
+
+
+def test_window_shards_reproduce_the_unsharded_batch():
+    """Event windows shard like the encoder batch: every rank holds only its slice of the raw event
+    table, the draws are made for the global batch and sliced with the same bounds; checked with the CPU oracle."""
+    from oracle import window_oracle as wo
+    ev = synth.make_raw_events(4000, seed=21)
+    starts = np.array([0, 300, 900, 1500, 1501, 2500, 1900])        # overlapping, not sorted by start
+    counts = np.array([800, 700, 600, 900, 10, 1500, 64])
+    rs = np.random.RandomState(3)
+    recs = [wo.aggregate(ev[s:s + c], "stream") for s, c in zip(starts, counts)]
+    idx = np.stack([rs.randint(0, r.shape[0], size=128) for r in recs])
+    whole = wo.build_windows(ev, starts, counts, idx, "stream")
+    for world in (1, 2, 3, 8):
+        parts = []
+        for rank in range(world):
+            row_lo, row_hi, ls, lc, (lo, hi) = sharding.shard_windows(starts, counts, rank, world)
+            if hi == lo:
+                assert row_hi == row_lo == 0 and len(ls) == 0
+                continue
+            local = ev[row_lo:row_hi]                                  # what this rank uploads
+            assert (ls >= 0).all() and (ls + lc <= local.shape[0]).all() and lc.dtype == np.int32
+            parts.append(wo.build_windows(local, ls, lc, idx[lo:hi], "stream"))
+        assert np.array_equal(np.concatenate(parts), whole, equal_nan=True)
+    with pytest.raises(ValueError):
+        sharding.shard_windows([0, 1], [5], 0, 1)
