@@ -794,3 +794,55 @@ def test_event_windows_feed_the_encoder(golden):
         a = enc(wins, fps_starts=(s1, s2))
         b = enc(dev(want), fps_starts=(s1, s2))
     assert torch.equal(a, b)
+
+
+def test_event_windows_sharded_equal_the_whole_batch():
+    """sharding.shard_windows: every rank builds its windows from its own slice of the event table; the union is
+    bit-identical to the unsharded batch (the draws are made for the global batch and sliced with the windows)."""
+    from ev2hands_b200 import sharding
+    ev = synth.make_raw_events(9000, seed=31)
+    starts = np.array([0, 300, 900, 1500, 1501, 2500, 1900, 6000, 6100])
+    counts = np.array([2048, 700, 2600, 900, 10, 1500, 64, 2999, 2048])
+    wb = e2h.EventWindowBuilder("stream", n_events=512)
+    rec, n_pix, n_bad = wb.aggregate(torch.from_numpy(ev).to(DEV), starts, counts)
+    m = n_pix.cpu().numpy()
+    idx = np.stack([np.random.RandomState(b).randint(0, m[b], size=512) for b in range(len(m))])
+    whole = wb.sample(rec, n_pix, n_bad, torch.from_numpy(idx)).cpu().numpy()
+    for world in (2, 4):
+        parts = []
+        for rank in range(world):
+            row_lo, row_hi, ls, lc, (lo, hi) = sharding.shard_windows(starts, counts, rank, world)
+            local = torch.from_numpy(ev[row_lo:row_hi]).to(DEV)            # the only rows this rank uploads
+            parts.append(wb(local, ls, lc, sample_idx=torch.from_numpy(idx[lo:hi]), check=True).cpu().numpy())
+        assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_event_windows_full_size_properties_batch1024():
+    """config-3-sized batch (1024 half-overlapping windows of 2048 events): size-independent properties instead
+    of an oracle run - pixel counts against numpy, every output point is one of its window's pixels with that
+    pixel's event counts, x / y / t normalised into [-1, 1] with t touching both ends."""
+    B, n, N = 1024, 2048, 2048
+    ev = synth.make_raw_events(B * n // 2 + n, seed=41, duration=2.0e3 * (B // 2 + 1))
+    starts, counts = np.arange(B) * (n // 2), np.full(B, n)
+    wb = e2h.EventWindowBuilder("stream", n_events=N)
+    np.random.seed(123)
+    out = wb(torch.from_numpy(ev).to(DEV), starts, counts, check=True).cpu().numpy()
+    m = wb.last_n_pixels.cpu().numpy()
+    pix = (ev[:, 1].astype(np.int64) * 346 + ev[:, 0].astype(np.int64))
+    assert out.shape == (B, 5, N) and int(wb.last_n_bad.sum()) == 0
+    assert np.abs(out[:, :3]).max() <= 1.0 and (out[:, 2].min(1) == -1.0).all() and (out[:, 2].max(1) == 1.0).all()
+    for b in range(0, B, 37):
+        w_pix = pix[starts[b]:starts[b] + n]
+        uniq, cnt = np.unique(w_pix, return_counts=True)
+        assert m[b] == uniq.size
+        # invert the normalisation: 2 * (v / size) - 1 in float32
+        gx = (2 * (np.arange(346, dtype=np.float32) / np.float32(346)) - 1).astype(np.float32)
+        gy = (2 * (np.arange(260, dtype=np.float32) / np.float32(260)) - 1).astype(np.float32)
+        xi, yi = np.searchsorted(gx, out[b, 0]), np.searchsorted(gy, out[b, 1])
+        assert np.array_equal(gx[xi], out[b, 0]) and np.array_equal(gy[yi], out[b, 1])
+        got_pix = yi.astype(np.int64) * 346 + xi
+        pos = np.searchsorted(uniq, got_pix)
+        assert np.array_equal(uniq[pos], got_pix)                        # a pixel of this window
+        assert np.array_equal(out[b, 3] + out[b, 4], cnt[pos].astype(np.float32))   # with that pixel's event count
+    for b in range(B):
+        assert m[b] == np.unique(pix[starts[b]:starts[b] + n]).size
