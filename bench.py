@@ -506,6 +506,21 @@ def run_ours(args):
             "draw": "host: pixel counts read back, np.random.choice per window like the reference (erpc.py:217)",
             "device_only": {"value": windows / (raw_dev_ms / 1e3), "unit": "windows/s", "ms_per_step": raw_dev_ms / args.steps,
                             "draw": "indices resident on the device"}}
+    if world == 1 and not args.no_cpu_baseline and "from_raw_events" in line:
+        # the reference's numpy recipe for the same windows on one host core (oracle/window_oracle.py, pinned bit for
+        # bit to the reference's dataset classes): np.add.at grids, nonzero, draw, pc_normalize
+        try:
+            import numpy as _np
+            from oracle import window_oracle as _wo
+            raw_h = synth.make_raw_events(16 * 1024 + 2048, seed=77, duration=2.0e3 * 17)
+            t0 = time.perf_counter()
+            for w in range(16):
+                r = _wo.aggregate(raw_h[w * 1024:w * 1024 + 2048], "stream")
+                _wo.sample_normalize(r, _np.random.RandomState(w).randint(0, r.shape[0], size=args.points))
+            line["from_raw_events"]["cpu_window_recipe"] = {"value": 16 / (time.perf_counter() - t0), "unit": "windows/s", "cores": 1,
+                                                            "kind": "port", "sample": "16 windows of 2048 raw events, window construction only"}
+        except Exception as exc:      # noqa: BLE001
+            print("bench.py: CPU window recipe failed (%s)" % exc, file=sys.stderr)
     if world == 1 and not args.no_cpu_baseline:
         wps, threads, times = time_cpu_oracle(4, 3, 1)
         line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": threads, "kind": "port",
