@@ -133,3 +133,32 @@ def test_raw_event_stream_is_deterministic_and_sensor_shaped():
     assert set(np.unique(a[:, 3])) <= {0.0, 1.0}
     u = synth.make_raw_events(2000, seed=1, duration=1.0e5, unique_times=True)
     assert np.unique(u[:, 2]).size == 2000
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/ev2h.h must be consumable from C (the boundary is a C ABI, not a C++ or Python one): a C99 program
+    that takes the address of every declared function links against libev2h.so, reports the version and gets a
+    status + message (not a crash) for a bad call."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    names = [n for n in _capi.declared_symbols()]
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "ev2h.h"\n'
+        "int main(void) {\n"
+        "    typedef void (*fn_t)(void);\n"
+        "    fn_t fns[] = {" + ", ".join("(fn_t)%s" % n for n in names) + "};\n"
+        "    size_t i, n = sizeof(fns) / sizeof(fns[0]);\n"
+        "    for (i = 0; i < n; ++i) if (!fns[i]) return 2;\n"
+        "    if (ev2h_fps_f32(NULL, 0, 0, 0, NULL, 1, 1, 1, NULL, NULL, NULL, NULL) != EV2H_ERR_BAD_ARGUMENT) return 3;\n"
+        '    if (!strstr(ev2h_last_error(), "null")) return 4;\n'
+        '    printf("%d %d\\n", ev2h_version(), (int)n);\n'
+        "    return 0;\n}\n")
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-l:libev2h.so", "-Wl,-rpath," + lib_dir])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[0]) >= 100 and int(out[1]) == len(names)
