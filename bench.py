@@ -389,8 +389,9 @@ def run_ours(args):
     # window are drawn on the host from numpy's generator exactly like the reference (one read-back of the pixel
     # counts per batch, np.random.choice per window), so this line includes that host work.
     raw_ms = raw_dev_ms = 0.0
-    if args.from_raw_events and args.points > 4096:
-        args.from_raw_events = False          # a 2048-event window has fewer occupied pixels than config 5 wants points
+    if args.from_raw_events and (args.points > 4096 or world > 1):
+        # a 2048-event window has fewer occupied pixels than config 5 wants points; the scaling runs time the headline only
+        args.from_raw_events = False
     if args.from_raw_events:
         try:
             import numpy as _np
