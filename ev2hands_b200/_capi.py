@@ -181,10 +181,21 @@ def fps(xyz: torch.Tensor, strides, start: torch.Tensor, B: int, N: int, S: int,
     """-> (idx int32 [B,S], centres_rows [B,S,3] | None, centres_cf [B,3,S] | None)"""
     _need_cuda_f32(xyz, "xyz")
     dev = xyz.device
+    if tuple(start.shape) != (B,):
+        raise RuntimeError("FPS start indices must have shape [%d], got %s" % (B, tuple(start.shape)))
     if not start.is_cuda:
-        # host-drawn start indices (the reference's torch.randint on the CPU generator): upload from pinned memory
-        # without blocking, so the host keeps running ahead of the device instead of syncing with it twice per step
-        start = start.to(dtype=torch.int64).contiguous().pin_memory().to(dev, non_blocking=True)
+        # host-drawn start indices (the reference's torch.randint on the CPU generator).  Inside a CUDA-graph capture
+        # an upload from a temporary pinned block would be baked into the graph and replayed from recycled memory
+        # (and the draw itself frozen), so a captured forward must be given device-resident start tensors.
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("FPS start indices are host tensors (or were drawn on the host) during CUDA-graph capture: "
+                               "pass device-resident fps_start / fps_starts tensors and refill them between replays")
+        start = start.to(dtype=torch.int64).contiguous()
+        if B > 0 and (int(start.min()) < 0 or int(start.max()) >= N):     # the reference would raise an IndexError (:77)
+            raise IndexError("FPS start index out of range [0, %d)" % N)
+        # upload from pinned memory without blocking, so the host keeps running ahead of the device instead of
+        # syncing with it twice per step
+        start = start.pin_memory().to(dev, non_blocking=True)
     else:
         start = start.to(device=dev, dtype=torch.int64).contiguous()
     idx = torch.empty((B, S), dtype=torch.int32, device=dev)

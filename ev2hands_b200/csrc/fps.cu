@@ -49,7 +49,10 @@ fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
         sx[i] = px; sy[i] = py; sz[i] = pz;
         if (XYZ_IN_REGS) { x[j] = px; y[j] = py; z[j] = pz; }
     }
-    int cur = (int)start[b];
+    // device-resident start indices cannot be validated on the host without a sync: clamp (the host binding
+    // range-checks host tensors and raises like the reference's indexing would, pointnet2_utils.py:77)
+    const int64_t st0 = start[b];
+    int cur = st0 < 0 ? 0 : (st0 >= N ? N - 1 : (int)st0);
     __syncthreads();
 
     for (int s = 0; s < S; ++s) {

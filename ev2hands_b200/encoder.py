@@ -7,6 +7,7 @@ metric ("encoder event-windows/s") is measured on.
 from __future__ import annotations
 
 import os
+import threading
 
 import torch
 import torch.nn as nn
@@ -20,10 +21,16 @@ _GEOM_STREAM = os.environ.get("EV2H_GEOM_STREAM", "1") != "0"
 _side_streams = {}
 
 
+_side_lock = threading.Lock()
+
+
 def _side_stream(device):
-    st = _side_streams.get(device)
-    if st is None:
-        st = _side_streams[device] = torch.cuda.Stream(device=device)
+    """one side stream per (device, host thread): nn.DataParallel runs a replica per thread"""
+    key = (device, threading.get_ident())
+    with _side_lock:
+        st = _side_streams.get(key)
+        if st is None:
+            st = _side_streams[key] = torch.cuda.Stream(device=device)
     return st
 
 
@@ -139,6 +146,12 @@ class GraphedForward:
 
     def __init__(self, fn, *example_inputs, warmup: int = 3):
         self.fn = fn
+        for i, x in enumerate(example_inputs):
+            if not (torch.is_tensor(x) and x.is_cuda):
+                # a host tensor (e.g. FPS start indices) would be uploaded inside the capture from a temporary pinned
+                # block and every replay would re-read that recycled memory: all inputs are static device buffers
+                raise RuntimeError("GraphedForward: input %d is not a CUDA tensor; every input (the windows AND the FPS "
+                                   "start indices) must be device resident - they are refilled by copy before each replay" % i)
         self.static_in = [x.clone() for x in example_inputs]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

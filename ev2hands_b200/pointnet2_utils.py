@@ -24,6 +24,7 @@ query, grouping (with scatter-add backward) and max-pool (with arg-max backward)
 from __future__ import annotations
 
 import os
+import threading
 import weakref
 
 import torch
@@ -83,12 +84,16 @@ def _pad4(c: int) -> int:
 # free functions (same signatures as the reference; tensors are [B, N, C] point-major)
 # --------------------------------------------------------------------------------------
 def square_distance(src, dst):
-    """[B,N,3],[B,M,3] -> [B,N,M]; bit-identical to the reference's expanded form."""
+    """[B,N,3],[B,M,3] -> [B,N,M]; bit-identical to the reference's expanded form (3 coordinates only)."""
+    if src.dim() != 3 or dst.dim() != 3 or src.shape[-1] != 3 or dst.shape[-1] != 3 or src.shape[0] != dst.shape[0]:
+        raise RuntimeError("square_distance expects [B,N,3] and [B,M,3], got %s and %s" % (tuple(src.shape), tuple(dst.shape)))
     return _capi.square_distance(src, dst)
 
 
 def index_points(points, idx):
     """points [B,N,C], idx [B,...] -> [B,...,C]."""
+    if points.dim() != 3 or idx.dim() < 2 or idx.shape[0] != points.shape[0]:
+        raise RuntimeError("index_points expects points [B,N,C] and idx [B,...], got %s and %s" % (tuple(points.shape), tuple(idx.shape)))
     return _capi.index_rows(points, idx)
 
 
@@ -181,6 +186,11 @@ class _GroupMax(torch.autograd.Function):
 # --------------------------------------------------------------------------------------
 # folded-weight cache for the inference path
 # --------------------------------------------------------------------------------------
+# nn.DataParallel (train.py:68) drives one Python thread per replica through the same module objects' caches:
+# every cache below is keyed by device and only replaced under this lock (entries are immutable once published).
+_CACHE_LOCK = threading.RLock()
+
+
 class _FoldedMLP:
     """Per-device folded (conv bias + eval BatchNorm) weights of one conv/bn stack.
 
@@ -190,6 +200,7 @@ class _FoldedMLP:
 
     def __init__(self):
         self.by_device = {}     # device -> (key, layers); replicas on other GPUs keep their own entry
+        self.generation = 0     # bumped at every refold: caches derived from the folded tensors key on it, not on addresses
 
     @staticmethod
     def _key(convs, bns):
@@ -202,18 +213,21 @@ class _FoldedMLP:
     def get(self, convs, bns, in_perm=None):
         key = self._key(convs, bns)
         dev = convs[0].weight.device
-        hit = self.by_device.get(dev)
-        if hit is None or hit[0] != key:
+        with _CACHE_LOCK:
+            hit = self.by_device.get(dev)
+            if hit is not None and hit[0] == key:
+                return hit[1]
+            self.generation += 1
             layers = []
             for j, (conv, bn) in enumerate(zip(convs, bns)):
                 w = conv.weight.detach().reshape(conv.out_channels, conv.in_channels)
                 if j == 0 and in_perm is not None:
                     w = w[:, in_perm if torch.is_tensor(in_perm) else torch.tensor(list(in_perm), device=w.device)]
                 wt, bias = _capi.fold_conv_bn(w, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-                layers.append({"wt": wt, "bias": bias, "cin": conv.in_channels, "cout": conv.out_channels, "packed": {}})
+                layers.append({"wt": wt, "bias": bias, "cin": conv.in_channels, "cout": conv.out_channels, "packed": {},
+                               "gen": (id(self), self.generation)})
             self.by_device[dev] = (key, layers)
             return layers
-        return hit[1]
 
 
 def _layer_mode(mode):
@@ -256,6 +270,11 @@ def _mlp_rows(x, M, ld_x, layers, pool_rows, out, ld_out, out_col):
 def _check_inputs(xyz, points):
     if xyz.dim() != 3 or xyz.shape[1] != 3:
         raise RuntimeError("xyz must be [B, 3, N], got %s" % (tuple(xyz.shape),))
+    if xyz.requires_grad and torch.is_grad_enabled():
+        # the reference differentiates through grouped_xyz - new_xyz; the model never asks for it and the
+        # gather kernels return no coordinate gradient, so say so instead of returning zeros
+        raise RuntimeError("ev2hands_b200 does not differentiate with respect to xyz (xyz.requires_grad is set); "
+                           "detach the coordinates or keep the reference module for that use")
     if not xyz.is_cuda:
         raise RuntimeError("ev2hands_b200 runs on CUDA devices only (xyz is on %s); there is no CPU path" % xyz.device)
     if xyz.dtype != torch.float32 or (points is not None and points.dtype != torch.float32):
@@ -313,12 +332,23 @@ class _LevelRows:
                 and (xyz.data_ptr(), xyz._version) == self._xyz_key and tuple(xyz.shape) == (self.B, 3, self.S))
 
 
+# How often a layer found the previous layer's rows riding on its channel-first input ("hit"), found a record that no
+# longer matches the tensor ("stale": modified in place since; the layer transposes the tensor like for any input) or
+# no record at all ("none": a fresh tensor).  bench.py reports the counts so that a lost shortcut shows up.
+ROW_SHORTCUT = {"hit": 0, "stale": 0, "none": 0}
+
+
 def _level_rows_of(xyz, points):
     """The _LevelRows record behind ``points`` (itself, or the one riding on a channel-first tensor), or None."""
     if isinstance(points, _LevelRows):
         return points
     rec = getattr(points, "_ev2h_rows", None)
-    return rec if rec is not None and rec.matches(xyz, points) else None
+    if rec is None:
+        ROW_SHORTCUT["none"] += 1
+        return None
+    ok = rec.matches(xyz, points)
+    ROW_SHORTCUT["hit" if ok else "stale"] += 1
+    return rec if ok else None
 
 
 def _wants_autograd(module, *tensors):
@@ -351,6 +381,7 @@ class PointNetSetAbstractionMsg(nn.Module):
             self.conv_blocks.append(convs)
             self.bn_blocks.append(bns)
         self._folded = [_FoldedMLP() for _ in mlp_list]
+        self._first_cat = {}      # device -> concatenated first-layer weights of the fused scales (per-point mode)
 
     # ---- shared front end: FPS + ball query -----------------------------------------
     def _pts8(self, xyz, points, strides):
@@ -463,8 +494,11 @@ class PointNetSetAbstractionMsg(nn.Module):
             ctr4[:, :3] = centres_rows.reshape(B * S, 3)
             # every fused scale's first layer in ONE GEMM: the folded weights side by side (same input rows)
             firsts = [layers[0] for layers, f in zip(all_layers, fused) if f]
-            key = tuple(L0["wt"].data_ptr() for L0 in firsts)
-            cat = getattr(self, "_first_cat", None)
+            # keyed on the refold generation of every source stack (an address can be handed out again by the caching
+            # allocator after a refold) and kept per device in an object nn.DataParallel replicas share
+            key = tuple(L0["gen"] for L0 in firsts)
+            with _CACHE_LOCK:
+                cat = self._first_cat.get(xyz.device)
             if cat is None or cat["key"] != key:
                 rows = firsts[0]["wt"].shape[0]
                 wt = torch.zeros((rows, (c1_total + 127) // 128 * 128), dtype=torch.float32, device=xyz.device)
@@ -476,7 +510,9 @@ class PointNetSetAbstractionMsg(nn.Module):
                     c += L0["cout"]
                 wx = torch.zeros((16, wt.shape[1]), dtype=torch.float32, device=xyz.device)
                 wx[:3] = wt[D:D + 3]
-                cat = self._first_cat = {"key": key, "wt": wt, "bias": bias, "wt_xyz": wx, "zero_bias": torch.zeros_like(bias), "packed": {}}
+                cat = {"key": key, "wt": wt, "bias": bias, "wt_xyz": wx, "zero_bias": torch.zeros_like(bias), "packed": {}}
+                with _CACHE_LOCK:
+                    self._first_cat[xyz.device] = cat
             if mode == _capi.TC_TF32X3 and _capi.tc_supported(c1_total, 0):
                 # the wide per-point layer on the tensor cores (fp32-level accuracy); bf16 mode keeps it
                 # in exact fp32 so that only the two tensor-core layers carry bf16 rounding

@@ -197,6 +197,50 @@ def main():
                         d0_every16=d0[:, :, ::16].numpy(), weight_seeds=np.array([300, 301, 302]),
                         feature_seed=np.array(55), **nn_tabs)
 
+    # ---- 6. sample_and_group / sampled (group_all=False) PointNetSetAbstraction (:110-138, :161-202) -----
+    # not reached by the model; pinned for API completeness
+    ev6 = synth.make_windows(2, 512, seed=1240)
+    xyz6 = torch.from_numpy(ev6[:, :3].transpose(0, 2, 1).copy())
+    pts6 = torch.from_numpy(ev6.transpose(0, 2, 1).copy())                  # [B,N,5]
+    s6 = seeded_starts(21, 512, 2)
+    g_xyz, g_points, g_grouped, g_fps = pu.sample_and_group(48, 0.3, 16, xyz6, pts6, returnfps=True)
+    s6b = seeded_starts(22, 512, 2)
+    g_xyz_np, g_points_np = pu.sample_and_group(48, 0.3, 16, xyz6, None)
+    sa_s = pu.PointNetSetAbstraction(npoint=48, radius=0.3, nsample=16, in_channel=5 + 3, mlp=[16, 32], group_all=False).eval()
+    st6 = synth.random_sa_state("mlp_convs.{j}", "mlp_bns.{j}", [[16, 32]], [8], seed=400)
+    sa_s.load_state_dict(to_t(st6), strict=True)
+    s6c = seeded_starts(23, 512, 2)
+    with torch.no_grad():
+        m_xyz, m_points = sa_s(torch.from_numpy(ev6[:, :3].copy()), torch.from_numpy(ev6))
+    np.savez_compressed(os.path.join(HERE, "sampled.npz"), events=ev6, start=s6.numpy(), start_nopoints=s6b.numpy(),
+                        start_module=s6c.numpy(), new_xyz=g_xyz.numpy(), new_points=g_points.numpy(),
+                        grouped_xyz=g_grouped.numpy(), fps_idx=small_idx(g_fps.numpy()),
+                        new_points_nopoints=g_points_np.numpy(), module_xyz=m_xyz.numpy(), module_points=m_points.numpy(),
+                        weight_seed=np.array(400))
+
+    # ---- 7. training step of the sa2-shaped module at the MODEL's shapes (D=320, K=64/128): forward in train mode
+    # (batch-statistics BatchNorm), backward of a fixed linear loss; reference autograd on CPU --------------------
+    torch.manual_seed(0)
+    sa_t = pu.PointNetSetAbstractionMsg(128, [0.4, 0.8], [64, 128], 320, [[128, 128, 256], [128, 196, 256]]).train()
+    st7 = synth.random_state_for(synth.ENCODER_SPECS["sa2"], seed=500)
+    sa_t.load_state_dict(to_t(st7), strict=True)
+    rs7 = np.random.RandomState(501)
+    ev7 = synth.make_windows(2, 512, seed=1250)
+    xyz7 = torch.from_numpy(ev7[:, :3].copy())
+    feats7 = torch.from_numpy(rs7.randn(2, 320, 512).astype(np.float32)).requires_grad_(True)
+    s7 = seeded_starts(31, 512, 2)
+    t_xyz, t_out = sa_t(xyz7, feats7)
+    lw = torch.from_numpy(np.linspace(0.5, 1.5, t_out.numel(), dtype=np.float32)).view_as(t_out)
+    (t_out * lw).sum().backward()
+    tr = {"events": ev7, "feats_seed": np.array(501), "start": s7.numpy(), "weight_seed": np.array(500),
+          "new_xyz": t_xyz.detach().numpy(), "out_every4": t_out.detach().numpy()[:, ::4, ::4],
+          "grad_feats_every8": feats7.grad.numpy()[:, :, ::8],
+          "running_mean_0_0": sa_t.bn_blocks[0][0].running_mean.numpy(), "running_var_1_2": sa_t.bn_blocks[1][2].running_var.numpy()}
+    for n, p in sa_t.named_parameters():
+        if n in ("conv_blocks.0.0.weight", "conv_blocks.1.1.weight", "conv_blocks.1.2.bias", "bn_blocks.0.1.weight", "bn_blocks.1.0.bias"):
+            tr["grad." + n] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "train_sa2.npz"), **tr)
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

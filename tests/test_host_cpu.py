@@ -162,3 +162,56 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                            "-L", lib_dir, "-l:libev2h.so", "-Wl,-rpath," + lib_dir])
     out = subprocess.check_output([str(exe)], text=True).split()
     assert int(out[0]) >= 100 and int(out[1]) == len(names)
+
+
+REF_MODEL_DIR = "/root/reference/src/Ev2Hands/model"
+
+
+def _load_tehnet(pkg_name, pointnet2_module=None):
+    """TEHNet.py of the reference, loaded by path under a stand-in package (model/__init__ imports trimesh / manopth,
+    absent here).  ``pointnet2_module`` given = the one-line change of INTEGRATION.md: TEHNet.py:6's
+    ``from .pointnet2_utils import ...`` resolves to that module instead of the reference's file."""
+    import importlib.util
+    import sys
+    import types
+    pkg = types.ModuleType(pkg_name)
+    pkg.__path__ = [REF_MODEL_DIR]
+    sys.modules[pkg_name] = pkg
+    if pointnet2_module is not None:
+        sys.modules[pkg_name + ".pointnet2_utils"] = pointnet2_module
+    spec = importlib.util.spec_from_file_location(pkg_name + ".TEHNet", os.path.join(REF_MODEL_DIR, "TEHNet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[pkg_name + ".TEHNet"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MODEL_DIR), reason="the reference tree exists in the build container only")
+def test_one_line_change_builds_the_real_tehnet_and_loads_its_checkpoint(monkeypatch):
+    """SURVEY 7 step 6 / INTEGRATION.md: the UNMODIFIED reference TEHNet.py with line 6 pointed at ev2hands_b200
+    constructs (TEHNet.__init__ :115-166, both MANORegressors :43-44 included), has the stock net's state_dict
+    names and shapes, and loads the stock net's state_dict with strict=True (demo.py:84)."""
+    monkeypatch.setenv("ERPC", "1")
+    from ev2hands_b200 import pointnet2_utils as ours
+    stock = _load_tehnet("refmodel_stock").TEHNet(n_pose_params=6)
+    patched_mod = _load_tehnet("refmodel_patched", ours)
+    patched = patched_mod.TEHNet(n_pose_params=6)
+    for name in ("sa1", "sa2"):
+        assert isinstance(getattr(patched, name), ours.PointNetSetAbstractionMsg)
+        assert not isinstance(getattr(stock, name), ours.PointNetSetAbstractionMsg)
+    assert isinstance(patched.sa3, ours.PointNetSetAbstraction) and isinstance(patched.fp1, ours.PointNetFeaturePropagation)
+    assert isinstance(patched.left_mano_regressor.sa1, ours.PointNetSetAbstractionMsg)
+    assert isinstance(patched.right_mano_regressor.sa2, ours.PointNetSetAbstraction)
+    sd_stock, sd_new = stock.state_dict(), patched.state_dict()
+    assert list(sd_stock.keys()) == list(sd_new.keys())
+    assert {k: tuple(v.shape) for k, v in sd_stock.items()} == {k: tuple(v.shape) for k, v in sd_new.items()}
+    assert {k: v.dtype for k, v in sd_stock.items()} == {k: v.dtype for k, v in sd_new.items()}
+    res = patched.load_state_dict(sd_stock, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in patched.state_dict().items():
+        assert torch.equal(v, sd_stock[k]), k
+    # and back: a checkpoint written by the patched net loads into the stock one
+    stock.load_state_dict(patched.state_dict(), strict=True)
+    # the patched net refuses to run on the CPU instead of silently falling back
+    with pytest.raises(RuntimeError, match="CUDA"):
+        patched.eval()(torch.zeros(1, 5, 2048), {"left": None, "right": None})
