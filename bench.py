@@ -116,12 +116,12 @@ def oracle_states():
     return {n: synth.random_state_for(synth.ENCODER_SPECS[n], seed=100 + i) for i, n in enumerate(("sa1", "sa2", "sa3"))}
 
 
-def time_cpu_oracle(n_windows: int, reps: int, warmup: int, device: str = "cpu"):
+def time_cpu_oracle(n_windows: int, reps: int, warmup: int, device: str = "cpu", threads: int | None = None):
     """Reference algorithm (oracle port) on the host - or, device="cuda", the same stock-PyTorch ops on the GPU,
     the comparator SURVEY.md 8d asks for since the reference ships no kernels: returns (windows/s, threads, seconds per rep)."""
     from ev2hands_b200 import synth
     from oracle import sa_oracle
-    threads = os.cpu_count() or 1
+    threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     states = oracle_states()
     ev = torch.from_numpy(synth.make_windows(n_windows, N_POINTS, seed=1234 + 1)).to(device)
@@ -170,6 +170,150 @@ def run_reference_arm(args):
     print(json.dumps(line))
     return 0
 
+
+
+# ----------------------------------------------------------------------------- secondary configs -
+def mlp_kernel_ms(kern):
+    n_, ms_ = 0, 0.0
+    for kname in ("ev2h_linear_relu_f32", "ev2h_linear_relu_tc", "ev2h_linear_f32", "ev2h_linear_tc", "ev2h_sa_msg_fused_tc"):
+        a, b = kern.get(kname, (0, 0.0))
+        n_, ms_ = n_ + a, ms_ + b
+    return n_, ms_
+
+
+def time_encoder_config(enc, device, B_local, n_points, seed, rank, world, steps, flush, barrier, precision, graph=True):
+    """One BASELINE config of the encoder forward on this rank's shard: `steps` timed steps (CUDA events per step, L2
+    flushed between steps, graph replay when it captures) and an eager pass with events around every kernel.
+    -> dict(ms_total, kern, graphed); the caller takes the max over ranks."""
+    import ev2hands_b200 as e2h
+    import ev2hands_b200.encoder as _enc_mod
+    from ev2hands_b200 import _capi, sharding, synth
+    from ev2hands_b200.encoder import GraphedForward
+    old_prec = e2h.get_mlp_precision()
+    e2h.set_mlp_precision(precision)
+    try:
+        ev_all = synth.make_windows(B_local * world, n_points, seed=seed)
+        s1_all = synth.make_start_indices(B_local * world, n_points, 0)
+        s2_all = synth.make_start_indices(B_local * world, 512, 1)
+        ev, s1, s2 = sharding.shard((torch.from_numpy(ev_all), torch.from_numpy(s1_all), torch.from_numpy(s2_all)), rank, world)
+        ev, s1, s2 = ev.to(device), s1.to(device), s2.to(device)
+
+        def fwd(e, a, b):
+            with torch.no_grad():
+                return enc(e, fps_starts=(a, b))
+
+        graphed = None
+        if graph:
+            try:
+                graphed = GraphedForward(fwd, ev, s1, s2)
+            except Exception as exc:      # noqa: BLE001
+                print("bench.py: capture failed for B=%d N=%d (%s); eager" % (B_local, n_points, exc), file=sys.stderr)
+        run = (lambda: graphed(ev, s1, s2)) if graphed is not None else (lambda: fwd(ev, s1, s2))
+        for _ in range(3):
+            run()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = run()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms_total = float(sum(a.elapsed_time(b) for a, b in evs))
+        geom_stream = _enc_mod._GEOM_STREAM
+        _enc_mod._GEOM_STREAM = False
+        _capi.LOG.reset(timing=True)
+        try:
+            for _ in range(steps):
+                flush.zero_()
+                fwd(ev, s1, s2)
+            barrier()
+            kern = _capi.LOG.totals_ms()
+        finally:
+            _capi.LOG.reset(timing=False)
+            _enc_mod._GEOM_STREAM = geom_stream
+        return {"ms_total": ms_total, "kern": kern, "graphed": graphed is not None, "checksum": float(out.double().sum().item())}
+    finally:
+        e2h.set_mlp_precision(old_prec)
+
+
+def config_line(name, res, ms_total, B_global, n_points, steps, precision, peaks):
+    n_mlp, mlp_ms = mlp_kernel_ms(res["kern"])
+    world_share = res["world"]                             # kernel times are this rank's shard of the global batch
+    ach = (2.0 * MLP_MAC_PER_WINDOW * (B_global // world_share) * steps) / (mlp_ms / 1e3) / 1e12 if mlp_ms > 0 else None
+    geo = sum(res["kern"].get(k, (0, 0.0))[1] for k in ("ev2h_fps_f32", "ev2h_ball_query_f32", "ev2h_first_occurrence_u8"))
+    tot_k = sum(v[1] for v in res["kern"].values())
+    return {"workload": name, "global_windows": B_global, "windows_per_gpu": B_global // world_share, "points": n_points,
+            "mlp": precision, "steps": steps, "ms_per_step": ms_total / steps, "value": B_global * steps / (ms_total / 1e3),
+            "unit": "windows/s", "launch": "graph replay" if res["graphed"] else "eager",
+            "roofline_frac": (ach / peaks["bf16_tflops"]) if ach else None, "mlp_tflops": ach,
+            "fps_ball_share_of_kernel_time": (geo / tot_k) if tot_k > 0 else None,
+            "kernels_ms_per_step": {k: v[1] / steps for k, v in sorted(res["kern"].items())}}
+
+
+def time_training_config(device, rank, world, steps, barrier):
+    """BASELINE configs[3]: full training step of the network (ev2hands_b200.tehnet.TEHNet: set abstraction, feature
+    propagation, classifier, attention, both hand regressors; MANO LBS and the criterion in PyTorch - MANO is a
+    MANO-shaped stand-in and loss_interpen is left out, both unavailable here), global batch 32 split over the ranks,
+    per-replica BatchNorm statistics, gradients averaged with bucketed NCCL all-reduces launched from backward hooks,
+    Adam.  -> dict of per-rank timings (ms) for the caller's max over ranks."""
+    from ev2hands_b200 import sharding, tehnet, trainer
+    os.environ.setdefault("ERPC", "1")
+    old_tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False          # fp32 convolutions, like the reference on its own hardware
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(0)                          # same initial weights on every rank
+        net = tehnet.TEHNet(n_pose_params=6).to(device).train()
+        hands = tehnet.create_standin_mano_layers(device, n_cmps=6)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)       # train.py:23,56
+        red = trainer.BucketedGradReducer(net.parameters(), n_buckets=4)
+        full = tehnet.make_training_batch(32, N_POINTS, seed=0)
+        lo, hi = sharding.shard_bounds(32, rank, world)
+
+        def cut(x):
+            return {k: cut(v) for k, v in x.items()} if isinstance(x, dict) else x[lo:hi].to(device)
+        batch = cut(full)
+        n_params = sum(p.numel() for p in net.parameters())
+
+        def step():
+            b = {k: (dict(v) if isinstance(v, dict) else v) for k, v in batch.items()}      # the criterion adds fields
+            return trainer.train_step(net, hands, b, opt, red, tehnet.training_losses)
+
+        for _ in range(2):
+            loss, _ = step()
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            loss, _ = step()
+        b_.record()
+        barrier()
+        step_ms = a.elapsed_time(b_) / steps
+        # the exchange alone: one blocking all-reduce of the whole flat gradient buffer
+        ar_ms = 0.0
+        if world > 1:
+            import torch.distributed as dist
+            for _ in range(2):
+                dist.all_reduce(red.flat)
+            barrier()
+            c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c.record()
+            for _ in range(5):
+                dist.all_reduce(red.flat)
+            d.record()
+            barrier()
+            ar_ms = c.elapsed_time(d) / 5
+        out = {"step_ms": step_ms, "allreduce_ms": ar_ms, "grad_bytes": red.bytes, "params": n_params, "loss": float(loss),
+               "buckets": len(red.buckets), "local_batch": hi - lo}
+        red.remove()
+        del net, opt, red
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old_tf32
 
 # ----------------------------------------------------------------------------- GPU arm -----------
 def build_encoder(device):
@@ -428,9 +572,60 @@ def run_ours(args):
             print("bench.py: raw-events leg failed (%s)" % exc, file=sys.stderr)
             raw_ms = raw_dev_ms = 0.0
 
+    # ---- secondary configs of BASELINE.json, every line of the run: config 3 = 1024 windows
+    # split over the ranks, config 5 = 16384-event windows, 256 split over the ranks, fp32-level and bf16 MLP;
+    # and a sustained figure: the headline loop for >= 2 s with the clocks sampled
+    cfg_res, sustained = {}, None
+    if args.configs:
+        plan = [("cfg3", max(1, 1024 // world), N_POINTS, args.mlp, min(args.steps, 5), 1234 + 3)]
+        plan += [("cfg5_" + pr, max(1, 256 // world), 16384, pr, 3, 1234 + 5) for pr in dict.fromkeys((args.mlp, "bf16"))]
+        for name, b_loc, n_pts, prec, k, seed in plan:
+            try:
+                r = time_encoder_config(enc, device, b_loc, n_pts, seed, rank, world, k, flush, barrier, prec, graph=args.graph)
+            except Exception as exc:      # noqa: BLE001 - a secondary number must not take the headline down
+                print("bench.py: %s failed (%s)" % (name, exc), file=sys.stderr)
+                r = {"ms_total": 0.0, "kern": {}, "graphed": False, "checksum": 0.0}
+            r.update(world=world, B_global=b_loc * world, n_points=n_pts, precision=prec, steps=k)
+            cfg_res[name] = r
+            torch.cuda.empty_cache()
+        # sustained: the headline step for >= 2 s (one event pair around the loop, L2 flushed every step, clocks sampled)
+        n_sus = int(min(4000, max(args.steps, 2200.0 / max(total_ms / args.steps, 0.05))))
+        for _ in range(3):
+            step_resident()
+        sus_sampler = ClockSampler(physical_gpu_index(local_rank), period_s=0.02)
+        barrier()
+        sus_sampler.start()
+        sa_, sb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sa_.record()
+        for _ in range(n_sus):
+            flush.zero_()
+            step_resident()
+        sb_.record()
+        barrier()
+        sustained = {"steps": n_sus, "ms_total": float(sa_.elapsed_time(sb_)), "clocks": sus_sampler.finish()}
+
+    train_res = None
+    if args.configs:
+        try:
+            train_res = time_training_config(device, rank, world, max(3, min(args.steps, 5)), barrier)
+        except Exception as exc:      # noqa: BLE001
+            print("bench.py: cfg4 (training step) failed (%s)" % exc, file=sys.stderr)
+            train_res = None
+        ok = sharding.max_over_ranks([0.0 if train_res is not None else 1.0], device=device)[0] == 0.0
+        if ok:
+            train_res["step_ms"], train_res["allreduce_ms"] = sharding.max_over_ranks([train_res["step_ms"], train_res["allreduce_ms"]], device=device)
+        else:
+            train_res = None
+
     # ---- max over ranks
     total_ms, e2e_ms, dec_ms, dense_ms, raw_ms, raw_dev_ms = sharding.max_over_ranks(
         [total_ms, e2e_ms, dec_ms, dense_ms, raw_ms, raw_dev_ms], device=device)
+    cfg_names = sorted(cfg_res)
+    if cfg_names:
+        mx = sharding.max_over_ranks([cfg_res[n]["ms_total"] for n in cfg_names] + [sustained["ms_total"]], device=device)
+        for n, v in zip(cfg_names, mx[:-1]):
+            cfg_res[n]["ms_total_max"] = v
+        sustained["ms_total"] = mx[-1]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -497,6 +692,44 @@ def run_ours(args):
     if comp and dense_ms > 0:
         line["compaction"]["dense_rows_eager"] = {"value": windows / (dense_ms / 1e3), "unit": "windows/s", "ms_per_step": dense_ms / args.steps,
                                                   "output_bits_equal": dense_equal}
+    from ev2hands_b200 import pointnet2_utils as _pu2
+    line["row_shortcut"] = dict(_pu2.ROW_SHORTCUT)      # levels handed over as rows (hit) vs transposed back (stale / none)
+    line["transposes_per_step"] = kern.get("ev2h_transpose_f32", (0, 0.0))[0] / args.steps
+    if cfg_res:
+        cfgs = {}
+        for n in sorted(cfg_res):
+            r = cfg_res[n]
+            if r["ms_total"] <= 0:
+                cfgs[n] = {"failed": True}
+                continue
+            what = {"cfg3": "BASELINE configs[2]: encoder forward, batch 1024 split over the ranks, no collective"}.get(
+                n, "BASELINE configs[4]: long-window stress, 16384-event windows, batch 256 split over the ranks")
+            cfgs[n] = config_line(what, r, r["ms_total_max"], r["B_global"], r["n_points"], r["steps"], r["precision"], peaks)
+        if "cfg5_bf16" in cfgs and ("cfg5_" + args.mlp) in cfgs and args.mlp != "bf16":
+            a_, b_ = cfg_res["cfg5_" + args.mlp], cfg_res["cfg5_bf16"]
+            cfgs["cfg5_bf16"]["checksum_rel_diff_vs_fp32_level"] = abs(a_["checksum"] - b_["checksum"]) / max(abs(a_["checksum"]), 1e-30)
+        line["configs"] = cfgs
+        mlp_share = mlp_ms / max(sum(v[1] for v in kern.values()), 1e-9)
+        sus_ms = sustained["ms_total"]
+        sus_tflops = (mlp_flops_per_step * sustained["steps"]) / (sus_ms * mlp_share / 1e3) / 1e12
+        line["sustained"] = {"value": B * world * sustained["steps"] / (sus_ms / 1e3), "unit": "windows/s", "steps": sustained["steps"],
+                             "seconds": sus_ms / 1e3, "ms_per_step": sus_ms / sustained["steps"], "clocks": sustained["clocks"],
+                             "roofline_frac": sus_tflops / peaks["bf16_tflops_sustained"], "peak": peaks["bf16_tflops_sustained"],
+                             "how": "the headline step repeated for >= 2 s, one event pair around the loop, L2 flushed every step; "
+                                    "MLP time = loop time x the MLP kernels' share of the per-kernel pass (%.3f); peak = measured sustained bf16" % mlp_share}
+    if train_res is not None:
+        line.setdefault("configs", {})["cfg4"] = {
+            "workload": "BASELINE configs[3]: full training step (set abstraction + feature propagation + classifier + attention + two hand "
+                        "regressors forward/backward on the GPU, MANO LBS + criterion in PyTorch), global batch 32 split over the ranks, "
+                        "per-replica BatchNorm, bucketed NCCL gradient all-reduce from backward hooks, Adam",
+            "global_batch": 32, "batch_per_gpu": train_res["local_batch"], "ms_per_step": train_res["step_ms"],
+            "value": 32.0 / (train_res["step_ms"] / 1e3), "unit": "windows/s", "params": train_res["params"],
+            "grad_allreduce_bytes": train_res["grad_bytes"], "grad_buckets": train_res["buckets"],
+            "allreduce_us_alone": 1e3 * train_res["allreduce_ms"], "loss": train_res["loss"], "dtype": "f32 (TF32 off)",
+            "stand_ins": "MANO layer = random MANO-shaped LBS (assets licence gated); criterion = losses.py:145-206 without loss_interpen "
+                         "(mesh_intersection absent): parity of those two parts unpinned",
+            "kernels": "FPS, ball query, grouping gather + scatter-add backward, max-pool + arg-max backward: libev2h.so; conv / BatchNorm "
+                       "(batch statistics) / ReLU: cuDNN through PyTorch"}
     if args.with_decoder:
         line["secondary"] = {"metric": "encoder + fp3/fp2/fp1 decoder event-windows/s (TEHNet.py:172-186)",
                              "value": windows / (dec_ms / 1e3), "unit": "windows/s", "ms_per_step": dec_ms / args.steps}
@@ -527,6 +760,17 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": wps, "unit": "windows/s", "cores": threads, "kind": "port",
                                 "sample": "4 windows per run, 1 warm-up + 3 timed runs of oracle/sa_oracle.py (torch CPU, "
                                           "the reference's algorithm op for op)"}
+        # BASELINE configs[0] (B = 1 on the host, the reference's own CPU-runnable case): min / median of
+        # 5 runs after 2 warm-ups, all host threads and one thread
+        try:
+            cfg1 = {}
+            for label, nthr in (("all_threads", os.cpu_count() or 1), ("one_thread", 1)):
+                _, _, t1 = time_cpu_oracle(1, 5, 2, threads=nthr)
+                cfg1[label] = {"threads": nthr, "windows_per_s_best": 1.0 / min(t1), "windows_per_s_median": 1.0 / float(np.median(t1)),
+                               "ms_min": 1e3 * min(t1), "ms_median": 1e3 * float(np.median(t1))}
+            line["cpu_baseline"]["cfg1_batch1"] = cfg1
+        except Exception as exc:      # noqa: BLE001
+            line["cpu_baseline"]["cfg1_batch1"] = {"unavailable": str(exc)[:200]}
         try:      # the same stock-PyTorch ops on this GPU (the reference ships no kernels): informational comparator
             gwps, _, _ = time_cpu_oracle(WINDOWS_PER_GPU, 2, 1, device="cuda")
             line["torch_gpu_baseline"] = {"value": gwps, "unit": "windows/s", "kind": "port",
@@ -548,6 +792,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--windows-per-gpu", type=int, default=WINDOWS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", dest="configs", action="store_false",
+                    help="skip the secondary configs (cfg3 / cfg5 / sustained) and time the headline only")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--with-decoder", action="store_true", help="also time encoder + feature-propagation decoder (secondary number)")
     ap.add_argument("--from-raw-events", dest="from_raw_events", action="store_true", default=True,

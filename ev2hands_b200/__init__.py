@@ -13,6 +13,7 @@ from .pointnet2_utils import (  # noqa: F401
     sample_and_group_all,
     square_distance,
 )
+from ._capi import check_numeric_range  # noqa: F401
 from .windows import EventWindowBuilder  # noqa: F401
 from .encoder import FeaturePropagationDecoder, RegressorSetAbstraction, SetAbstractionEncoder  # noqa: F401
 

@@ -43,7 +43,7 @@ _SIGNATURES = {
                              c_vp, c_int, c_vp, c_int, c_vp,
                              c_vp, c_int, c_int, c_vp, c_int, c_int,
                              c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
-                             c_vp, c_int, c_int, c_int, c_vp],
+                             c_vp, c_int, c_int, c_int, c_vp, c_vp],
     "ev2h_ball_query_cnt_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f),
                                 ctypes.POINTER(ctypes.c_int32), c_vp, c_vp, c_vp],
     "ev2h_first_occurrence_u8": [c_vp, c_int, c_int, c_vp, c_vp],
@@ -58,7 +58,7 @@ _SIGNATURES = {
                                      c_vp, c_int, c_vp, c_int, c_vp,
                                      c_vp, c_int, c_int, c_vp, c_int, c_int,
                                      c_int, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
-                                     c_vp, c_int, c_int, c_int, c_vp],
+                                     c_vp, c_int, c_int, c_int, c_vp, c_vp],
     "ev2h_three_nn_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_three_interp_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_window_aggregate_f64": [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
@@ -380,7 +380,7 @@ def linear_relu(x, M, ld_x, Cin, wt, bias, Cout, pool_rows, y, ld_y, y_col_off=0
                                           y_col_off, _stream(x)), "ev2h_linear_relu_f32")
 
 
-TC_BF16, TC_TF32X3, TC_TF32_BF16C = 0, 1, 2
+TC_BF16, TC_TF32X3, TC_TF32_BF16C, TC_F16X3 = 0, 1, 2, 3
 
 
 def tc_supported(Cout: int, pool_rows: int) -> bool:
@@ -436,32 +436,60 @@ def fused_supported(K: int, widths, first_in: int, per_point: bool, mode: int = 
         return False
     if per_point and widths[0] % 32 != 0:
         return False
-    if not per_point and first_in > 8:
+    if not per_point and (first_in > 8 or widths[0] > 128):      # layer 1 in the loader warps: weights are kernel parameters
         return False
     return fused_kc(mode, widths[1:]) > 0
 
 
-def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, first_wt, first_bias, P, ld_p, p_col, C, ld_c, c_col,
+_range_flags = {}
+
+
+def range_flag(device) -> torch.Tensor:
+    """int32 [1] on `device`: bit 0 is set by the fused kernel when an fp16-split operand overflowed (TC_F16X3)."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    t = _range_flags.get(device)
+    if t is None:
+        t = _range_flags[device] = torch.zeros((1,), dtype=torch.int32, device=device)
+    return t
+
+
+def check_numeric_range(device="cuda", reset: bool = True) -> bool:
+    """True if no fused launch on `device` saw an activation outside the fp16 range since the last reset
+    (synchronises; call it at a checkpoint, not per step).  Raise-free so callers decide what to do."""
+    t = range_flag(device)
+    ok = int(t.item()) == 0
+    if reset:
+        t.zero_()
+    return ok
+
+
+def sa_msg_fused(idx, k_off, centres_rows, B, N, S, K, pts8, D, first_wt_host, first_bias_host, P, ld_p, p_col, C, ld_c, c_col,
                  c1, couts, packed, biases, out_rows, ld_out, out_col, mode, compact=None):
-    """compact = (rowmap, blockgroup, n_rows_scalar_view) runs the kernel over the compacted row list."""
+    """compact = (rowmap, blockgroup, n_rows_scalar_view) runs the kernel over the compacted row list.
+    first_wt_host / first_bias_host: contiguous float32 HOST tensors (gather mode), the folded layer-1 map."""
     a_cout = (ctypes.c_int32 * 2)(*couts)
     a_w = (c_vp * 2)(*[t.data_ptr() for t in packed])
     a_b = (c_vp * 2)(*[t.data_ptr() for t in biases])
+    if first_wt_host is not None and (first_wt_host.is_cuda or first_bias_host.is_cuda or not first_wt_host.is_contiguous()):
+        raise RuntimeError("sa_msg_fused: the layer-1 weights of the gather mode are passed as contiguous HOST tensors")
+    flag = range_flag(out_rows.device) if mode == TC_F16X3 else None
     with torch.cuda.device(out_rows.device):
         if compact is not None:
             rm, bg, nr = compact
             with _timed("ev2h_sa_msg_fused_tc"):
                 _check(lib().ev2h_sa_msg_fused_compact_tc(_p(rm), _p(bg), _p(nr), _p(centres_rows), B, N, S, K,
-                                                          _p(pts8), D, _p(first_wt), 0 if first_wt is None else first_wt.shape[1],
-                                                          _p(first_bias), _p(P), ld_p, p_col, _p(C), ld_c, c_col,
-                                                          c1, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode,
+                                                          _p(pts8), D, _p(first_wt_host), 0 if first_wt_host is None else first_wt_host.shape[1],
+                                                          _p(first_bias_host), _p(P), ld_p, p_col, _p(C), ld_c, c_col,
+                                                          c1, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode, _p(flag),
                                                           _stream(out_rows)), "ev2h_sa_msg_fused_compact_tc")
             return
         with _timed("ev2h_sa_msg_fused_tc"):
             _check(lib().ev2h_sa_msg_fused_tc(_p(idx), idx.shape[-1], k_off, _p(centres_rows), B, N, S, K,
-                                              _p(pts8), D, _p(first_wt), 0 if first_wt is None else first_wt.shape[1],
-                                              _p(first_bias), _p(P), ld_p, p_col, _p(C), ld_c, c_col,
-                                              c1, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode,
+                                              _p(pts8), D, _p(first_wt_host), 0 if first_wt_host is None else first_wt_host.shape[1],
+                                              _p(first_bias_host), _p(P), ld_p, p_col, _p(C), ld_c, c_col,
+                                              c1, a_cout, a_w, a_b, _p(out_rows), ld_out, out_col, mode, _p(flag),
                                               _stream(out_rows)), "ev2h_sa_msg_fused_tc")
 
 

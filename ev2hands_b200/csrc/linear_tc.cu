@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace ev2h {
 
@@ -33,9 +34,10 @@ constexpr int TC_LOADER_GROUPS = 2;    // groups of 4 loader warps working on di
 constexpr int TC_THREADS = 32 * (5 + 4 * TC_LOADER_GROUPS);   // 4 epilogue + 1 issuer + loader warps
 constexpr int TC_MAX_STAGES = 8;
 
-enum { TC_MODE_BF16 = 0, TC_MODE_TF32X3 = 1, TC_MODE_MIXED = 2 };   // MIXED: weight images for sa_fused_tc.cu only
+// MIXED: tf32 hi*hi + two bf16 correction products;  F16X3: fp16 hi/lo pairs, three kind::f16 products (tc::split_f16x2)
+enum { TC_MODE_BF16 = 0, TC_MODE_TF32X3 = 1, TC_MODE_MIXED = 2, TC_MODE_F16X3 = 3 };
 
-__host__ __device__ constexpr int tc_elem_bytes(int mode) { return mode == TC_MODE_BF16 ? 2 : 4; }
+__host__ __device__ constexpr int tc_elem_bytes(int mode) { return (mode == TC_MODE_BF16 || mode == TC_MODE_F16X3) ? 2 : 4; }
 // bytes of one operand image holding `rows` rows x TC_KC channels (one precision part)
 __host__ __device__ constexpr int tc_part_bytes(int mode, int rows) { return rows * TC_KC * tc_elem_bytes(mode); }
 __host__ __device__ constexpr int tc_parts(int mode) { return mode == TC_MODE_BF16 ? 1 : 2; }
@@ -81,6 +83,11 @@ tc_pack_kernel(const float *__restrict__ wt, int ld_w, int cin_rows, int cout_co
     const size_t off = (size_t)(kk / CH) * ((size_t)n_blk * 16) + (size_t)n * 16 + (size_t)(kk % CH) * EB;
     if (MODE == TC_MODE_BF16) {
         *reinterpret_cast<__nv_bfloat16 *>(stage + off) = __float2bfloat16_rn(w);
+    } else if (MODE == TC_MODE_F16X3) {
+        // [hi as fp16 | lo as fp16], 16-byte chunks of 8 channels
+        const __half hi = __float2half_rn(w);
+        *reinterpret_cast<__half *>(stage + off) = hi;
+        *reinterpret_cast<__half *>(stage + part + off) = __float2half_rn(w - __half2float(hi));
     } else if (MODE == TC_MODE_MIXED) {
         // [hi as tf32 | w as bf16 | lo as bf16]: the fused kernel's hi*hi runs in tf32, the two correction
         // products on the bf16 copies (16-byte chunks of 8 channels)
@@ -215,6 +222,17 @@ linear_tc_kernel(const TcParams p) {
                             *reinterpret_cast<float4 *>(st + c * (TC_BLOCK_M * 16) + row * 16) = hi;
                             *reinterpret_cast<float4 *>(st + A_PART + c * (TC_BLOCK_M * 16) + row * 16) = lo;
                         }
+                    } else if (MODE == TC_MODE_F16X3) {
+                        // [x_hi as fp16 | x_lo as fp16]: 8 channels of a row = one 16-byte chunk of each part
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = 32 * wq + i * 8 + l8;
+                            uint4 hb, lb;
+                            tc::split_f16x2(v[2 * i].x, v[2 * i].y, hb.x, lb.x); tc::split_f16x2(v[2 * i].z, v[2 * i].w, hb.y, lb.y);
+                            tc::split_f16x2(v[2 * i + 1].x, v[2 * i + 1].y, hb.z, lb.z); tc::split_f16x2(v[2 * i + 1].z, v[2 * i + 1].w, hb.w, lb.w);
+                            *reinterpret_cast<uint4 *>(st + oct * (TC_BLOCK_M * 16) + row * 16) = hb;
+                            *reinterpret_cast<uint4 *>(st + A_PART + oct * (TC_BLOCK_M * 16) + row * 16) = lb;
+                        }
                     } else if (MODE == TC_MODE_MIXED) {
                         // [x_hi as tf32 | x as bf16 | x_lo as bf16] (the layout of tc_pack_kernel<MIXED> and of
                         // sa_fused_tc.cu): 8 channels of a row = two tf32 chunks and one chunk of each bf16 copy
@@ -266,8 +284,12 @@ linear_tc_kernel(const TcParams p) {
         }
     } else if (warp == 4) {
         // ================================ UMMA issuer ================================
-        if (lane == 0) {
-            const uint32_t idesc = tc::instr_desc(MODE == TC_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, TC_BLOCK_M, (uint32_t)n_blk);
+        // the whole warp walks the stages, one ELECTED lane issues: descriptors stay in uniform registers (under
+        // `if (lane == 0)` every UTCHMMA is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop, see sa_fused_tc.cu)
+        {
+            const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
+            const uint32_t idesc = tc::instr_desc(MODE == TC_MODE_BF16 ? tc::FMT_BF16 : MODE == TC_MODE_F16X3 ? tc::FMT_F16 : tc::FMT_TF32,
+                                                  TC_BLOCK_M, (uint32_t)n_blk);
             const uint32_t idesc16 = tc::instr_desc(tc::FMT_BF16, TC_BLOCK_M, (uint32_t)n_blk);      // MIXED: the correction products
             const uint32_t a_lbo = TC_BLOCK_M * 16, b_lbo = (uint32_t)n_blk * 16, sbo = 128;
             const bool swap = p.debug & 1;       // debug: exchange the roles of the two descriptor offsets
@@ -286,6 +308,7 @@ linear_tc_kernel(const TcParams p) {
                     tc::tc_fence_after();
                     const uint32_t a0 = tc::smem_u32(ring + (size_t)stage * stage_bytes);
                     const uint32_t b0 = a0 + PARTS * A_PART;
+                    if (tc::elect_one()) {
 #pragma unroll
                     for (int j = 0; j < K_STEPS; ++j) {
                         const uint32_t a_off = (uint32_t)j * 2 * a_lbo, b_off = (uint32_t)j * 2 * b_lbo;
@@ -298,6 +321,14 @@ linear_tc_kernel(const TcParams p) {
                             tc::umma_tf32(d_tmem, a_lo, b_hi, idesc, first);     // small terms first
                             tc::umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
                             tc::umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                        } else if (MODE == TC_MODE_F16X3) {
+                            const uint64_t a_hi = desc(a0 + a_off, a_lbo);
+                            const uint64_t a_lo = desc(a0 + A_PART + a_off, a_lbo);
+                            const uint64_t b_hi = desc(b0 + b_off, b_lbo);
+                            const uint64_t b_lo = desc(b0 + b_part + b_off, b_lbo);
+                            tc::umma_f16(d_tmem, a_lo, b_hi, idesc, first);      // small terms first
+                            tc::umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+                            tc::umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
                         } else if (MODE == TC_MODE_MIXED) {
                             tc::umma_tf32(d_tmem, desc(a0 + a_off, a_lbo), desc(b0 + b_off, b_lbo), idesc, first);      // x_hi * w_hi
                         } else {
@@ -315,9 +346,12 @@ linear_tc_kernel(const TcParams p) {
                         }
                     }
                     tc::umma_commit(empty_bar + stage);             // stage reusable once these UMMAs retire
+                    }
+                    __syncwarp();
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                tc::umma_commit(acc_full + acc);                    // accumulator complete
+                if (tc::elect_one()) tc::umma_commit(acc_full + acc);                    // accumulator complete
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -433,7 +467,7 @@ static int tc_n_blk_aligned(int Cout, int row_align) {
 
 extern "C" int64_t ev2h_tc_packed_bytes_kc(int Cin, int Cout, int mode, int kc, int row_align) {
     using namespace ev2h;
-    if (Cin <= 0 || Cout <= 0 || (mode != TC_MODE_BF16 && mode != TC_MODE_TF32X3 && mode != TC_MODE_MIXED) || (kc != 16 && kc != 32) ||
+    if (Cin <= 0 || Cout <= 0 || (mode < TC_MODE_BF16 || mode > TC_MODE_F16X3) || (kc != 16 && kc != 32) ||
         (row_align != 16 && row_align != 128)) return -1;
     const int n_blk = tc_n_blk_aligned(Cout, row_align);
     return (int64_t)((Cout + n_blk - 1) / n_blk) * ((Cin + kc - 1) / kc) * tc_parts(mode) * n_blk * kc * tc_elem_bytes(mode);
@@ -454,7 +488,7 @@ extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int C
     EV2H_REQUIRE(row_align == 16 || row_align == 128, "ev2h_tc_pack_weights: row_align must be 16 or 128");
     EV2H_REQUIRE(wt && packed, "ev2h_tc_pack_weights: null argument");
     EV2H_REQUIRE(Cin > 0 && Cout > 0 && ld_w >= Cout, "ev2h_tc_pack_weights: bad sizes");
-    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3 || mode == TC_MODE_MIXED, "ev2h_tc_pack_weights: unknown mode %d", mode);
+    EV2H_REQUIRE(mode >= TC_MODE_BF16 && mode <= TC_MODE_F16X3, "ev2h_tc_pack_weights: unknown mode %d", mode);
     const int n_blk = tc_n_blk_aligned(Cout, row_align), n_blocks = (Cout + n_blk - 1) / n_blk, n_kc = (Cin + kc - 1) / kc;
     const int64_t total = (int64_t)n_blocks * n_kc * n_blk * kc;
     const unsigned grid = (unsigned)((total + 255) / 256);
@@ -465,6 +499,8 @@ extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int C
         tc_pack_kernel<TC_MODE_BF16><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
     else if (mode == TC_MODE_MIXED)
         tc_pack_kernel<TC_MODE_MIXED><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
+    else if (mode == TC_MODE_F16X3)
+        tc_pack_kernel<TC_MODE_F16X3><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
     else
         tc_pack_kernel<TC_MODE_TF32X3><<<grid, 256, 0, as_stream(stream)>>>(wt, ld_w, cin_rows, cout_cols, n_blk, n_blocks, n_kc, kc, (uint8_t *)packed);
     return check_launch("ev2h_tc_pack_weights");
@@ -489,7 +525,7 @@ static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const vo
     using namespace ev2h;
     EV2H_REQUIRE(x && w_packed && bias && y, "ev2h_linear_relu_tc: null argument");
     EV2H_REQUIRE(M > 0 && Cin > 0 && Cout > 0, "ev2h_linear_relu_tc: bad sizes");
-    EV2H_REQUIRE(mode == TC_MODE_BF16 || mode == TC_MODE_TF32X3 || mode == TC_MODE_MIXED, "ev2h_linear_relu_tc: unknown mode %d", mode);
+    EV2H_REQUIRE(mode >= TC_MODE_BF16 && mode <= TC_MODE_F16X3, "ev2h_linear_relu_tc: unknown mode %d", mode);
     EV2H_REQUIRE(ld_x % 4 == 0 && ld_x >= Cin, "ev2h_linear_relu_tc: ld_x=%d must be a multiple of 4 and >= Cin=%d", ld_x, Cin);
     EV2H_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "ev2h_linear_relu_tc: x and w_packed must be 16-byte aligned");
     EV2H_REQUIRE(pool_rows >= 0 && (pool_rows == 0 || M % pool_rows == 0), "ev2h_linear_relu_tc: M must be a multiple of pool_rows");
@@ -532,6 +568,9 @@ static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const vo
     } else if (mode == TC_MODE_MIXED) {
         e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) linear_tc_kernel<TC_MODE_MIXED><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);
+    } else if (mode == TC_MODE_F16X3) {
+        e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_F16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) linear_tc_kernel<TC_MODE_F16X3><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);
     } else {
         e = cudaFuncSetAttribute(linear_tc_kernel<TC_MODE_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) linear_tc_kernel<TC_MODE_TF32X3><<<grid, TC_THREADS, smem, as_stream(stream)>>>(p);

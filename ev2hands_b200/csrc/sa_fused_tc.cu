@@ -39,9 +39,15 @@
 // copies.  The corrections are 2^-11 of the result, so bf16's 2^-9 relative error on them is 2^-20 of the
 // result (measured end to end: same error against the reference as TF32X3), while tensor time and the
 // shared-memory operand reads per product drop by a third (the kernel is shared-memory-bandwidth bound).
+// F16X3 (round 2, the default fp32-level mode): x = hi + lo and w = hi + lo as fp16 pairs (tc::split_f16x2, ~22 bits),
+// three kind::f16 UMMAs lo*hi + hi*lo + hi*hi.  Against MIXED: three quarters of the tensor time, HALF the operand
+// bytes written to and fetched from shared memory (4 instead of 8 bytes per element), and 32-channel chunks fit the
+// two-CTAs-per-SM instances, which halves the hand-shakes per tile.  Domain: activations below 65520 (fp16 range) -
+// an overflow raises the caller's range flag instead of passing silently.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <string.h>
 #include <stdlib.h>
 
@@ -61,7 +67,9 @@ constexpr int FZ_MAX_PRODUCERS = 3;       // up to two loader groups + the epilo
 __host__ __device__ constexpr int fz_issuers(int occ) { return occ == 1 ? 2 : 1; }
 __host__ __device__ constexpr int fz_threads(int lg, int occ) { return 32 * (5 + 4 * lg + fz_issuers(occ)); }
 
-enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1, FZ_MODE_MIXED = 2 };
+enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1, FZ_MODE_MIXED = 2, FZ_MODE_F16X3 = 3 };
+__host__ __device__ constexpr bool fz_two_byte(int mode) { return mode == FZ_MODE_BF16 || mode == FZ_MODE_F16X3; }
+constexpr int FZ_W1_MAX = 128;            // widest layer 1 evaluated in the loader warps (weights travel as kernel parameters)
 
 struct FusedParams {
     // geometry of the grouping
@@ -75,8 +83,12 @@ struct FusedParams {
     // layer 1
     int per_point;                               // 0 = gather + FFMA, 1 = relu(P - C)
     const float *pts8; int D;                    // gather: [B,N,8] rows = [features(D) | xyz | 0]
-    const float *first_wt; int first_ld;         // gather: folded layer-1 weights [16, first_ld], input-channel major
-    const float *first_bias;
+    // gather: folded layer-1 weights and bias as KERNEL PARAMETERS (constant bank, read through the uniform datapath:
+    // LDCU + FFMA2 with a uniform-register operand), so that the loaders' weight reads stay off the shared-memory
+    // pipe the tensor cores' operand fetches and the operand stores saturate (round 1: 46-50 % of the LSU wavefronts
+    // of the sa1 launches were these warp-uniform LDS.128).  Channel pairs interleaved: w1c[pair][k][2], b1c[ch].
+    float w1c[FZ_W1_MAX * 8];
+    float b1c[FZ_W1_MAX];
     const float *P; int ld_p, p_col;             // per-point: layer-1 pre-activation per point [B*N, ld_p]
     const float *C; int ld_c, c_col;             // per-point: per-centre offset [B*S, ld_c]
     int c1;                                      // layer-1 width = layer-2 input channels
@@ -94,6 +106,7 @@ struct FusedParams {
     float *out; int ld_out, out_col, c_out;
     // rings
     int sa, sb, a_slot_bytes, b_slot_bytes;
+    int32_t *range_flag;                         // optional: bit 0 set when an F16X3 operand left the fp16 range
     long long *dbg;     // optional trace buffer (EV2H_FUSED_TRACE builds only, tools/fused_trace.py)
 };
 
@@ -126,11 +139,11 @@ __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs,
 
 template <int MODE, int KC, int LG, int OCC>
 __global__ void __launch_bounds__(fz_threads(LG, OCC), OCC)
-sa_fused_tc_kernel(const FusedParams p) {
+sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
     constexpr int THREADS = fz_threads(LG, OCC);
     constexpr int NI = fz_issuers(OCC);
-    constexpr int EB = MODE == FZ_MODE_BF16 ? 2 : 4;
+    constexpr int EB = fz_two_byte(MODE) ? 2 : 4;
     constexpr int PARTS = MODE == FZ_MODE_BF16 ? 1 : 2;
     constexpr int A_PART = FZ_BLOCK_M * KC * EB;         // per precision part: 16 KB (tf32, KC 32) ... 8 KB
     constexpr int A_B16 = FZ_BLOCK_M * KC * 2;           // MIXED: bf16 copy of hi at A_PART, bf16 lo at A_PART + A_B16
@@ -138,7 +151,7 @@ sa_fused_tc_kernel(const FusedParams p) {
     constexpr int UMMA_K = 32 / EB;
     constexpr int K_STEPS = KC / UMMA_K;
     constexpr int CHUNK_ROWS_BYTES = FZ_BLOCK_M * 16;    // one 16-byte operand chunk for all 128 rows
-    static_assert(NCH >= 2 && (MODE != FZ_MODE_BF16 || KC == 32), "unsupported chunk geometry");
+    static_assert(NCH >= 2 && (!fz_two_byte(MODE) || KC == 32), "unsupported chunk geometry");
 
     uint8_t *a_ring = fz_smem;
     uint8_t *b_ring = a_ring + (size_t)p.sa * p.a_slot_bytes;
@@ -158,8 +171,6 @@ sa_fused_tc_kernel(const FusedParams p) {
     uint64_t *turn = init_done + FZ_GEMMS;               // [2] two issuers: turn[i] = issuer i has ISSUED another of its chunks
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(turn + FZ_GEMMS);
     float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);          // [n0 + n1]; tail offset 464, 16-byte aligned
-    float *w1s = bias_s + p.n[0] + p.n[1];                             // [c1_pad][8] layer-1 weights (gather mode)
-    float *b1s = w1s + (p.per_point ? 0 : p.n_chunks[0] * KC * 8);     // [c1_pad]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef EV2H_FUSED_TRACE
@@ -185,15 +196,7 @@ sa_fused_tc_kernel(const FusedParams p) {
     }
     for (int g = 0; g < FZ_GEMMS; ++g)
         for (int i = tid; i < p.n[g]; i += THREADS) bias_s[p.bias_off[g] + i] = p.bias[g][i];
-    if (!p.per_point) {
-        const int c1_pad = nc0 * KC;
-        for (int i = tid; i < c1_pad * 8; i += THREADS) {
-            // channel pairs interleaved, [pair][k][2], so one 64-bit word feeds one packed FMA
-            const int ch = 2 * (i >> 4) + (i & 1), k = (i >> 1) & 7;
-            w1s[i] = ch < p.c1 ? p.first_wt[(size_t)k * p.first_ld + ch] : 0.f;
-        }
-        for (int i = tid; i < c1_pad; i += THREADS) b1s[i] = i < p.c1 ? p.first_bias[i] : 0.f;
-    }
+    uint32_t hmax = 0;              // F16X3: running maximum of the fp16 hi words this thread wrote (range check)
     // Warp roles, lowest to highest warp id = lowest to highest scheduler priority: loaders (work with
     // slack), weight streamer, UMMA issuer, and the epilogue warps, which are the serial bottleneck of a tile.
     constexpr int STREAMER_WARP = 4 * LG, ISSUER_WARP = 4 * LG + 1, EPI_WARP0 = 4 * LG + 1 + NI;
@@ -225,6 +228,16 @@ sa_fused_tc_kernel(const FusedParams p) {
                 lb.z = tc::bf16x2(l1.x, l1.y); lb.w = tc::bf16x2(l1.z, l1.w);
                 *reinterpret_cast<uint4 *>(st + A_PART + c8 * CHUNK_ROWS_BYTES + r * 16) = xb;
                 *reinterpret_cast<uint4 *>(st + A_PART + A_B16 + c8 * CHUNK_ROWS_BYTES + r * 16) = lb;
+            }
+        } else if (MODE == FZ_MODE_F16X3) {
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) {               // 8 channels = one 16-byte chunk of each part
+                uint4 hb, lb;
+                tc::split_f16x2(v[8 * cc], v[8 * cc + 1], hb.x, lb.x); tc::split_f16x2(v[8 * cc + 2], v[8 * cc + 3], hb.y, lb.y);
+                tc::split_f16x2(v[8 * cc + 4], v[8 * cc + 5], hb.z, lb.z); tc::split_f16x2(v[8 * cc + 6], v[8 * cc + 7], hb.w, lb.w);
+                hmax = tc::max_u16x2(tc::max_u16x2(hmax, tc::max_u16x2(hb.x, hb.y)), tc::max_u16x2(hb.z, hb.w));
+                *reinterpret_cast<uint4 *>(st + cc * CHUNK_ROWS_BYTES + r * 16) = hb;
+                *reinterpret_cast<uint4 *>(st + A_PART + cc * CHUNK_ROWS_BYTES + r * 16) = lb;
             }
         } else if (MODE == FZ_MODE_TF32X3) {
 #pragma unroll
@@ -303,16 +316,23 @@ sa_fused_tc_kernel(const FusedParams p) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) xx[i] = tc::pack2(x[i], x[i]);
                 valid = valid_n;
+                const ulonglong2 *w1p = reinterpret_cast<const ulonglong2 *>(p.w1c);      // constant bank (kernel parameters)
+                const uint64_t *b1p = reinterpret_cast<const uint64_t *>(p.b1c);
                 gather(tile + gridDim.x, xn, valid_n);            // next tile's record is in flight during this tile
-                for (int kc = 0; kc < nc0; ++kc) {
+                // kc is a compile-time constant in every copy of the body, so every weight address is an immediate offset
+                // into the parameter block: LDCU.128 into uniform registers feeding FFMA2 directly (with a run-time kc
+                // the compiler falls back to one per-thread LDC.64 per FMA)
+#pragma unroll
+                for (int kc = 0; kc < FZ_W1_MAX / KC; ++kc) {
+                    if (kc >= nc0) break;
                     if (!mine(it, kc)) continue;
                     float v[KC];
 #pragma unroll
                     for (int j = 0; j < KC; j += 2) {
                         const int ch = kc * KC + j;
-                        const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(w1s + ch * 8);
+                        const ulonglong2 *wp = w1p + ch * 2;                  // [pair][k][2]: 16 floats per channel pair
                         const ulonglong2 w01 = wp[0], w23 = wp[1], w45 = wp[2], w67 = wp[3];
-                        uint64_t acc = *reinterpret_cast<const uint64_t *>(b1s + ch);
+                        uint64_t acc = b1p[ch >> 1];
                         acc = tc::fma2(w01.x, xx[0], acc); acc = tc::fma2(w01.y, xx[1], acc);
                         acc = tc::fma2(w23.x, xx[2], acc); acc = tc::fma2(w23.y, xx[3], acc);
                         acc = tc::fma2(w45.x, xx[4], acc); acc = tc::fma2(w45.y, xx[5], acc);
@@ -394,6 +414,14 @@ sa_fused_tc_kernel(const FusedParams p) {
                         const uint32_t o16 = (quad >> 1) * CHUNK_ROWS_BYTES + row * 16 + (quad & 1) * 8;
                         *reinterpret_cast<uint2 *>(st + A_PART + o16) = make_uint2(tc::bf16x2(v[i].x, v[i].y), tc::bf16x2(v[i].z, v[i].w));
                         *reinterpret_cast<uint2 *>(st + A_PART + A_B16 + o16) = make_uint2(tc::bf16x2(lo.x, lo.y), tc::bf16x2(lo.z, lo.w));
+                    } else if (MODE == FZ_MODE_F16X3) {     // a 16-byte fp16 chunk holds two fp32 quads
+                        uint2 hb, lb;
+                        tc::split_f16x2(v[i].x, v[i].y, hb.x, lb.x);
+                        tc::split_f16x2(v[i].z, v[i].w, hb.y, lb.y);
+                        hmax = tc::max_u16x2(hmax, tc::max_u16x2(hb.x, hb.y));
+                        const uint32_t o16 = (quad >> 1) * CHUNK_ROWS_BYTES + row * 16 + (quad & 1) * 8;
+                        *reinterpret_cast<uint2 *>(st + o16) = hb;
+                        *reinterpret_cast<uint2 *>(st + A_PART + o16) = lb;
                     } else if (MODE == FZ_MODE_TF32X3) {
                         float4 hi, lo;
                         tc::split_tf32x2(v[i].x, v[i].y, hi.x, hi.y, lo.x, lo.y);
@@ -474,8 +502,16 @@ sa_fused_tc_kernel(const FusedParams p) {
         // layer overwrites the accumulator: the owner of chunk 1 additionally waits until chunk 0 has COMPLETED
         // (tcgen05.commit -> init_done), and the accumulator goes to the epilogue after both issuers' commits
         // (acc_full counts NI).  Both wait for acc_empty at the start of every layer.
+        // The WHOLE warp walks the chunk sequence (waits included) and one elected lane issues: every value that
+        // reaches a tcgen05 instruction is then provably warp-uniform (kernel parameters, loop counters, and the two
+        // run-time scalars - the TMEM base and the tile count - broadcast with a shuffle), so descriptors live in
+        // uniform registers.  Under `if (lane == 0)` the compiler cannot know the branch holds one thread and wraps
+        // each UTCHMMA in an ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY loop (~13 dependent instructions per UMMA: the
+        // issuing thread, not the tensor pipe, then sets the pace - ~170 cycles per 64-cycle UMMA in the round-2 trace).
         const uint32_t me = (uint32_t)(warp - ISSUER_WARP);
-        if (lane == 0) {
+        {
+            const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+            const int64_t n_tiles = ((int64_t)__shfl_sync(0xffffffffu, (uint32_t)((M + FZ_BLOCK_M - 1) / FZ_BLOCK_M), 0));
             const uint32_t sa = (uint32_t)p.sa, sb = (uint32_t)p.sb, mb3 = (uint32_t)p.mb3;
             const uint32_t a_full_u = tc::smem_u32(a_full), a_grant_u = tc::smem_u32(a_grant), b_full_u = tc::smem_u32(b_full),
                            b_empty_u = tc::smem_u32(b_empty), acc_full_u = tc::smem_u32(acc_full), acc_empty_u = tc::smem_u32(acc_empty),
@@ -500,7 +536,8 @@ sa_fused_tc_kernel(const FusedParams p) {
                     // g == 0: D[rows x n0]      = X[rows x K] * W2[n0 x K]^T      (A = activations, B = weights)
                     // g == 1: D[chan x rows]^T: per 128-channel block  D = W3[128 x K] * X[rows x K]^T  (A = weights, B = activations)
                     const uint32_t n_umma = g == 0 ? wr[0] : (uint32_t)FZ_BLOCK_M;
-                    const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : tc::FMT_TF32, FZ_BLOCK_M, n_umma);
+                    const uint32_t idesc = tc::instr_desc(MODE == FZ_MODE_BF16 ? tc::FMT_BF16 : MODE == FZ_MODE_F16X3 ? tc::FMT_F16 : tc::FMT_TF32,
+                                                          FZ_BLOCK_M, n_umma);
                     const uint32_t idesc16 = tc::instr_desc(tc::FMT_BF16, FZ_BLOCK_M, n_umma);     // MIXED: the correction products
                     const uint32_t b_lbo_d = wr[g];                      // (w_rows * 16) >> 4
                     const uint32_t b_step = 2 * b_lbo_d;
@@ -508,19 +545,19 @@ sa_fused_tc_kernel(const FusedParams p) {
                     const uint32_t b_base = b_ring_d | (b_lbo_d << 16);
                     const uint32_t n_mb = g == 0 ? 1u : mb3;
                     tc::mbar_wait_u32(acc_empty_u + 8 * g, (it & 1) ^ 1, 30 + g);      // previous tile's epilogue drained this accumulator
-                    if (me == 0) FZ_TRACE(3, 1, it, g * 50);
+                    if (me == 0 && lane == 0) FZ_TRACE(3, 1, it, g * 50);
                     tc::tc_fence_after();
                     // one product: x = activation operand, w = weight operand (descriptor low words)
                     auto mma = [&](bool k16, uint32_t d, uint32_t x, uint32_t w, uint32_t acc) {
                         const uint64_t dx = tc::make_desc(x, desc_hi), dw = tc::make_desc(w, desc_hi);
                         if (k16) { if (g == 0) tc::umma_f16(d, dx, dw, idesc16, acc); else tc::umma_f16(d, dw, dx, idesc16, acc); }
-                        else if (MODE == FZ_MODE_BF16) { if (g == 0) tc::umma_f16(d, dx, dw, idesc, acc); else tc::umma_f16(d, dw, dx, idesc, acc); }
+                        else if (fz_two_byte(MODE)) { if (g == 0) tc::umma_f16(d, dx, dw, idesc, acc); else tc::umma_f16(d, dw, dx, idesc, acc); }
                         else { if (g == 0) tc::umma_tf32(d, dx, dw, idesc, acc); else tc::umma_tf32(d, dw, dx, idesc, acc); }
                     };
                     // the products of K step j (8 tf32 / 16 bf16 channels) of one chunk into accumulator block mb
                     auto k_step = [&](uint32_t x0, uint32_t w0, uint32_t mb, uint32_t j, uint32_t acc) {
                         const uint32_t d = dt[g] + mb * FZ_BLOCK_M, x = x0 + j * a_step, w = w0 + mb * 128u + j * b_step;
-                        if (MODE == FZ_MODE_TF32X3) {
+                        if (MODE == FZ_MODE_TF32X3 || MODE == FZ_MODE_F16X3) {      // small terms first: x_lo*w_hi + x_hi*w_lo + x_hi*w_hi
                             mma(false, d, x + A_PART_D, w, acc);
                             mma(false, d, x, w + b_part_d, 1u);
                             mma(false, d, x, w, 1u);
@@ -538,7 +575,7 @@ sa_fused_tc_kernel(const FusedParams p) {
                     for (uint32_t c = 0; c < nch[g]; ++c) {
                         if (NI == 1 || par == me) {
                         tc::mbar_wait2_u32(a_full_u + 8 * a_slot, a_phase, b_full_u + 8 * b_slot, b_phase, 40 + g, 50 + g);
-                        if (me == 0) FZ_TRACE(3, 3, it, g * 50 + c);
+                        if (me == 0 && lane == 0) FZ_TRACE(3, 3, it, g * 50 + c);
                         if (NI == 2) {
                             // my chunk is number 2 * own + me: the other issuer must have issued number 2 * own + me - 1
                             if (me == 1) tc::mbar_wait_u32(turn_u, own & 1u, 37);
@@ -548,6 +585,9 @@ sa_fused_tc_kernel(const FusedParams p) {
                         tc::tc_fence_after();
                         const uint32_t x0 = a_base + a_slot * a_slot_d, w0 = b_base + b_slot * b_slot_d;
                         const uint32_t acc0 = c > 0 ? 1u : 0u;
+                        // the producer that fills this operand slot next: a loader group or the epilogue warps
+                        const uint32_t next_prod = g_q < (uint32_t)nc0 ? (LG == 1 ? 0u : (g_it * (uint32_t)nc0 + g_q) % LG) : (uint32_t)LG;
+                        if (tc::elect_one()) {
                         if (c + 1 < nch[g] || ksl[g] == (uint32_t)K_STEPS) {
 #pragma unroll
                             for (uint32_t mb = 0; mb < 2; ++mb) {
@@ -574,22 +614,23 @@ sa_fused_tc_kernel(const FusedParams p) {
                         if (NI == 2) {
                             tc::tc_fence_before();
                             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(turn_u + 8 * me) : "memory");
-                            ++own;
                         }
                         if (me == 0) FZ_TRACE(3, 6, it, g * 50 + c);
-                        // the producer that fills this operand slot next: a loader group or the epilogue warps
-                        const uint32_t next_prod = g_q < (uint32_t)nc0 ? (LG == 1 ? 0u : (g_it * (uint32_t)nc0 + g_q) % LG) : (uint32_t)LG;
                         tc::umma_commit_u32(a_grant_u + 8 * (next_prod * FZ_MAX_RING + a_slot));
                         tc::umma_commit_u32(b_empty_u + 8 * b_slot);
                         if (NI == 2 && c == 0) tc::umma_commit_u32(init_done_u + 8 * g);
                         if (me == 0) FZ_TRACE(3, 7, it, g * 50 + c);
+                        }      // elected lane
+                        if (NI == 2) ++own;
+                        __syncwarp();
                         }
                         if (++a_slot == sa) { a_slot = 0; a_phase ^= 1; }
                         if (++b_slot == sb) { b_slot = 0; b_phase ^= 1; }
                         if (++g_q == Q) { g_q = 0; ++g_it; }
                         par ^= 1u;
                     }
-                    tc::umma_commit_u32(acc_full_u + 8 * g);      // this issuer's UMMAs into accumulator g are done (all of them with NI == 1)
+                    if (tc::elect_one()) tc::umma_commit_u32(acc_full_u + 8 * g);      // this issuer's UMMAs into accumulator g are done (all of them with NI == 1)
+                    __syncwarp();
                 }
             }
         }
@@ -735,6 +776,7 @@ sa_fused_tc_kernel(const FusedParams p) {
         }
     }
 
+    if (MODE == FZ_MODE_F16X3 && p.range_flag != nullptr && tc::f16x2_overflowed(hmax)) atomicOr(p.range_flag, 1);
     tc::tc_fence_before();
     __syncthreads();
     if (warp == ISSUER_WARP) {
@@ -761,7 +803,7 @@ static FusedPlan fused_plan(int mode, const int32_t *cout) {
     pl.ok = cout[0] <= 256 && cout[1] <= 256 && ext <= 512;
     pl.occ = ext <= 256 ? 2 : 1;
     if (const char *e = getenv("EV2H_FUSED_OCC")) { if (e[0] == '1') pl.occ = 1; }     // experiment switch: one CTA per SM, 32-channel chunks
-    pl.kc = (pl.occ == 2 && mode != FZ_MODE_BF16) ? 16 : 32;
+    pl.kc = (pl.occ == 2 && !fz_two_byte(mode)) ? 16 : 32;
     pl.tmem_cols = 32;
     while (pl.tmem_cols < ext) pl.tmem_cols *= 2;
     return pl;
@@ -782,61 +824,62 @@ extern "C" int ev2h_fused_set_debug_buffer(void *buf) { ev2h::g_fused_dbg = (lon
 
 extern "C" int ev2h_sa_msg_fused_kc(int mode, const int32_t *cout_host) {
     using namespace ev2h;
-    if (!cout_host || (mode != FZ_MODE_BF16 && mode != FZ_MODE_TF32X3 && mode != FZ_MODE_MIXED)) return -1;
+    if (!cout_host || mode < FZ_MODE_BF16 || mode > FZ_MODE_F16X3) return -1;
     const FusedPlan pl = fused_plan(mode, cout_host);
     return pl.ok ? pl.kc : -1;
 }
 
 static int sa_msg_fused_impl(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
-    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *pts8, int D, const float *first_wt_host, int first_ld, const float *first_bias_host,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
-    float *out_rows, int ld_out, int out_col, int mode,
+    float *out_rows, int ld_out, int out_col, int mode, int32_t *range_flag,
     const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev, ev2h_stream_t stream);
 
 extern "C" int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
-    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *pts8, int D, const float *first_wt_host, int first_ld, const float *first_bias_host,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
-    float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream) {
-    return sa_msg_fused_impl(idx, idx_ld, k_off, centres_rows, B, N, S, K, pts8, D, first_wt, first_ld, first_bias, P, ld_p, p_col,
-                             C, ld_c, c_col, c1, cout_host, w_packed_host, bias_host, out_rows, ld_out, out_col, mode,
+    float *out_rows, int ld_out, int out_col, int mode, int32_t *range_flag, ev2h_stream_t stream) {
+    return sa_msg_fused_impl(idx, idx_ld, k_off, centres_rows, B, N, S, K, pts8, D, first_wt_host, first_ld, first_bias_host, P, ld_p, p_col,
+                             C, ld_c, c_col, c1, cout_host, w_packed_host, bias_host, out_rows, ld_out, out_col, mode, range_flag,
                              nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int ev2h_sa_msg_fused_compact_tc(
     const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev,
     const float *centres_rows, int B, int N, int S, int K,
-    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *pts8, int D, const float *first_wt_host, int first_ld, const float *first_bias_host,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
-    float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream) {
+    float *out_rows, int ld_out, int out_col, int mode, int32_t *range_flag, ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(rowmap && blockgroup && n_rows_dev, "ev2h_sa_msg_fused_compact_tc: null row list");
-    return sa_msg_fused_impl(rowmap, K, 0, centres_rows, B, N, S, K, pts8, D, first_wt, first_ld, first_bias, P, ld_p, p_col,
-                             C, ld_c, c_col, c1, cout_host, w_packed_host, bias_host, out_rows, ld_out, out_col, mode,
+    return sa_msg_fused_impl(rowmap, K, 0, centres_rows, B, N, S, K, pts8, D, first_wt_host, first_ld, first_bias_host, P, ld_p, p_col,
+                             C, ld_c, c_col, c1, cout_host, w_packed_host, bias_host, out_rows, ld_out, out_col, mode, range_flag,
                              rowmap, blockgroup, n_rows_dev, stream);
 }
 
 static int sa_msg_fused_impl(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
-    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *pts8, int D, const float *first_wt_host, int first_ld, const float *first_bias_host,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
-    float *out_rows, int ld_out, int out_col, int mode,
+    float *out_rows, int ld_out, int out_col, int mode, int32_t *range_flag,
     const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev, ev2h_stream_t stream) {
     using namespace ev2h;
     EV2H_REQUIRE(idx && centres_rows && out_rows && cout_host && w_packed_host && bias_host, "ev2h_sa_msg_fused_tc: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0 && k_off >= 0 && k_off + K <= idx_ld && c1 > 0, "ev2h_sa_msg_fused_tc: bad sizes");
-    EV2H_REQUIRE(mode == FZ_MODE_BF16 || mode == FZ_MODE_TF32X3 || mode == FZ_MODE_MIXED, "ev2h_sa_msg_fused_tc: unknown mode %d", mode);
+    EV2H_REQUIRE(mode >= FZ_MODE_BF16 && mode <= FZ_MODE_F16X3, "ev2h_sa_msg_fused_tc: unknown mode %d", mode);
     if (K != 32 && K != 64 && K != 128)
         return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: K=%d (supported: 32, 64, 128)", K);
     const bool per_point = P != nullptr;
     if (!per_point) {
-        EV2H_REQUIRE(pts8 && first_wt && first_bias && first_ld >= c1, "ev2h_sa_msg_fused_tc: gather mode needs pts8 and the folded layer-1 weights");
+        EV2H_REQUIRE(pts8 && first_wt_host && first_bias_host && first_ld >= c1, "ev2h_sa_msg_fused_tc: gather mode needs pts8 and the folded layer-1 weights (host copies)");
         if (D < 0 || D + 3 > 8) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: gather mode needs D+3 <= 8 input channels (D=%d)", D);
+        if (c1 > FZ_W1_MAX) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: gather mode evaluates at most %d layer-1 channels in the loaders (got %d)", FZ_W1_MAX, c1);
     } else {
         EV2H_REQUIRE(C != nullptr && ld_p % 4 == 0 && ld_c % 4 == 0 && p_col % 4 == 0 && c_col % 4 == 0,
                      "ev2h_sa_msg_fused_tc: per-point tables must be float4 addressable");
@@ -846,13 +889,20 @@ static int sa_msg_fused_impl(
     const FusedPlan pl = fused_plan(mode, cout_host);
     if (!pl.ok) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: layer widths (%d, %d) exceed 256 or the 512 TMEM columns", cout_host[0], cout_host[1]);
     const int KC = pl.kc;
-    const int EB = mode == FZ_MODE_BF16 ? 2 : 4, PARTS = mode == FZ_MODE_BF16 ? 1 : 2, UMMA_K = 32 / EB;
+    const int EB = fz_two_byte(mode) ? 2 : 4, PARTS = mode == FZ_MODE_BF16 ? 1 : 2, UMMA_K = 32 / EB;
 
     FusedParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
     p.rowmap = rowmap; p.blockgroup = blockgroup; p.n_rows_dev = n_rows_dev;
-    p.per_point = per_point ? 1 : 0; p.pts8 = pts8; p.D = D; p.first_wt = first_wt; p.first_ld = first_ld; p.first_bias = first_bias;
+    p.per_point = per_point ? 1 : 0; p.pts8 = pts8; p.D = D; p.range_flag = range_flag;
+    if (!per_point) {
+        // layer-1 weights into the parameter block: channel pairs interleaved, [pair][k][2], so one 64-bit word feeds one packed FMA
+        for (int ch = 0; ch < c1; ++ch) {
+            for (int k = 0; k < 8; ++k) p.w1c[(ch >> 1) * 16 + k * 2 + (ch & 1)] = k < D + 3 ? first_wt_host[(size_t)k * first_ld + ch] : 0.f;
+            p.b1c[ch] = first_bias_host[ch];
+        }
+    }
     p.P = P; p.ld_p = ld_p; p.p_col = p_col; p.C = C; p.ld_c = ld_c; p.c_col = c_col; p.c1 = c1;
     p.tmem_cols = pl.tmem_cols; p.mb3 = pl.mb3;
     int boff = 0, max_n = 0;
@@ -875,8 +925,7 @@ static int sa_msg_fused_impl(
 
     p.a_slot_bytes = PARTS * FZ_BLOCK_M * KC * EB;
     p.b_slot_bytes = PARTS * max_n * KC * EB;
-    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 4 * FZ_GEMMS) * 8 + 16 + boff * 4 +
-                     (per_point ? 0 : p.n_chunks[0] * KC * 9 * 4);
+    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 4 * FZ_GEMMS) * 8 + 16 + boff * 4;
     int occ = pl.occ;
     int budget = (occ == 2 ? 113 : 227) * 1024 - tail - 512;
     if (occ == 2 && budget < 2 * p.a_slot_bytes + 2 * p.b_slot_bytes) { occ = 1; budget = 227 * 1024 - tail - 512; }
@@ -906,6 +955,11 @@ static int sa_msg_fused_impl(
         if (KC == 16) return occ == 2 ? launch_fused<FZ_MODE_TF32X3, 16, 1, 2>(p, smem, grid, st)
                                       : launch_fused<FZ_MODE_TF32X3, 16, 1, 1>(p, smem, grid, st);
         return launch_fused<FZ_MODE_TF32X3, 32, 2, 1>(p, smem, grid, st);
+    }
+    if (mode == FZ_MODE_F16X3) {
+        if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_F16X3, 32, 1, 2>(p, smem, grid, st)
+                                         : launch_fused<FZ_MODE_F16X3, 32, 1, 1>(p, smem, grid, st);
+        return launch_fused<FZ_MODE_F16X3, 32, 2, 1>(p, smem, grid, st);
     }
     if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_BF16, 32, 1, 2>(p, smem, grid, st)
                                      : launch_fused<FZ_MODE_BF16, 32, 1, 1>(p, smem, grid, st);

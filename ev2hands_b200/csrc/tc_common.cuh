@@ -273,5 +273,23 @@ __device__ __forceinline__ void split_tf32x2(float x0, float x1, float &h0, floa
     unpack2(sub2(pack2(x0, x1), pack2(h0, h1)), l0, l1);
 }
 
+// fp16 split: x = hi + lo with hi = fp16(x) (11 significant bits) and lo = fp16(x - hi) (the next 11): the pair
+// carries ~22 bits, and hi*hi + hi*lo + lo*hi (three kind::f16 UMMAs, fp32 accumulate) is an fp32-level product at
+// three quarters of the tensor time and half the operand bytes of the tf32 + 2 bf16 split.  x - hi is exact in fp32.
+// Domain: |x| < 65520 (fp16 range); values below 2^-14 lose relative, not absolute, precision (lo goes subnormal).
+// Two values per call; the first one lands in the low half of each packed word.
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &h, uint32_t &l) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    float f0, f1;
+    asm("{\n.reg .f16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(f0), "=f"(f1) : "r"(h));
+    float r0, r1;
+    unpack2(sub2(pack2(x0, x1), pack2(f0, f1)), r0, r1);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+}
+// running maximum of packed non-negative fp16 pairs (bit patterns of values >= +0 order like unsigned integers)
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+// true if either half is +inf / NaN (exponent all ones)
+__device__ __forceinline__ bool f16x2_overflowed(uint32_t m) { return ((m & 0x7c00u) == 0x7c00u) || ((m & 0x7c000000u) == 0x7c000000u); }
+
 }  // namespace tc
 }  // namespace ev2h

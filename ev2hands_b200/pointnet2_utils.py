@@ -46,9 +46,13 @@ _mlp_precision = os.environ.get("EV2H_MLP", "tf32x3")
 # The fused grouping + MLP + max-pool kernel (sa_fused_tc.cu) is used for every scale it
 # covers when a tensor-core precision is selected; EV2H_FUSED=0 forces the layer-by-layer path.
 _FUSED_ENABLED = os.environ.get("EV2H_FUSED", "1") != "0"
-# fp32-level precision ("tf32x3") in the fused kernel: tf32 hi*hi + bf16 correction products (default), or
-# three tf32 products with EV2H_TF32X3_PURE=1.
+# fp32-level precision ("tf32x3") on the tensor cores, three split products per multiply:
+#   EV2H_SPLIT=f16  (default) fp16 hi/lo pairs, three kind::f16 products - 3 tensor time units and 4 operand bytes per
+#                   element; activations must stay below 65520 (ev2hands_b200.check_numeric_range() reports overflows)
+#   EV2H_SPLIT=tf32 tf32 hi*hi + two bf16 correction products - 4 units, 8 bytes, fp32 exponent range (round 1's default)
+#   EV2H_TF32X3_PURE=1  three tf32 products - 6 units
 _TF32X3_PURE = os.environ.get("EV2H_TF32X3_PURE", "0") == "1"
+_SPLIT = os.environ.get("EV2H_SPLIT", "f16")
 # Run the fused kernel over compacted rows (padded duplicate neighbours skipped; bit-identical results).
 _COMPACT = os.environ.get("EV2H_COMPACT", "1") != "0"
 # ... and over exact-duplicate points only once (event windows are sampled with replacement).
@@ -234,8 +238,27 @@ def _layer_mode(mode):
     """arithmetic of the per-layer tensor-core kernel for the selected precision: fp32-level = tf32 hi*hi + two bf16
     correction products (4 UMMA time units per 16 channels instead of the 6 of three tf32 products)"""
     if mode == _capi.TC_TF32X3 and _LINEAR_MIXED and not _TF32X3_PURE:
-        return _capi.TC_TF32_BF16C
+        return _capi.TC_F16X3 if _SPLIT == "f16" else _capi.TC_TF32_BF16C
     return mode
+
+
+def _fused_mode(mode):
+    """arithmetic of the fused kernel for the selected precision (see _SPLIT)"""
+    if mode == _capi.TC_TF32X3 and not _TF32X3_PURE:
+        return _capi.TC_F16X3 if _SPLIT == "f16" else _capi.TC_TF32_BF16C
+    return mode
+
+
+def _host_first_layer(L0):
+    """host copy of a folded first layer (rows 0..7 of wt, bias): the gather mode of the fused kernel takes them as kernel
+    parameters.  Made once per fold (one device-to-host copy), never per step."""
+    h = L0.get("host")
+    if h is None:
+        with _CACHE_LOCK:
+            h = L0.get("host")
+            if h is None:
+                h = L0["host"] = (L0["wt"][:8].contiguous().cpu(), L0["bias"].cpu())
+    return h
 
 
 def _mlp_rows(x, M, ld_x, layers, pool_rows, out, ld_out, out_col):
@@ -464,7 +487,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         out_rows = torch.zeros((B, S, ld_out), dtype=torch.float32, device=xyz.device)
         out_rows[:, :, c_total:c_total + 3] = centres_rows
         mode = {"tf32x3": _capi.TC_TF32X3, "bf16": _capi.TC_BF16}.get(_mlp_precision)
-        fmode = _capi.TC_TF32_BF16C if (mode == _capi.TC_TF32X3 and not _TF32X3_PURE) else mode   # fused kernel's mode
+        fmode = _fused_mode(mode)
         all_layers = [self._folded[i].get(self.conv_blocks[i], self.bn_blocks[i]) for i in range(len(self.nsample_list))]
         widths = [[L["cout"] for L in layers] for layers in all_layers]
 
@@ -547,8 +570,8 @@ class PointNetSetAbstractionMsg(nn.Module):
                     if key not in L["packed"]:
                         L["packed"][key] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], fmode, kc, key[2])
                     packed.append(L["packed"][key])
-                _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D,
-                                   None if per_point else layers[0]["wt"], None if per_point else layers[0]["bias"],
+                w1_host, b1_host = (None, None) if per_point else _host_first_layer(layers[0])
+                _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D, w1_host, b1_host,
                                    P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
                                    C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
                                    layers[0]["cout"], [L["cout"] for L in use], packed, [L["bias"] for L in use],

@@ -226,6 +226,8 @@ EV2H_API int ev2h_linear_f32(const float *x, int64_t M, int ld_x, int Cin, const
 #define EV2H_TC_BF16 0
 #define EV2H_TC_TF32X3 1
 #define EV2H_TC_TF32_BF16C 2
+#define EV2H_TC_F16X3 3      /* x = hi + lo, w = hi + lo as fp16 pairs, three kind::f16 products: fp32-level accuracy for
+                              * |activations| < 65520 (an overflow raises the fused kernel's range flag) */
 EV2H_API int64_t ev2h_tc_packed_bytes(int Cin, int Cout, int mode);
 EV2H_API int ev2h_tc_pack_weights(const float *wt, int ld_w, int Cin, int Cout, int mode, void *packed,
                                   ev2h_stream_t stream);
@@ -253,8 +255,10 @@ EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, c
  * Layer 1 (width c1), one of:
  *   gather mode    (P == NULL): pts8 [B,N,8] rows = [features(D) | xyz | 0], D + 3 <= 8; the kernel
  *                  forms [features | xyz - centre] as the reference does and evaluates layer 1 in
- *                  exact fp32 on the CUDA cores from first_wt / first_bias (the folded map written
- *                  by ev2h_fold_conv_bn_f32, row length first_ld).
+ *                  exact fp32 on the CUDA cores from first_wt_host / first_bias_host: HOST copies of
+ *                  the folded map written by ev2h_fold_conv_bn_f32 (row length first_ld, c1 <= 128).
+ *                  They travel as kernel parameters (constant bank), which keeps the loaders'
+ *                  weight reads off the shared-memory pipe the tensor cores' operands saturate.
  *   per-point mode (P != NULL): layer 1 was evaluated per point / per centre:
  *                  P [B*N, ld_p] = W1' [features; xyz] + b1' (ev2h_linear_f32) at column p_col,
  *                  C [B*S, ld_c] = W1'_xyz centre at column c_col; the kernel forms
@@ -262,13 +266,16 @@ EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, c
  * Layers 2 and 3 run on the tensor cores: cout_host[2] their widths, w_packed_host[2] their
  * ev2h_tc_pack_weights_kc images (kc from ev2h_sa_msg_fused_kc), bias_host[2] their folded biases
  * (device pointers in host arrays).  out_rows [B*S, ld_out]: the pooled features of this scale
- * are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3 / EV2H_TC_TF32_BF16C. */
+ * are written at column out_col.  mode: EV2H_TC_BF16 / EV2H_TC_TF32X3 / EV2H_TC_TF32_BF16C / EV2H_TC_F16X3.
+ * range_flag (device int32, may be NULL): bit 0 is set when an EV2H_TC_F16X3 operand left the fp16 range.
+ * Deviation from the reference (all modes): ReLU and the max-pool are evaluated with fmaxf / an integer atomic
+ * max on zero-initialised output, so a NaN activation becomes 0 where F.relu / torch.max would propagate it. */
 EV2H_API int ev2h_sa_msg_fused_tc(
     const int32_t *idx, int idx_ld, int k_off, const float *centres_rows, int B, int N, int S, int K,
-    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *pts8, int D, const float *first_wt_host, int first_ld, const float *first_bias_host,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
-    float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream);
+    float *out_rows, int ld_out, int out_col, int mode, int32_t *range_flag, ev2h_stream_t stream);
 
 /* The fused kernel over a compacted row list (ev2h_group_compact_i32) instead of the dense [B,S,K] index
  * block: same arguments otherwise, bit-identical pooled features (out_rows must be zero-filled: groups that
@@ -276,10 +283,10 @@ EV2H_API int ev2h_sa_msg_fused_tc(
 EV2H_API int ev2h_sa_msg_fused_compact_tc(
     const int32_t *rowmap, const int32_t *blockgroup, const int32_t *n_rows_dev,
     const float *centres_rows, int B, int N, int S, int K,
-    const float *pts8, int D, const float *first_wt, int first_ld, const float *first_bias,
+    const float *pts8, int D, const float *first_wt_host, int first_ld, const float *first_bias_host,
     const float *P, int ld_p, int p_col, const float *C, int ld_c, int c_col,
     int c1, const int32_t *cout_host, const void *const *w_packed_host, const float *const *bias_host,
-    float *out_rows, int ld_out, int out_col, int mode, ev2h_stream_t stream);
+    float *out_rows, int ld_out, int out_col, int mode, int32_t *range_flag, ev2h_stream_t stream);
 
 /* K-chunk length (16 or 32) the fused kernel uses for layers of widths cout_host[2], i.e. the kc
  * to pack their weights with; -1 if the pair is not supported. */

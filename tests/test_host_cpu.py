@@ -215,3 +215,61 @@ def test_one_line_change_builds_the_real_tehnet_and_loads_its_checkpoint(monkeyp
     # the patched net refuses to run on the CPU instead of silently falling back
     with pytest.raises(RuntimeError, match="CUDA"):
         patched.eval()(torch.zeros(1, 5, 2048), {"left": None, "right": None})
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MODEL_DIR), reason="the reference tree exists in the build container only")
+def test_tehnet_wiring_has_the_reference_checkpoint_layout_and_attention_matches(monkeypatch):
+    """ev2hands_b200.tehnet.TEHNet (the wiring the training configuration and rows N2 / N4 run on): same state_dict
+    names, shapes and dtypes as the reference's TEHNet, strict loads in both directions, and AttentionBlock equal to
+    the reference's (TEHNet.py:9-27) on random inputs."""
+    monkeypatch.setenv("ERPC", "1")
+    from ev2hands_b200 import tehnet
+    ref_mod = _load_tehnet("refmodel_stock2")
+    ref = ref_mod.TEHNet(n_pose_params=6)
+    ours = tehnet.TEHNet(n_pose_params=6)
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    ours.load_state_dict(a, strict=True)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    torch.manual_seed(1)
+    key, val, qry = torch.randn(2, 4, 64), torch.randn(2, 256, 64), torch.randn(2, 256, 64)
+    assert torch.allclose(tehnet.AttentionBlock()(key, val, qry), ref_mod.AttentionBlock()(key, val, qry), rtol=1e-5, atol=1e-6)
+    # the heads after the encoder (classifier, query convs, attention) agree with the reference's on CPU
+    ref.eval(), ours.eval()
+    feats = torch.randn(2, 256, 64)
+    with torch.no_grad():
+        for name in ("classifier", "left_query_conv", "right_query_conv"):
+            assert torch.equal(getattr(ours, name)(feats), getattr(ref, name)(feats)), name
+
+
+def test_standin_mano_layer_and_training_losses():
+    """the MANO-shaped stand-in (parity unpinned) has MANO's interface and is differentiable; the criterion
+    (losses.py:145-206 minus loss_interpen) gives finite terms with the reference's names"""
+    from ev2hands_b200 import tehnet
+    hands = tehnet.create_standin_mano_layers("cpu", n_cmps=6)
+    B = 3
+    go = torch.randn(B, 3, requires_grad=True)
+    out = hands["left"](global_orient=go, hand_pose=torch.randn(B, 6), betas=torch.randn(B, 10), transl=torch.randn(B, 3))
+    assert out.vertices.shape == (B, 778, 3) and out.joints.shape == (B, 21, 3)
+    assert hands["left"].faces.shape == (1538, 3) and hands["left"].shapedirs.shape == (778, 3, 10)
+    out.joints.sum().backward()
+    assert torch.isfinite(go.grad).all() and go.grad.abs().sum() > 0
+    # zero pose / shape / translation: the template, joints from the regressor
+    z = hands["right"](global_orient=torch.zeros(1, 3), hand_pose=torch.zeros(1, 6) , betas=torch.zeros(1, 10), transl=torch.zeros(1, 3))
+    again = hands["right"](global_orient=torch.zeros(1, 3), hand_pose=torch.zeros(1, 6), betas=torch.zeros(1, 10), transl=torch.ones(1, 3))
+    assert torch.allclose(again.vertices, z.vertices + 1, atol=1e-6) and torch.allclose(again.joints, z.joints + 1, atol=1e-6)
+    batch = tehnet.make_training_batch(B, 256, seed=3)
+    assert batch["events"].shape == (B, 5, 256) and batch["class_logits"].shape == (B, 256) and batch["handedness"].shape == (B, 2)
+    outs = {"class_logits": torch.randn(B, 4, 256, requires_grad=True)}
+    for side in ("left", "right"):
+        p = {"global_orient": torch.randn(B, 3), "hand_pose": torch.randn(B, 6), "betas": torch.randn(B, 10), "transl": torch.randn(B, 3)}
+        o = hands[side](**p)
+        outs[side] = dict(p, vertices=o.vertices, j3d=o.joints)
+    losses = tehnet.training_losses(outs, batch, hands)
+    assert set(losses) == {"loss_inter_shape", "loss_inter_transl", "loss_inter_j3d", "loss_global_orient", "loss_hand_pose",
+                           "loss_rj3d", "loss_j3d", "loss_shape", "loss_transl", "loss_class_logits"}
+    total = sum(losses.values())
+    assert torch.isfinite(total)
+    total.backward()
+    assert outs["class_logits"].grad.abs().sum() > 0

@@ -101,3 +101,65 @@ def test_window_shards_reproduce_the_unsharded_batch():
         assert np.array_equal(np.concatenate(parts), whole, equal_nan=True)
     with pytest.raises(ValueError):
         sharding.shard_windows([0, 1], [5], 0, 1)
+
+
+# ------------------------------------------------------------------ training step: bucketed gradient exchange ----
+def _mlp():
+    torch.manual_seed(0)          # same initial weights on every rank, like the replicas of nn.DataParallel
+    return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16), torch.nn.ReLU(),
+                               torch.nn.Linear(16, 3), torch.nn.ReLU(), torch.nn.Linear(3, 2, bias=False))
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ev2hands_b200.trainer import BucketedGradReducer
+    torch.set_num_threads(1)
+    net = _mlp()
+    net[6].weight.requires_grad_(True)
+    red = BucketedGradReducer(net.parameters(), n_buckets=3)
+    assert len(red.buckets) >= 2 and red.buckets[0][0] == 0 and red.buckets[-1][1] == red.flat.numel()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    x_all = torch.from_numpy(np.random.RandomState(5).randn(8, 6).astype(np.float32))
+    (x,) = sharding.shard((x_all,), rank, world)
+    for step in range(3):
+        red.zero_grad()
+        out = net(x)
+        # step 1 leaves the last layer out of the loss: its bucket gets no hook and must be flushed by finish()
+        loss = out.pow(2).mean() if step != 1 else net[:6](x).pow(2).mean()
+        loss.backward()
+        for p in net.parameters():                        # gradients live in the flat buffer
+            assert p.grad.data_ptr() >= red.flat.data_ptr() and p.grad.data_ptr() < red.flat.data_ptr() + red.bytes
+        red.finish()
+        opt.step()
+    torch.save([p.detach().clone() for p in net.parameters()], os.path.join(out_dir, "params_%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_exchange_equals_full_batch_training(tmp_path):
+    """world_size-2 gloo: per-rank shards + bucketed all-reduce (launched from backward hooks, AVG) must reproduce
+    single-process training on the whole batch (equal shard sizes: mean of shard means = batch mean), and keep
+    the replicas identical."""
+    world = 2
+    mp.spawn(_train_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [torch.load(os.path.join(str(tmp_path), "params_%d.pt" % r)) for r in range(world)]
+    for a, b in zip(*got):
+        assert torch.equal(a, b)
+    net = _mlp()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    x_all = torch.from_numpy(np.random.RandomState(5).randn(8, 6).astype(np.float32))
+    for step in range(3):
+        opt.zero_grad(set_to_none=False)
+        for p in net.parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        if step != 1:
+            loss = 0.5 * (net(x_all[:4]).pow(2).mean() + net(x_all[4:]).pow(2).mean())
+        else:
+            loss = 0.5 * (net[:6](x_all[:4]).pow(2).mean() + net[:6](x_all[4:]).pow(2).mean())
+        loss.backward()
+        opt.step()
+    for a, b in zip(got[0], net.parameters()):
+        assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-7)
