@@ -15,6 +15,13 @@
 
 namespace ev2h {
 
+// packed fp32x2 arithmetic (sm_100): both halves are IEEE round-to-nearest operations, bit-identical to the scalar ones
+__device__ __forceinline__ uint64_t pack2f(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2f(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t add2f(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t fma2f(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
 constexpr int kMaxScales = 4;
 constexpr int kBqCentres = 32;    // centres per CTA (one per lane)
 constexpr int kBqSegs = 8;        // point ranges scanned in parallel (one per warp)
@@ -53,7 +60,11 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
     // Optional second list (first_flag != nullptr): the same first-K hits without exact duplicates of an earlier
     // point (first_flag[b,n] = 0), in index order, for the row compaction; ucnt_out = its length.
     // The flag travels in the sign bit of the staged |p|^2 (a sum of squares is never negative), read back with fabsf.
-    __shared__ float4 pts[kBqTile];
+    // staged points, two per record pair so that the distance runs on packed fp32x2 arithmetic (two IEEE operations per
+    // instruction, each half rounded exactly like the scalar instruction): ptsA[i] = (x0, x1, y0, y1), ptsB[i] =
+    // (z0, z1, |p0|^2, |p1|^2) for points 2i, 2i + 1 of the tile; flagw = first-occurrence bits, one word per 32 points
+    __shared__ float4 ptsA[kBqTile / 2], ptsB[kBqTile / 2];
+    __shared__ uint32_t flagw[kBqTile / 32];
     __shared__ int ucnt_s[kBqSegs][NS][kBqCentres];
     __shared__ int uemit_s[NS][kBqCentres];              // unique hits written (i.e. within the first K hits), summed over ranges
     __shared__ int cnt_s[kBqSegs][NS][kBqCentres];      // hits of this tile per (range, radius, centre)
@@ -85,15 +96,24 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
     for (int t0 = 0; t0 < N; t0 += kBqTile) {
         const int n_tile = min(kBqTile, N - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < n_tile; i += kBqCentres * kBqSegs) {
-            const int64_t g = (int64_t)(t0 + i) * sn;
-            const float x = base[g], y = base[sc + g], z = base[2 * sc + g];
+        for (int i = threadIdx.x; i < ((n_tile + 31) & ~31); i += kBqCentres * kBqSegs) {
+            // past the end of the tile: a point far outside every radius (finite arithmetic, never a hit)
+            float x = 1e18f, y = 1e18f, z = 1e18f;
+            bool fresh = false;
+            if (i < n_tile) {
+                const int64_t g = (int64_t)(t0 + i) * sn;
+                x = base[g]; y = base[sc + g]; z = base[2 * sc + g];
+                fresh = !(dedup && first_flag[(int64_t)b * N + t0 + i] == 0);
+            }
             const float nn = sq_norm3(x, y, z);
-            const bool dup = dedup && first_flag[(int64_t)b * N + t0 + i] == 0;
-            pts[i] = make_float4(x, y, z, dup ? __uint_as_float(__float_as_uint(nn) | 0x80000000u) : nn);
+            float *pa = reinterpret_cast<float *>(&ptsA[i >> 1]) + (i & 1), *pb = reinterpret_cast<float *>(&ptsB[i >> 1]) + (i & 1);
+            pa[0] = x; pa[2] = y; pb[0] = z; pb[2] = nn;
+            const uint32_t fw = __ballot_sync(0xffffffffu, fresh);        // i / 32 is the same for the whole warp
+            if (lane == 0) flagw[i >> 5] = fw;
         }
         __syncthreads();
-        const int per = (n_tile + kBqSegs - 1) / kBqSegs;              // <= kBqTile / kBqSegs = 32 * WORDS points
+        // ranges are whole 32-point words (pairs never straddle a range)
+        const int per = (((n_tile + kBqSegs - 1) / kBqSegs) + 31) & ~31;              // <= kBqTile / kBqSegs = 32 * WORDS points
         const int i0 = min(seg * per, n_tile), i1 = min(i0 + per, n_tile);
 
         // pass 1: one distance evaluation per (centre, point); the hits of this range are kept as bit masks
@@ -103,24 +123,39 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
         int cnt[NS], fst[NS], ucnt[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) { cnt[k] = 0; fst[k] = N; ucnt[k] = 0; }
+        const uint64_t qx2 = pack2f(qx, qx), qy2 = pack2f(qy, qy), qz2 = pack2f(qz, qz), qn2 = pack2f(qn, qn), m2 = pack2f(-2.0f, -2.0f);
 #pragma unroll
         for (int w = 0; w < WORDS; ++w) {
-            // first-occurrence flags of the word's 32 points: the point is the same for every lane, so each lane
-            // looks at one point and a ballot assembles the word
-            const int ip = i0 + 32 * w + lane;
-            fl[w] = __ballot_sync(0xffffffffu, ip < i1 && (__float_as_uint(pts[ip].w) >> 31) == 0u);
             uint32_t m[NS];
 #pragma unroll
             for (int k = 0; k < NS; ++k) m[k] = 0u;
-            const int nb = min(32, i1 - (i0 + 32 * w));
-            for (int j = 0; j < nb; ++j) {
-                float4 pw = pts[i0 + 32 * w + j];
-                pw.w = fabsf(pw.w);
-                const float d = sqdist_expanded(qx, qy, qz, qn, pw);
-                if (d > prm.r2_max) continue;            // outside every radius
+            fl[w] = 0u;
+            if (i0 + 32 * w < i1) {
+                fl[w] = flagw[(i0 >> 5) + w];
+                const int pbase = (i0 >> 1) + 16 * w;
+#pragma unroll 4
+                for (int j = 0; j < 32; j += 2) {
+                    const float4 a = ptsA[pbase + (j >> 1)], c = ptsB[pbase + (j >> 1)];
+                    // sqdist_expanded for two points at once: x*x', two FMAs, * -2, + |q|^2, + |p|^2 (geom.cuh)
+                    uint64_t t = mul2f(qx2, pack2f(a.x, a.y));
+                    t = fma2f(qy2, pack2f(a.z, a.w), t);
+                    t = fma2f(qz2, pack2f(c.x, c.y), t);
+                    t = mul2f(m2, t);
+                    t = add2f(t, qn2);
+                    t = add2f(t, pack2f(c.z, c.w));
+                    float d0, d1;
+                    unpack2f(t, d0, d1);
+                    if (!(d0 > prm.r2_max)) {
 #pragma unroll
-                for (int k = 0; k < NS; ++k)
-                    if (!(d > prm.r2[k])) m[k] |= 1u << j;    // group_idx[sqrdists > r**2] = N  (:102)
+                        for (int k = 0; k < NS; ++k)
+                            if (!(d0 > prm.r2[k])) m[k] |= 1u << j;          // group_idx[sqrdists > r**2] = N  (:102)
+                    }
+                    if (!(d1 > prm.r2_max)) {
+#pragma unroll
+                        for (int k = 0; k < NS; ++k)
+                            if (!(d1 > prm.r2[k])) m[k] |= 2u << j;
+                    }
+                }
             }
 #pragma unroll
             for (int k = 0; k < NS; ++k) {

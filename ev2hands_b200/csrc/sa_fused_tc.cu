@@ -107,6 +107,7 @@ struct FusedParams {
     // rings
     int sa, sb, a_slot_bytes, b_slot_bytes;
     int32_t *range_flag;                         // optional: bit 0 set when an F16X3 operand left the fp16 range
+    int pool_loader;                             // 1: the loader warps pool layer 3 (experiment), 0: the epilogue warps do
     long long *dbg;     // optional trace buffer (EV2H_FUSED_TRACE builds only, tools/fused_trace.py)
 };
 
@@ -169,8 +170,12 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     uint64_t *acc_empty = acc_full + FZ_GEMMS;           // [2]
     uint64_t *init_done = acc_empty + FZ_GEMMS;          // [2] two issuers: chunk 0 of a layer (the accumulator's overwrite) has completed
     uint64_t *turn = init_done + FZ_GEMMS;               // [2] two issuers: turn[i] = issuer i has ISSUED another of its chunks
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(turn + FZ_GEMMS);
-    float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);          // [n0 + n1]; tail offset 464, 16-byte aligned
+    // layer 3's "accumulator full" when two loader groups pool ALTERNATE tiles (LG == 2, one 128-channel block): one
+    // barrier per tile parity, so that each group consumes every phase of the barrier it waits on (a parity wait that
+    // skips a phase returns at once on the phase in between)
+    uint64_t *acc_full1_alt = turn + FZ_GEMMS;           // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full1_alt + FZ_GEMMS);
+    float *bias_s = reinterpret_cast<float *>(tmem_slot + 4);          // [n0 + n1]; tail offset 480, 16-byte aligned
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef EV2H_FUSED_TRACE
@@ -189,8 +194,8 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
         }
         for (int s = 0; s < p.sb; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
         for (int g = 0; g < FZ_GEMMS; ++g) {
-            tc::mbar_init(acc_full + g, NI); tc::mbar_init(acc_empty + g, 128); tc::mbar_init(init_done + g, 1);
-            tc::mbar_init(turn + g, 1);
+            tc::mbar_init(acc_full + g, NI); tc::mbar_init(acc_empty + g, g == 1 && p.pool_loader && LG == 2 && p.mb3 == 2 ? 256 : 128); tc::mbar_init(init_done + g, 1);
+            tc::mbar_init(turn + g, 1); tc::mbar_init(acc_full1_alt + g, NI);
         }
         tc::fence_mbar_init();
     }
@@ -208,22 +213,24 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // fp32 values of one row -> operand chunk(s) in the K-major, no-swizzle UMMA layout.  Thread = row:
-    // consecutive threads write consecutive 16-byte pieces, conflict free.
-    auto store_row_chunk = [&](uint8_t *st, int r, const float (&v)[KC]) {
+    // 16 fp32 values of one row (channels j0 .. j0 + 15 of the K chunk, j0 a multiple of 16) -> operand pieces in the
+    // K-major, no-swizzle UMMA layout.  Thread = row: consecutive threads write consecutive 16-byte pieces, conflict
+    // free.  Producers work in 16-channel pieces so that at most 16 values (not KC) are live per thread.
+    auto store_row_16 = [&](uint8_t *st, int r, int j0, const float (&v)[16]) {
         if (MODE == FZ_MODE_MIXED) {
 #pragma unroll
-            for (int c8 = 0; c8 < KC / 8; ++c8) {
+            for (int c = 0; c < 2; ++c) {
+                const int c8 = j0 / 8 + c;
                 float4 h0, l0, h1, l1;
-                tc::split_tf32x2(v[8 * c8], v[8 * c8 + 1], h0.x, h0.y, l0.x, l0.y);
-                tc::split_tf32x2(v[8 * c8 + 2], v[8 * c8 + 3], h0.z, h0.w, l0.z, l0.w);
-                tc::split_tf32x2(v[8 * c8 + 4], v[8 * c8 + 5], h1.x, h1.y, l1.x, l1.y);
-                tc::split_tf32x2(v[8 * c8 + 6], v[8 * c8 + 7], h1.z, h1.w, l1.z, l1.w);
+                tc::split_tf32x2(v[8 * c], v[8 * c + 1], h0.x, h0.y, l0.x, l0.y);
+                tc::split_tf32x2(v[8 * c + 2], v[8 * c + 3], h0.z, h0.w, l0.z, l0.w);
+                tc::split_tf32x2(v[8 * c + 4], v[8 * c + 5], h1.x, h1.y, l1.x, l1.y);
+                tc::split_tf32x2(v[8 * c + 6], v[8 * c + 7], h1.z, h1.w, l1.z, l1.w);
                 *reinterpret_cast<float4 *>(st + (2 * c8) * CHUNK_ROWS_BYTES + r * 16) = h0;
                 *reinterpret_cast<float4 *>(st + (2 * c8 + 1) * CHUNK_ROWS_BYTES + r * 16) = h1;
                 uint4 xb, lb;
-                xb.x = tc::bf16x2(v[8 * c8], v[8 * c8 + 1]); xb.y = tc::bf16x2(v[8 * c8 + 2], v[8 * c8 + 3]);
-                xb.z = tc::bf16x2(v[8 * c8 + 4], v[8 * c8 + 5]); xb.w = tc::bf16x2(v[8 * c8 + 6], v[8 * c8 + 7]);
+                xb.x = tc::bf16x2(v[8 * c], v[8 * c + 1]); xb.y = tc::bf16x2(v[8 * c + 2], v[8 * c + 3]);
+                xb.z = tc::bf16x2(v[8 * c + 4], v[8 * c + 5]); xb.w = tc::bf16x2(v[8 * c + 6], v[8 * c + 7]);
                 lb.x = tc::bf16x2(l0.x, l0.y); lb.y = tc::bf16x2(l0.z, l0.w);
                 lb.z = tc::bf16x2(l1.x, l1.y); lb.w = tc::bf16x2(l1.z, l1.w);
                 *reinterpret_cast<uint4 *>(st + A_PART + c8 * CHUNK_ROWS_BYTES + r * 16) = xb;
@@ -231,36 +238,140 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
             }
         } else if (MODE == FZ_MODE_F16X3) {
 #pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {               // 8 channels = one 16-byte chunk of each part
+            for (int c = 0; c < 2; ++c) {                    // 8 channels = one 16-byte piece of each part
+                const int cc = j0 / 8 + c;
                 uint4 hb, lb;
-                tc::split_f16x2(v[8 * cc], v[8 * cc + 1], hb.x, lb.x); tc::split_f16x2(v[8 * cc + 2], v[8 * cc + 3], hb.y, lb.y);
-                tc::split_f16x2(v[8 * cc + 4], v[8 * cc + 5], hb.z, lb.z); tc::split_f16x2(v[8 * cc + 6], v[8 * cc + 7], hb.w, lb.w);
+                tc::split_f16x2(v[8 * c], v[8 * c + 1], hb.x, lb.x); tc::split_f16x2(v[8 * c + 2], v[8 * c + 3], hb.y, lb.y);
+                tc::split_f16x2(v[8 * c + 4], v[8 * c + 5], hb.z, lb.z); tc::split_f16x2(v[8 * c + 6], v[8 * c + 7], hb.w, lb.w);
                 hmax = tc::max_u16x2(tc::max_u16x2(hmax, tc::max_u16x2(hb.x, hb.y)), tc::max_u16x2(hb.z, hb.w));
                 *reinterpret_cast<uint4 *>(st + cc * CHUNK_ROWS_BYTES + r * 16) = hb;
                 *reinterpret_cast<uint4 *>(st + A_PART + cc * CHUNK_ROWS_BYTES + r * 16) = lb;
             }
         } else if (MODE == FZ_MODE_TF32X3) {
 #pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {
+            for (int c = 0; c < 4; ++c) {
+                const int cc = j0 / 4 + c;
                 float4 hi, lo;
-                tc::split_tf32x2(v[4 * cc], v[4 * cc + 1], hi.x, hi.y, lo.x, lo.y);
-                tc::split_tf32x2(v[4 * cc + 2], v[4 * cc + 3], hi.z, hi.w, lo.z, lo.w);
+                tc::split_tf32x2(v[4 * c], v[4 * c + 1], hi.x, hi.y, lo.x, lo.y);
+                tc::split_tf32x2(v[4 * c + 2], v[4 * c + 3], hi.z, hi.w, lo.z, lo.w);
                 *reinterpret_cast<float4 *>(st + cc * CHUNK_ROWS_BYTES + r * 16) = hi;
                 *reinterpret_cast<float4 *>(st + A_PART + cc * CHUNK_ROWS_BYTES + r * 16) = lo;
             }
         } else {
 #pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {
-                __nv_bfloat162 q0 = __floats2bfloat162_rn(v[8 * cc], v[8 * cc + 1]);
-                __nv_bfloat162 q1 = __floats2bfloat162_rn(v[8 * cc + 2], v[8 * cc + 3]);
-                __nv_bfloat162 q2 = __floats2bfloat162_rn(v[8 * cc + 4], v[8 * cc + 5]);
-                __nv_bfloat162 q3 = __floats2bfloat162_rn(v[8 * cc + 6], v[8 * cc + 7]);
+            for (int c = 0; c < 2; ++c) {
+                const int cc = j0 / 8 + c;
                 uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
-                pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
+                pk.x = tc::bf16x2(v[8 * c], v[8 * c + 1]); pk.y = tc::bf16x2(v[8 * c + 2], v[8 * c + 3]);
+                pk.z = tc::bf16x2(v[8 * c + 4], v[8 * c + 5]); pk.w = tc::bf16x2(v[8 * c + 6], v[8 * c + 7]);
                 *reinterpret_cast<uint4 *>(st + cc * CHUNK_ROWS_BYTES + r * 16) = pk;
             }
         }
+    };
+
+    // ---- max-pool of a tile's layer-3 accumulator.  Runs in the LOADER warps (warp w of a loader group owns TMEM lane
+    // quadrant w % 4, like an epilogue warp): the epilogue warps are the serial bottleneck of a tile (round-2 timeline:
+    // hand-off 5.2 k + pool 3.7 k cycles per tile in the same four warps, loaders mostly waiting for slot grants), so
+    // the pool of tile i now overlaps the hand-off of tile i + 1.  With two loader groups and two 128-channel blocks
+    // group g pools block g; with one block the groups alternate tiles.
+    const bool pool_loader = p.pool_loader != 0;
+    const int pool_groups = (pool_loader && LG == 2 && p.mb3 == 2) ? 2 : 1;
+    const bool pool_alt = pool_loader && LG == 2 && p.mb3 == 1;      // the two loader groups pool alternate tiles
+    auto pools_tile = [&](uint32_t it_, int grp_) { return pool_loader && (LG == 1 || pool_groups == 2 || (int)(it_ % LG) == grp_); };
+    auto pool_tile = [&](uint32_t it, int64_t tile, int q, int mb_lo, int mb_hi, bool ptrace) {
+        // layer 3 (transposed accumulator): lane = output channel, columns = the tile's rows.  The max over the K rows
+        // of a group = per-thread max over K columns; bias and ReLU commute with the max (both monotone) and are
+        // applied once per pooled value.
+        const int64_t m0 = tile * FZ_BLOCK_M;
+        const int K = p.K;
+        // group ids of the tile's sixteen 8-row blocks (compacted rows), fetched before the accumulator is waited for
+        const int my_gid = (compact && lane < 16 && (tile * 16 + lane) * 8 < M) ? __ldg(p.blockgroup + tile * 16 + lane) : -1;   // -1: past the end
+        if (pool_alt) tc::mbar_wait(acc_full1_alt + (it & 1), (it >> 1) & 1, 62);
+        else tc::mbar_wait(acc_full + 1, it & 1, 61);
+        if (ptrace) { if (pool_loader) FZ_TRACE(1, 5, it, 0); else FZ_TRACE(4, 5, it, 0); }
+        tc::tc_fence_after();
+        const int64_t rows_left = M - m0;                       // rows >= M do not exist (last tile)
+        for (int mb = mb_lo; mb < mb_hi; ++mb) {
+            const int ch = mb * 128 + q * 32 + lane;
+            const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + (uint32_t)(mb * FZ_BLOCK_M) + ((uint32_t)(q * 32) << 16);
+            const float b = ch < p.n[1] ? bias_s[p.bias_off[1] + ch] : 0.f;
+            // compacted rows: a group is a run of 8-row blocks with the same group id (warp uniform).  Groups may straddle
+            // tiles, so the first and the last group of a tile are merged into the (zero-initialised) output with an
+            // integer atomic max - pooled values are >= 0 after the ReLU, where float order equals integer order - the
+            // others are stored.  Dense rows: a group is K consecutive columns.
+            int cur = -1;
+            bool first_group = true;
+            float acc = -INFINITY;
+            auto flush = [&](bool edge) {
+                if (cur >= 0 && ch < p.c_out) {
+                    float *dst = p.out + (int64_t)cur * p.ld_out + p.out_col + ch;
+                    const float v = fmaxf(acc + b, 0.f);
+                    if (edge) atomicMax(reinterpret_cast<int *>(dst), __float_as_int(v));
+                    else *dst = v;
+                }
+            };
+            auto consume16 = [&](const uint32_t (&raw)[16], int col0) {
+                if (compact) {
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const int gid = __shfl_sync(0xffffffffu, my_gid, (col0 >> 3) + blk);
+                        const float m8 = fmaxf(fmaxf(fmaxf(__uint_as_float(raw[8 * blk]), __uint_as_float(raw[8 * blk + 1])),
+                                                     fmaxf(__uint_as_float(raw[8 * blk + 2]), __uint_as_float(raw[8 * blk + 3]))),
+                                               fmaxf(fmaxf(__uint_as_float(raw[8 * blk + 4]), __uint_as_float(raw[8 * blk + 5])),
+                                                     fmaxf(__uint_as_float(raw[8 * blk + 6]), __uint_as_float(raw[8 * blk + 7]))));
+                        if (gid != cur) {
+                            flush(first_group);
+                            if (cur >= 0) first_group = false;
+                            cur = gid; acc = m8;
+                        } else {
+                            acc = fmaxf(acc, m8);
+                        }
+                    }
+                } else {
+                    float m;
+                    if (rows_left >= FZ_BLOCK_M) {           // every tile but possibly the last: no row mask
+                        float m0_ = -INFINITY, m1_ = -INFINITY, m2_ = -INFINITY, m3_ = -INFINITY;   // 4 chains for ILP
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            m0_ = fmaxf(m0_, __uint_as_float(raw[j])); m1_ = fmaxf(m1_, __uint_as_float(raw[j + 1]));
+                            m2_ = fmaxf(m2_, __uint_as_float(raw[j + 2])); m3_ = fmaxf(m3_, __uint_as_float(raw[j + 3]));
+                        }
+                        m = fmaxf(fmaxf(m0_, m1_), fmaxf(m2_, m3_));
+                    } else {
+                        m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) m = fmaxf(m, (col0 + j) < rows_left ? __uint_as_float(raw[j]) : -INFINITY);
+                    }
+                    acc = fmaxf(acc, m);
+                    if (((col0 + 16) % K) == 0) {            // a group of K rows is complete (K in {32, 64, 128})
+                        const int64_t row0 = m0 + col0 + 16 - K;
+                        if (row0 < M && ch < p.c_out)
+                            p.out[(row0 / K) * (int64_t)p.ld_out + p.out_col + ch] = fmaxf(acc + b, 0.f);
+                        acc = -INFINITY;
+                    }
+                }
+            };
+            // 16 columns per TMEM load, two buffers: the next load is in flight while this one is reduced
+            uint32_t ra[16], rb[16];
+            tc::tmem_ld16(t_addr, ra);
+#pragma unroll 1
+            for (int c0 = 0; c0 < FZ_BLOCK_M; c0 += 32) {
+                tc::tmem_ld_wait();
+                tc::tmem_ld16(t_addr + c0 + 16, rb);
+                consume16(ra, c0);
+                tc::tmem_ld_wait();
+                if (c0 + 32 < FZ_BLOCK_M) tc::tmem_ld16(t_addr + c0 + 32, ra);
+                else if (mb + 1 == mb_hi) {
+                    // everything this warp reads of the accumulator is in registers: hand it back before the last
+                    // reductions and the global stores
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(acc_empty + 1);
+                }
+                consume16(rb, c0 + 16);
+            }
+            if (compact) flush(true);
+        }
+        if (ptrace) { if (pool_loader) FZ_TRACE(1, 6, it, 0); else FZ_TRACE(4, 6, it, 0); }
     };
 
     if (is_loader) {
@@ -273,52 +384,64 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
         if (!p.per_point) {
             // ---- gather + layer 1 in exact fp32 on the CUDA cores; thread = row ------------------------
             const int r = wq * 32 + lane;
-            float x[8], xn[8];
-            bool valid = false, valid_n = false;
-            auto gather = [&](int64_t tile, float (&o)[8], bool &ok) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = 0.f;
-                ok = false;
+            // Three-stage software pipeline over the tiles of this CTA, so that no load is waited for where it is issued
+            // (the chain row list -> point record -> centre is three dependent L2 round trips):
+            //   A  tile t + 2: row-list entries (global point row, group id)
+            //   B  tile t + 1: the 32-byte point record and the group's centre, addressed with A's result of a tile ago
+            //   C  tile t    : subtract the centre, layer 1
+            int a_pt = -1, a_bs = 0;                 // stage A result (compact: point row / group; dense: point index / group)
+            float4 b_r0 = make_float4(0.f, 0.f, 0.f, 0.f), b_r1 = b_r0;      // stage B result
+            float b_c0 = 0.f, b_c1 = 0.f, b_c2 = 0.f;
+            bool b_ok = false;
+            auto stage_a = [&](int64_t tile) {
+                a_pt = -1; a_bs = 0;
                 const int64_t R = tile * FZ_BLOCK_M + r;
                 if (tile >= n_tiles || R >= M) return;
-                int64_t bs, pt_row;
                 if (compact) {
-                    pt_row = __ldg(p.rowmap + R);
-                    bs = __ldg(p.blockgroup + (R >> 3));
-                    if (pt_row < 0) return;
+                    a_pt = __ldg(p.rowmap + R);
+                    a_bs = __ldg(p.blockgroup + (R >> 3));
                 } else {
-                    bs = R / p.K;
-                    const int j = (int)(R - bs * p.K);
-                    const int64_t b = bs / p.S;
-                    const int pt = p.idx[bs * p.idx_ld + p.k_off + j];
-                    if (pt < 0 || pt >= p.N) return;
-                    pt_row = b * p.N + pt;
-                }
-                ok = true;
-                const float4 *src = reinterpret_cast<const float4 *>(p.pts8 + pt_row * 8);
-                const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
-                o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
-                const float *c = p.centres + bs * 3;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float ca = __ldg(c + a);
-#pragma unroll
-                    for (int ch = 0; ch < 8; ++ch)
-                        if (ch == p.D + a) o[ch] = __fsub_rn(o[ch], ca);   // grouped_xyz -= new_xyz (:245)
+                    const int64_t bs = R / p.K;
+                    a_bs = (int)bs;
+                    a_pt = p.idx[bs * p.idx_ld + p.k_off + (int)(R - bs * p.K)];
                 }
             };
-            gather(blockIdx.x, xn, valid_n);
+            auto stage_b = [&]() {
+                b_ok = false;
+                int64_t pt_row = a_pt;
+                if (!compact) {
+                    if (a_pt >= p.N) return;
+                    pt_row = (int64_t)(a_bs / p.S) * p.N + a_pt;
+                }
+                if (a_pt < 0) return;
+                b_ok = true;
+                const float4 *src = reinterpret_cast<const float4 *>(p.pts8 + pt_row * 8);
+                b_r0 = __ldg(src); b_r1 = __ldg(src + 1);
+                const float *c = p.centres + (int64_t)a_bs * 3;
+                b_c0 = __ldg(c); b_c1 = __ldg(c + 1); b_c2 = __ldg(c + 2);
+            };
+            float x[8];
+            bool valid = false;
+            stage_a(blockIdx.x);
+            stage_b();
+            stage_a((int64_t)blockIdx.x + gridDim.x);
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                // stage C of this tile
+                valid = b_ok;
+                x[0] = b_r0.x; x[1] = b_r0.y; x[2] = b_r0.z; x[3] = b_r0.w; x[4] = b_r1.x; x[5] = b_r1.y; x[6] = b_r1.z; x[7] = b_r1.w;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = xn[i];
+                for (int ch = 0; ch < 8; ++ch) {                               // grouped_xyz -= new_xyz (:245)
+                    const float ca = ch == p.D ? b_c0 : ch == p.D + 1 ? b_c1 : ch == p.D + 2 ? b_c2 : 0.f;
+                    x[ch] = valid ? (ch >= p.D && ch < p.D + 3 ? __fsub_rn(x[ch], ca) : x[ch]) : 0.f;
+                }
                 uint64_t xx[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) xx[i] = tc::pack2(x[i], x[i]);
-                valid = valid_n;
                 const ulonglong2 *w1p = reinterpret_cast<const ulonglong2 *>(p.w1c);      // constant bank (kernel parameters)
                 const uint64_t *b1p = reinterpret_cast<const uint64_t *>(p.b1c);
-                gather(tile + gridDim.x, xn, valid_n);            // next tile's record is in flight during this tile
+                stage_b();                                        // tile t + 1: records in flight during this tile
+                stage_a(tile + 2 * (int64_t)gridDim.x);           // tile t + 2: row-list entries in flight
                 // kc is a compile-time constant in every copy of the body, so every weight address is an immediate offset
                 // into the parameter block: LDCU.128 into uniform registers feeding FFMA2 directly (with a run-time kc
                 // the compiler falls back to one per-thread LDC.64 per FMA)
@@ -326,34 +449,45 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 for (int kc = 0; kc < FZ_W1_MAX / KC; ++kc) {
                     if (kc >= nc0) break;
                     if (!mine(it, kc)) continue;
-                    float v[KC];
+                    // layer 1 for 16 channels of the row: exact fp32, packed FMAs, weights from the constant bank
+                    auto layer1_16 = [&](int j0, float (&v)[16]) {
 #pragma unroll
-                    for (int j = 0; j < KC; j += 2) {
-                        const int ch = kc * KC + j;
-                        const ulonglong2 *wp = w1p + ch * 2;                  // [pair][k][2]: 16 floats per channel pair
-                        const ulonglong2 w01 = wp[0], w23 = wp[1], w45 = wp[2], w67 = wp[3];
-                        uint64_t acc = b1p[ch >> 1];
-                        acc = tc::fma2(w01.x, xx[0], acc); acc = tc::fma2(w01.y, xx[1], acc);
-                        acc = tc::fma2(w23.x, xx[2], acc); acc = tc::fma2(w23.y, xx[3], acc);
-                        acc = tc::fma2(w45.x, xx[4], acc); acc = tc::fma2(w45.y, xx[5], acc);
-                        acc = tc::fma2(w67.x, xx[6], acc); acc = tc::fma2(w67.y, xx[7], acc);
-                        float a0, a1;
-                        tc::unpack2(acc, a0, a1);
-                        v[j] = fmaxf(a0, 0.f); v[j + 1] = fmaxf(a1, 0.f);
-                    }
-                    if (!valid) {
-#pragma unroll
-                        for (int j = 0; j < KC; ++j) v[j] = 0.f;
-                    }
+                        for (int j = 0; j < 16; j += 2) {
+                            const int ch = kc * KC + j0 + j;
+                            const ulonglong2 *wp = w1p + ch * 2;              // [pair][k][2]: 16 floats per channel pair
+                            const ulonglong2 w01 = wp[0], w23 = wp[1], w45 = wp[2], w67 = wp[3];
+                            uint64_t acc = b1p[ch >> 1];
+                            acc = tc::fma2(w01.x, xx[0], acc); acc = tc::fma2(w01.y, xx[1], acc);
+                            acc = tc::fma2(w23.x, xx[2], acc); acc = tc::fma2(w23.y, xx[3], acc);
+                            acc = tc::fma2(w45.x, xx[4], acc); acc = tc::fma2(w45.y, xx[5], acc);
+                            acc = tc::fma2(w67.x, xx[6], acc); acc = tc::fma2(w67.y, xx[7], acc);
+                            float a0, a1;
+                            tc::unpack2(acc, a0, a1);
+                            v[j] = valid ? fmaxf(a0, 0.f) : 0.f; v[j + 1] = valid ? fmaxf(a1, 0.f) : 0.f;
+                        }
+                    };
+                    float v[16];
+                    layer1_16(0, v);                                          // the first piece is ready before the slot is
                     if (tid == 0) FZ_TRACE(1, 1, it, kc);
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)kc, p.sa, bits, 10);
                     if (tid == 0) FZ_TRACE(1, 2, it, kc);
-                    store_row_chunk(a_ring + (size_t)slot * p.a_slot_bytes, r, v);
+                    uint8_t *st = a_ring + (size_t)slot * p.a_slot_bytes;
+                    store_row_16(st, r, 0, v);
+                    if constexpr (KC == 32) {
+                        layer1_16(16, v);
+                        store_row_16(st, r, 16, v);
+                    }
                     tc::fence_proxy_async();
                     tc::mbar_arrive(a_full + slot);
                     if (tid == 0) FZ_TRACE(1, 3, it, kc);
                 }
+                // this tile's rows are on their way: pool the previous tile while its successor's layer 2 runs
+                if (it > 0 && pools_tile(it - 1, grp))
+                    pool_tile(it - 1, tile - gridDim.x, wq, pool_groups == 2 ? grp : 0, pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
             }
+            if (it > 0 && pools_tile(it - 1, grp))
+                pool_tile(it - 1, (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x, wq, pool_groups == 2 ? grp : 0,
+                          pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
         } else {
             // ---- per-point mode: relu(P[p] - C[s]); octet lane mapping, P rows prefetched a tile ahead ----
             // 8 consecutive lanes = 8 consecutive rows of ONE 16-byte operand chunk (conflict-free store),
@@ -361,7 +495,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
             constexpr int QP = KC / 16;             // passes of 4 channel quads per 8-row group
             constexpr int NV = 4 * QP;              // float4 per lane per chunk
             const int l8 = lane & 7, oct = lane >> 3;
-            auto rows_of = [&](int64_t tile, int64_t (&p_row)[4], int64_t (&c_row)[4]) {
+            auto rows_of = [&](int64_t tile, int32_t (&p_row)[4], int32_t (&c_row)[4]) {
                 const int64_t m0 = tile * FZ_BLOCK_M;
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
@@ -376,25 +510,25 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                             const int j = (int)(R - bs * p.K);
                             const int64_t b = bs / p.S;
                             const int pt = p.idx[bs * p.idx_ld + p.k_off + j];
-                            if (pt >= 0 && pt < p.N) { p_row[h] = b * p.N + pt; c_row[h] = bs; }
+                            if (pt >= 0 && pt < p.N) { p_row[h] = (int32_t)(b * p.N + pt); c_row[h] = (int32_t)bs; }
                         }
                     }
                 }
             };
-            auto load_p = [&](const int64_t (&p_row)[4], int kc, float4 (&v)[NV]) {
+            auto load_p = [&](const int32_t (&p_row)[4], int kc, float4 (&v)[NV]) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     const int k = kc * KC + 4 * (oct + 4 * (i % QP));
-                    v[i] = p_row[i / QP] >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.P + p_row[i / QP] * p.ld_p + p.p_col + k))
+                    v[i] = p_row[i / QP] >= 0 ? __ldg(reinterpret_cast<const float4 *>(p.P + (int64_t)p_row[i / QP] * p.ld_p + p.p_col + k))
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            auto emit = [&](const int64_t (&p_row)[4], const int64_t (&c_row)[4], uint32_t it, int kc, float4 (&v)[NV]) {
+            auto emit = [&](const int32_t (&p_row)[4], const int32_t (&c_row)[4], uint32_t it, int kc, float4 (&v)[NV]) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     if (p_row[i / QP] >= 0) {        // C comes from L1: a few rows per tile, shared by all K neighbours
                         const int k = kc * KC + 4 * (oct + 4 * (i % QP));
-                        const float4 c = __ldg(reinterpret_cast<const float4 *>(p.C + c_row[i / QP] * p.ld_c + p.c_col + k));
+                        const float4 c = __ldg(reinterpret_cast<const float4 *>(p.C + (int64_t)c_row[i / QP] * p.ld_c + p.c_col + k));
                         v[i] = make_float4(fmaxf(v[i].x - c.x, 0.f), fmaxf(v[i].y - c.y, 0.f), fmaxf(v[i].z - c.z, 0.f), fmaxf(v[i].w - c.w, 0.f));
                     }
                 }
@@ -440,7 +574,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 if (tid == 0) FZ_TRACE(1, 3, it, kc);
             };
 
-            int64_t p_cur[4], c_cur[4], p_nxt[4], c_nxt[4];
+            int32_t p_cur[4], c_cur[4], p_nxt[4], c_nxt[4];      // row indices fit 32 bits (B * N, B * S < 2^31 is checked on the host)
             float4 v0[NV], v1[NV];                  // P rows of my first two chunks of the coming tile
             int kc0 = -1, kc1 = -1;
             auto prefetch = [&](int64_t tile, uint32_t it) {
@@ -466,7 +600,12 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                     else { float4 vj[NV]; load_p(p_cur, kc, vj); emit(p_cur, c_cur, it, kc, vj); }
                 }
                 prefetch(tile + gridDim.x, it + 1);     // my rows are out: fetch the next tile's P rows now
+                if (it > 0 && pools_tile(it - 1, grp))  // ... and pool the previous tile under their latency
+                    pool_tile(it - 1, tile - gridDim.x, wq, pool_groups == 2 ? grp : 0, pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
             }
+            if (it > 0 && pools_tile(it - 1, grp))
+                pool_tile(it - 1, (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x, wq, pool_groups == 2 ? grp : 0,
+                          pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
         }
     } else if (warp == STREAMER_WARP) {
         // =============================== weight streamer ===============================
@@ -629,7 +768,9 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                         if (++g_q == Q) { g_q = 0; ++g_it; }
                         par ^= 1u;
                     }
-                    if (tc::elect_one()) tc::umma_commit_u32(acc_full_u + 8 * g);      // this issuer's UMMAs into accumulator g are done (all of them with NI == 1)
+                    // this issuer's UMMAs into accumulator g are done (all of them with NI == 1)
+                    if (tc::elect_one())
+                        tc::umma_commit_u32(g == 1 && p.pool_loader && LG == 2 && mb3 == 1 ? tc::smem_u32(acc_full1_alt) + 8 * (it & 1) : acc_full_u + 8 * g);
                     __syncwarp();
                 }
             }
@@ -638,44 +779,59 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     } else {
         // =============================== epilogue warps ===============================
         const int q = warp & 3, r = q * 32 + lane;       // TMEM lane quadrant of a warp is warp_id % 4
-        const int K = p.K;
         uint64_t *my_grants = a_grant + LG * FZ_MAX_RING;
         uint32_t bits = 0;
         uint32_t it = 0;
         const bool eprof = warp == EPI_WARP0 && lane == 0;    // the thread that writes this role's trace events
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int64_t m0 = tile * FZ_BLOCK_M;
             {
-                // ---- layer 2 activations -> operand chunks of layer 3 ----
+                // ---- layer 2 activations -> operand chunks of layer 3 (the pool of layer 3 runs in the loader warps) ----
                 const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[0] + ((uint32_t)(q * 32) << 16);
                 const float *bias_g = bias_s + p.bias_off[0];
                 tc::mbar_wait(acc_full + 0, it & 1, 60);
                 if (eprof) FZ_TRACE(4, 1, it, 0);
                 tc::tc_fence_after();
-                for (int c = 0; c < nc1; ++c) {
-                    uint32_t raw[KC];
-                    if constexpr (KC == 32) tc::tmem_ld32(t_addr + c * 32, raw);
-                    else tc::tmem_ld16(t_addr + c * 16, raw);
-                    tc::tmem_ld_wait();
-                    float v[KC];
+                // bias + ReLU of 16 accumulator columns (columns past n[0] are padding: zero)
+                auto act16 = [&](const uint32_t (&raw)[16], int col0, float (&v)[16]) {
 #pragma unroll
-                    for (int j4 = 0; j4 < KC; j4 += 4) {
-                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2 *>(bias_g + c * KC + j4);   // past n[0]: finite, masked below
+                    for (int j4 = 0; j4 < 16; j4 += 4) {
+                        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2 *>(bias_g + col0 + j4);   // past n[0]: finite, masked below
                         float t0, t1, t2, t3;
                         tc::unpack2(tc::add2(tc::pack2(__uint_as_float(raw[j4 + 0]), __uint_as_float(raw[j4 + 1])), b4.x), t0, t1);
                         tc::unpack2(tc::add2(tc::pack2(__uint_as_float(raw[j4 + 2]), __uint_as_float(raw[j4 + 3])), b4.y), t2, t3);
                         v[j4 + 0] = fmaxf(t0, 0.f); v[j4 + 1] = fmaxf(t1, 0.f);
                         v[j4 + 2] = fmaxf(t2, 0.f); v[j4 + 3] = fmaxf(t3, 0.f);
                     }
-                    if ((c + 1) * KC > p.n[0]) {                  // last chunk only: columns past the accumulator are padding
+                    if (col0 + 16 > p.n[0]) {
 #pragma unroll
-                        for (int j = 0; j < KC; ++j)
-                            if (c * KC + j >= p.n[0]) v[j] = 0.f;
+                        for (int j = 0; j < 16; ++j)
+                            if (col0 + j >= p.n[0]) v[j] = 0.f;
                     }
+                };
+                // 16 columns per TMEM load, two buffers: the next load is in flight while this one is converted and
+                // stored (tcgen05.wait::ld waits for every outstanding load, so exactly one is outstanding at a wait)
+                uint32_t ra[16], rb[16];
+                float v[16];
+                tc::tmem_ld16(t_addr, ra);
+                for (int c = 0; c < nc1; ++c) {
+                    tc::tmem_ld_wait();                                       // ra: columns c * KC .. + 15
+                    if constexpr (KC == 32) tc::tmem_ld16(t_addr + c * KC + 16, rb);
+                    else if (c + 1 < nc1) tc::tmem_ld16(t_addr + (c + 1) * KC, rb);
+                    act16(ra, c * KC, v);
                     if (eprof) FZ_TRACE(4, 2, it, c);
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)(nc0 + c), p.sa, bits, 70);
                     if (eprof) FZ_TRACE(4, 3, it, c);
-                    store_row_chunk(a_ring + (size_t)slot * p.a_slot_bytes, r, v);
+                    uint8_t *st = a_ring + (size_t)slot * p.a_slot_bytes;
+                    store_row_16(st, r, 0, v);
+                    if constexpr (KC == 32) {
+                        tc::tmem_ld_wait();                                   // rb: columns c * KC + 16 .. + 31
+                        if (c + 1 < nc1) tc::tmem_ld16(t_addr + (c + 1) * KC, ra);
+                        act16(rb, c * KC + 16, v);
+                        store_row_16(st, r, 16, v);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) ra[j] = rb[j];
+                    }
                     tc::fence_proxy_async();
                     tc::mbar_arrive(a_full + slot);
                     if (eprof) FZ_TRACE(4, 4, it, c);
@@ -683,96 +839,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 0);
             }
-            {
-                // ---- layer 3 (transposed accumulator): lane = output channel, columns = the tile's rows.
-                // max over the K rows of a group = per-thread max over K columns; bias and ReLU commute
-                // with the max (both monotone) and are applied once per pooled value.
-                tc::mbar_wait(acc_full + 1, it & 1, 61);
-                if (eprof) FZ_TRACE(4, 5, it, 0);
-                tc::tc_fence_after();
-                const int64_t rows_left = M - m0;                       // rows >= M do not exist (last tile)
-                if (compact) {
-                    // Compacted rows: a group is a run of 8-row blocks with the same group id (warp uniform, one id
-                    // per lane fetched once per tile).  Groups may straddle tiles, so the first and the last group of
-                    // a tile are merged into the (zero-initialised) output with an integer atomic max - pooled
-                    // values are >= 0 after the ReLU, where float order equals integer order - the others stored.
-                    const int my_gid = (lane < 16 && (tile * 16 + lane) * 8 < M) ? __ldg(p.blockgroup + tile * 16 + lane) : -1;   // -1: past the end
-                    for (int mb = 0; mb < p.mb3; ++mb) {
-                        const int ch = mb * 128 + q * 32 + lane;
-                        const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + (uint32_t)(mb * FZ_BLOCK_M) + ((uint32_t)(q * 32) << 16);
-                        const float b = ch < p.n[1] ? bias_s[p.bias_off[1] + ch] : 0.f;
-                        int cur = -1;
-                        bool first_group = true;
-                        float acc = -INFINITY;
-                        auto flush = [&](bool edge) {
-                            if (cur >= 0 && ch < p.c_out) {
-                                float *dst = p.out + (int64_t)cur * p.ld_out + p.out_col + ch;
-                                const float v = fmaxf(acc + b, 0.f);
-                                if (edge) atomicMax(reinterpret_cast<int *>(dst), __float_as_int(v));
-                                else *dst = v;
-                            }
-                        };
-#pragma unroll 1
-                        for (int c0 = 0; c0 < FZ_BLOCK_M; c0 += 32) {
-                            uint32_t raw[32];
-                            tc::tmem_ld32(t_addr + c0, raw);
-                            tc::tmem_ld_wait();
-#pragma unroll
-                            for (int blk = 0; blk < 4; ++blk) {
-                                const int gid = __shfl_sync(0xffffffffu, my_gid, (c0 >> 3) + blk);
-                                float m8 = fmaxf(fmaxf(fmaxf(__uint_as_float(raw[8 * blk]), __uint_as_float(raw[8 * blk + 1])),
-                                                       fmaxf(__uint_as_float(raw[8 * blk + 2]), __uint_as_float(raw[8 * blk + 3]))),
-                                                 fmaxf(fmaxf(__uint_as_float(raw[8 * blk + 4]), __uint_as_float(raw[8 * blk + 5])),
-                                                       fmaxf(__uint_as_float(raw[8 * blk + 6]), __uint_as_float(raw[8 * blk + 7]))));
-                                if (gid != cur) {
-                                    flush(first_group);
-                                    if (cur >= 0) first_group = false;
-                                    cur = gid; acc = m8;
-                                } else {
-                                    acc = fmaxf(acc, m8);
-                                }
-                            }
-                        }
-                        flush(true);
-                    }
-                } else
-                for (int mb = 0; mb < p.mb3; ++mb) {
-                    const int ch = mb * 128 + q * 32 + lane;
-                    const uint32_t t_addr = tmem_base + (uint32_t)p.tmem_col[1] + (uint32_t)(mb * FZ_BLOCK_M) + ((uint32_t)(q * 32) << 16);
-                    const float b = ch < p.n[1] ? bias_s[p.bias_off[1] + ch] : 0.f;
-                    float gmax = -INFINITY;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < FZ_BLOCK_M; c0 += 32) {
-                        uint32_t raw[32];
-                        tc::tmem_ld32(t_addr + c0, raw);
-                        tc::tmem_ld_wait();
-                        float m;
-                        if (rows_left >= FZ_BLOCK_M) {               // every tile but possibly the last: no row mask
-                            float m0_ = -INFINITY, m1_ = -INFINITY, m2_ = -INFINITY, m3_ = -INFINITY;   // 4 chains for ILP
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                m0_ = fmaxf(m0_, __uint_as_float(raw[j])); m1_ = fmaxf(m1_, __uint_as_float(raw[j + 1]));
-                                m2_ = fmaxf(m2_, __uint_as_float(raw[j + 2])); m3_ = fmaxf(m3_, __uint_as_float(raw[j + 3]));
-                            }
-                            m = fmaxf(fmaxf(m0_, m1_), fmaxf(m2_, m3_));
-                        } else {
-                            m = -INFINITY;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) m = fmaxf(m, (c0 + j) < rows_left ? __uint_as_float(raw[j]) : -INFINITY);
-                        }
-                        gmax = fmaxf(gmax, m);
-                        if (((c0 + 32) % K) == 0) {                      // a group of K rows is complete (K in {32, 64, 128})
-                            const int64_t row0 = m0 + c0 + 32 - K;
-                            if (row0 < M && ch < p.c_out)
-                                p.out[(row0 / K) * (int64_t)p.ld_out + p.out_col + ch] = fmaxf(gmax + b, 0.f);
-                            gmax = -INFINITY;
-                        }
-                    }
-                }
-                tc::tc_fence_before();
-                tc::mbar_arrive(acc_empty + 1);
-                if (eprof) FZ_TRACE(4, 6, it, 0);
-            }
+            if (!pool_loader) pool_tile(it, tile, q, 0, p.mb3, eprof);
         }
     }
 
@@ -872,6 +939,7 @@ static int sa_msg_fused_impl(
     using namespace ev2h;
     EV2H_REQUIRE(idx && centres_rows && out_rows && cout_host && w_packed_host && bias_host, "ev2h_sa_msg_fused_tc: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0 && k_off >= 0 && k_off + K <= idx_ld && c1 > 0, "ev2h_sa_msg_fused_tc: bad sizes");
+    EV2H_REQUIRE((int64_t)B * N < 2147483647LL && (int64_t)B * S < 2147483647LL, "ev2h_sa_msg_fused_tc: B * N and B * S must fit 32 bits");
     EV2H_REQUIRE(mode >= FZ_MODE_BF16 && mode <= FZ_MODE_F16X3, "ev2h_sa_msg_fused_tc: unknown mode %d", mode);
     if (K != 32 && K != 64 && K != 128)
         return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: K=%d (supported: 32, 64, 128)", K);
@@ -896,6 +964,8 @@ static int sa_msg_fused_impl(
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
     p.rowmap = rowmap; p.blockgroup = blockgroup; p.n_rows_dev = n_rows_dev;
     p.per_point = per_point ? 1 : 0; p.pts8 = pts8; p.D = D; p.range_flag = range_flag;
+    static const int pool_in_loader = [] { const char *e = getenv("EV2H_POOL_LOADER"); return (e && e[0] == '1') ? 1 : 0; }();
+    p.pool_loader = pool_in_loader;
     if (!per_point) {
         // layer-1 weights into the parameter block: channel pairs interleaved, [pair][k][2], so one 64-bit word feeds one packed FMA
         for (int ch = 0; ch < c1; ++ch) {
@@ -925,7 +995,7 @@ static int sa_msg_fused_impl(
 
     p.a_slot_bytes = PARTS * FZ_BLOCK_M * KC * EB;
     p.b_slot_bytes = PARTS * max_n * KC * EB;
-    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 4 * FZ_GEMMS) * 8 + 16 + boff * 4;
+    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 5 * FZ_GEMMS) * 8 + 16 + boff * 4;
     int occ = pl.occ;
     int budget = (occ == 2 ? 113 : 227) * 1024 - tail - 512;
     if (occ == 2 && budget < 2 * p.a_slot_bytes + 2 * p.b_slot_bytes) { occ = 1; budget = 227 * 1024 - tail - 512; }
@@ -957,6 +1027,8 @@ static int sa_msg_fused_impl(
         return launch_fused<FZ_MODE_TF32X3, 32, 2, 1>(p, smem, grid, st);
     }
     if (mode == FZ_MODE_F16X3) {
+        static const bool lg2 = [] { const char *e = getenv("EV2H_FUSED_LG2"); return e && e[0] == '1'; }();   // experiment: two loader groups at two CTAs per SM (448 threads, 72 registers)
+        if (pl.occ == 2 && occ == 2 && lg2) return launch_fused<FZ_MODE_F16X3, 32, 2, 2>(p, smem, grid, st);
         if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_F16X3, 32, 1, 2>(p, smem, grid, st)
                                          : launch_fused<FZ_MODE_F16X3, 32, 1, 1>(p, smem, grid, st);
         return launch_fused<FZ_MODE_F16X3, 32, 2, 1>(p, smem, grid, st);

@@ -19,7 +19,7 @@ torch.cuda.synchronize()
 orig = _capi.sa_msg_fused
 buf = torch.zeros(512, 16, dtype=torch.int64, device=dev)
 ROLE = {1: "load", 2: "strm", 3: "issu", 4: "epil"}
-EV = {(1, 1): "chunk computed", (1, 2): "slot granted", (1, 3): "arrived a_full",
+EV = {(1, 1): "chunk computed", (1, 2): "slot granted", (1, 3): "arrived a_full", (1, 5): "acc_full1 seen (pool)", (1, 6): "pool done",
       (2, 1): "b_empty ok -> copy", (3, 1): "acc_empty ok", (3, 2): "a_full ok", (3, 3): "b_full ok", (3, 6): "mmas issued", (3, 7): "commits issued",
       (4, 1): "acc_full0 seen", (4, 2): "chunk converted", (4, 3): "slot granted", (4, 4): "arrived a_full",
       (4, 5): "acc_full1 seen", (4, 6): "pool done"}
