@@ -604,6 +604,40 @@ def run_ours(args):
         barrier()
         sustained = {"steps": n_sus, "ms_total": float(sa_.elapsed_time(sb_)), "clocks": sus_sampler.finish()}
 
+    # whole-network inference (secondary): the reference's TEHNet.forward wiring in eval mode - encoder, decoder,
+    # classifier + query convolutions + attention, both hand regressors' set abstraction + FC head, stand-in MANO layer
+    full_ms = 0.0
+    if args.configs:
+        try:
+            from ev2hands_b200 import tehnet as _th
+            os.environ.setdefault("ERPC", "1")
+            torch.manual_seed(0)
+            fnet = _th.TEHNet(n_pose_params=6).to(device).eval()
+            fhands = _th.create_standin_mano_layers(device)
+
+            def full_step():
+                with torch.no_grad():
+                    return fnet(ev_dev, fhands)
+
+            for _ in range(3):
+                full_step()
+            barrier()
+            f_evs = []
+            for _ in range(args.steps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                full_step()
+                b.record()
+                f_evs.append((a, b))
+            barrier()
+            full_ms = float(sum(a.elapsed_time(b) for a, b in f_evs))
+            del fnet
+        except Exception as exc:      # noqa: BLE001
+            print("bench.py: full-network leg failed (%s)" % exc, file=sys.stderr)
+            full_ms = 0.0
+        full_ms = sharding.max_over_ranks([full_ms], device=device)[0]
+
     train_res = None
     if args.configs:
         try:
@@ -717,6 +751,12 @@ def run_ours(args):
                              "roofline_frac": sus_tflops / peaks["bf16_tflops_sustained"], "peak": peaks["bf16_tflops_sustained"],
                              "how": "the headline step repeated for >= 2 s, one event pair around the loop, L2 flushed every step; "
                                     "MLP time = loop time x the MLP kernels' share of the per-kernel pass (%.3f); peak = measured sustained bf16" % mlp_share}
+    if full_ms > 0:
+        line.setdefault("configs", {})["full_network_eval"] = {
+            "workload": "TEHNet.forward wiring in eval mode (TEHNet.py:168-197): encoder + decoder + classifier + query convolutions + "
+                        "attention + two hand regressors (set abstraction on the kernels, FC head and stand-in MANO layer in PyTorch), "
+                        "%d windows per GPU, eager launches, host-drawn FPS starts" % B,
+            "ms_per_step": full_ms / args.steps, "value": windows / (full_ms / 1e3), "unit": "windows/s"}
     if train_res is not None:
         line.setdefault("configs", {})["cfg4"] = {
             "workload": "BASELINE configs[3]: full training step (set abstraction + feature propagation + classifier + attention + two hand "

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "ev2h_three_interp_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_window_aggregate_f64": [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "ev2h_window_sample_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "ev2h_conv1d_tc": [c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp],
+    "ev2h_class_attention_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp],
     "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_group_max_bwd_f32": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
 }
@@ -427,6 +429,26 @@ def linear_no_relu(x, M, ld_x, Cin, wt, bias, Cout, y, ld_y, y_col_off=0):
         with _timed("ev2h_linear_f32"):
             _check(lib().ev2h_linear_f32(_p(x), M, ld_x, Cin, _p(wt), _p(bias), Cout, _p(y), ld_y, y_col_off, _stream(x)),
                    "ev2h_linear_f32")
+
+
+def conv1d_tc(x_rows, M, ld_x, Cin, taps, rows_per_seq, packed, bias, Cout, relu, post_scale, post_shift, y, ld_y, y_col_off, mode):
+    """Conv1d (kernel size taps, zero padding taps // 2) over point-major rows [+ ReLU] [+ per-channel affine]."""
+    with torch.cuda.device(x_rows.device):
+        with _timed("ev2h_conv1d_tc"):
+            _check(lib().ev2h_conv1d_tc(_p(x_rows), M, ld_x, Cin, taps, rows_per_seq, _p(packed), _p(bias), Cout, 1 if relu else 0,
+                                        _p(post_scale), _p(post_shift), _p(y), ld_y, y_col_off, mode, _stream(x_rows)), "ev2h_conv1d_tc")
+
+
+def class_attention(key_rows, ld_k, query_rows, ld_q, value_rows, ld_v, B, N, C, D, scale):
+    """AttentionBlock on rows -> context [B, C, N] channel-first."""
+    dev = value_rows.device
+    partial = torch.empty((B, 8, C, D), dtype=torch.float32, device=dev)
+    out = torch.empty((B, C, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        with _timed("ev2h_class_attention_f32", launches=2):
+            _check(lib().ev2h_class_attention_f32(_p(key_rows), ld_k, _p(query_rows), ld_q, _p(value_rows), ld_v, B, N, C, D, float(scale),
+                                                  _p(partial), _p(out), _stream(value_rows)), "ev2h_class_attention_f32")
+    return out
 
 
 def fused_supported(K: int, widths, first_in: int, per_point: bool, mode: int = TC_TF32X3) -> bool:

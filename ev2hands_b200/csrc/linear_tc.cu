@@ -57,6 +57,12 @@ struct TcParams {
     int stages;
     int debug;
     int relu;           // 0: y = x W' + b' (no activation)
+    // Conv1d over the row axis (kernel size `taps`, zero padding taps / 2, rows_per_win consecutive rows = one sequence):
+    // the operand row of output row r is [x[r - taps/2], ..., x[r + taps/2]] (tap_cin channels each), rows outside the
+    // sequence being zero - gathered by the loaders, never materialised.  taps == 1: the plain layer.
+    int taps, tap_cin, rows_per_win;
+    // optional per-channel affine AFTER the activation (a BatchNorm that follows the ReLU): y = act(.) * scale + shift
+    const float *post_scale, *post_shift;
 };
 
 // ---- weight packing: folded [Cin_pad16, ld_w] fp32 (input-channel major) -> per (n-block, stage)
@@ -128,7 +134,9 @@ linear_tc_kernel(const TcParams p) {
     uint64_t *acc_empty = acc_full + 2;                                // [2]
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
     float *bias_s = reinterpret_cast<float *>(tmem_base_slot + 4);     // [n_blocks * n_blk]
-    float *red = bias_s + p.n_blocks * n_blk;                          // [2][4][n_blk]
+    float *post_a = bias_s + p.n_blocks * n_blk;                       // [n_blocks * n_blk] each (scale 1 / shift 0 when absent)
+    float *post_b = post_a + p.n_blocks * n_blk;
+    float *red = post_b + p.n_blocks * n_blk;                          // [2][4][n_blk]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m_tiles = (p.M + TC_BLOCK_M - 1) / TC_BLOCK_M;
@@ -145,7 +153,12 @@ linear_tc_kernel(const TcParams p) {
         }
         tc::fence_mbar_init();
     }
-    for (int i = tid; i < p.n_blocks * n_blk; i += TC_THREADS) bias_s[i] = p.bias[i];
+    for (int i = tid; i < p.n_blocks * n_blk; i += TC_THREADS) {
+        bias_s[i] = p.bias[i];
+        post_a[i] = (p.post_scale && i < p.Cout) ? p.post_scale[i] : 1.f;
+        post_b[i] = (p.post_shift && i < p.Cout) ? p.post_shift[i] : 0.f;
+    }
+    const bool post = p.post_scale != nullptr || p.post_shift != nullptr;
     if (warp == 4) tc::tmem_alloc(tmem_base_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
@@ -169,22 +182,37 @@ linear_tc_kernel(const TcParams p) {
             const int64_t tile = blockIdx.x + (int64_t)(n / (uint32_t)p.n_kc) * gridDim.x;
             const int kc = (int)(n % (uint32_t)p.n_kc);
             const int64_t m0 = (tile / p.n_blocks) * TC_BLOCK_M;
+            // Conv1d taps: a 32-channel chunk lies inside one tap (tap_cin is a multiple of 32); its source row is shifted
+            // by tap - taps / 2 and must stay inside the output row's sequence
+            const int tap = p.taps > 1 ? (kc * TC_KC) / p.tap_cin : 0;
+            const int k_base = kc * TC_KC - tap * p.tap_cin;
+            const int shift = tap - (p.taps >> 1);
+            auto src_row = [&](int64_t out_row, bool &ok) {
+                ok = out_row < p.M;
+                if (p.taps == 1) return out_row;
+                const int64_t sr = out_row + shift;
+                ok = ok && sr >= 0 && sr < p.M && (sr / p.rows_per_win) == (out_row / p.rows_per_win);
+                return sr;
+            };
             if (MODE == TC_MODE_TF32X3) {                     // (MIXED uses the 8-channels-per-lane mapping below)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int row = 32 * wq + (i >> 1) * 8 + l8;
-                    const int k = kc * TC_KC + 4 * (oct + 4 * (i & 1));
-                    v[i] = ((m0 + row) < p.M && k < p.ld_x)
-                               ? __ldg(reinterpret_cast<const float4 *>(p.x + (m0 + row) * (int64_t)p.ld_x + k))
+                    const int k = k_base + 4 * (oct + 4 * (i & 1));
+                    bool ok;
+                    const int64_t sr = src_row(m0 + row, ok);
+                    v[i] = (ok && k < p.ld_x)
+                               ? __ldg(reinterpret_cast<const float4 *>(p.x + sr * (int64_t)p.ld_x + k))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = 32 * wq + i * 8 + l8;
-                    const int k = kc * TC_KC + 8 * oct;
-                    const float *src = p.x + (m0 + row) * (int64_t)p.ld_x + k;
-                    const bool ok = (m0 + row) < p.M;
+                    const int k = k_base + 8 * oct;
+                    bool ok;
+                    const int64_t sr = src_row(m0 + row, ok);
+                    const float *src = p.x + sr * (int64_t)p.ld_x + k;
                     v[2 * i] = (ok && k < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     v[2 * i + 1] = (ok && k + 4 < p.ld_x) ? __ldg(reinterpret_cast<const float4 *>(src + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -381,6 +409,7 @@ linear_tc_kernel(const TcParams p) {
                 for (int j = 0; j < 32; ++j) {
                     const float t = __uint_as_float(raw[j]) + bias_s[col0 + c0 + j];
                     v[j] = p.relu ? fmaxf(t, 0.f) : t;
+                    if (post) v[j] = __fmaf_rn(v[j], post_a[col0 + c0 + j], post_b[col0 + c0 + j]);
                 }
                 if (K == 0) {
                     if (row_ok) {
@@ -507,7 +536,8 @@ extern "C" int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int C
 }
 
 static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed, const float *bias, int Cout,
-                          int pool_rows, float *y, int ld_y, int y_col_off, int mode, int relu, ev2h_stream_t stream);
+                          int pool_rows, float *y, int ld_y, int y_col_off, int mode, int relu, ev2h_stream_t stream,
+                          int taps = 1, int rows_per_win = 0, const float *post_scale = nullptr, const float *post_shift = nullptr);
 
 extern "C" int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
                                    const float *bias, int Cout, int pool_rows, float *y, int ld_y, int y_col_off,
@@ -520,13 +550,25 @@ extern "C" int ev2h_linear_tc(const float *x, int64_t M, int ld_x, int Cin, cons
     return linear_tc_impl(x, M, ld_x, Cin, w_packed, bias, Cout, 0, y, ld_y, y_col_off, mode, 0, stream);
 }
 
+extern "C" int ev2h_conv1d_tc(const float *x_rows, int64_t M, int ld_x, int Cin, int taps, int rows_per_seq, const void *w_packed,
+                              const float *bias, int Cout, int relu, const float *post_scale, const float *post_shift,
+                              float *y, int ld_y, int y_col_off, int mode, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(taps == 1 || taps == 3 || taps == 5, "ev2h_conv1d_tc: kernel size %d (supported: 1, 3, 5)", taps);
+    EV2H_REQUIRE(Cin > 0 && (taps == 1 || Cin % TC_KC == 0), "ev2h_conv1d_tc: Cin=%d must be a multiple of %d for kernel sizes > 1", Cin, TC_KC);
+    EV2H_REQUIRE(rows_per_seq > 0 && M % rows_per_seq == 0, "ev2h_conv1d_tc: M must be a whole number of sequences");
+    return linear_tc_impl(x_rows, M, ld_x, Cin * taps, w_packed, bias, Cout, 0, y, ld_y, y_col_off, mode, relu, stream, taps, rows_per_seq,
+                          post_scale, post_shift);
+}
+
 static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed, const float *bias, int Cout,
-                          int pool_rows, float *y, int ld_y, int y_col_off, int mode, int relu, ev2h_stream_t stream) {
+                          int pool_rows, float *y, int ld_y, int y_col_off, int mode, int relu, ev2h_stream_t stream,
+                          int taps, int rows_per_win, const float *post_scale, const float *post_shift) {
     using namespace ev2h;
     EV2H_REQUIRE(x && w_packed && bias && y, "ev2h_linear_relu_tc: null argument");
     EV2H_REQUIRE(M > 0 && Cin > 0 && Cout > 0, "ev2h_linear_relu_tc: bad sizes");
     EV2H_REQUIRE(mode >= TC_MODE_BF16 && mode <= TC_MODE_F16X3, "ev2h_linear_relu_tc: unknown mode %d", mode);
-    EV2H_REQUIRE(ld_x % 4 == 0 && ld_x >= Cin, "ev2h_linear_relu_tc: ld_x=%d must be a multiple of 4 and >= Cin=%d", ld_x, Cin);
+    EV2H_REQUIRE(ld_x % 4 == 0 && ld_x >= Cin / taps, "ev2h_linear_relu_tc: ld_x=%d must be a multiple of 4 and >= Cin=%d", ld_x, Cin / taps);
     EV2H_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_packed & 15) == 0, "ev2h_linear_relu_tc: x and w_packed must be 16-byte aligned");
     EV2H_REQUIRE(pool_rows >= 0 && (pool_rows == 0 || M % pool_rows == 0), "ev2h_linear_relu_tc: M must be a multiple of pool_rows");
     EV2H_REQUIRE(y_col_off >= 0 && ld_y >= y_col_off + Cout, "ev2h_linear_relu_tc: ld_y too small");
@@ -547,13 +589,15 @@ static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const vo
         p.n_store_total = room < padded ? room : padded;     // also write the exact-zero padding columns
     }
     const int stage_bytes = tc_stage_bytes(mode, p.n_blk);
-    const int tail_bytes = (2 * TC_MAX_STAGES + 4) * 8 + 16 + (p.n_blocks * p.n_blk + 2 * 4 * p.n_blk) * 4;
+    const int tail_bytes = (2 * TC_MAX_STAGES + 4) * 8 + 16 + (3 * p.n_blocks * p.n_blk + 2 * 4 * p.n_blk) * 4;
     int stages = (227 * 1024 - tail_bytes - 1024) / stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_linear_relu_tc: stage of %d bytes does not fit twice", stage_bytes);
     p.stages = stages;
     p.debug = g_tc_debug;
     p.relu = relu;
+    p.taps = taps; p.tap_cin = Cin / taps; p.rows_per_win = rows_per_win > 0 ? rows_per_win : 1;
+    p.post_scale = post_scale; p.post_shift = post_shift;
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes;
 
     int dev = 0, sms = 0;

@@ -776,6 +776,9 @@ class PointNetFeaturePropagation(nn.Module):
         _mlp_rows(x, B * N, ld_x, layers, 0, out, ld_o, 0)
         cf = torch.empty((B, c_out, N), dtype=torch.float32, device=dev)
         _capi.transpose(out, (N * ld_o, ld_o, 1), B, N, c_out, cf, c_out * N, N, 0)
+        # the point-major rows ride on the channel-first result (like _LevelRows): the heads that follow the decoder
+        # (ev2hands_b200.tehnet) work on rows and read them instead of transposing back
+        cf._ev2h_fp_rows = (out, ld_o, c_out, cf._version)
         return cf
 
     def _forward_autograd(self, xyz1, xyz2, points1, points2):

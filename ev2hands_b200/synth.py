@@ -161,6 +161,38 @@ def random_state_for(spec: dict, seed: int) -> dict:
                            [spec["in_channel"]], seed)
 
 
+def random_head_state(seed: int, num_classes: int = 4, width: int = 256) -> dict:
+    """Random weights for the heads that follow the decoder, named like the reference's
+    ``TEHNet.state_dict()`` (TEHNet.py:135-166): ``classifier`` (Conv1d k=1, ReLU, BatchNorm1d, Dropout, Conv1d k=1)
+    and ``left_query_conv`` / ``right_query_conv`` (Conv1d k=3, ReLU, BatchNorm1d, Dropout, Conv1d k=3, BatchNorm1d).
+    BatchNorm statistics and affine terms are randomised like in ``random_sa_state``."""
+    rs = np.random.RandomState(seed)
+    st = {}
+
+    def conv(name, cout, cin, k):
+        bound = 1.0 / np.sqrt(cin * k)
+        st[name + ".weight"] = rs.uniform(-bound, bound, (cout, cin, k)).astype(np.float32)
+        st[name + ".bias"] = rs.uniform(-bound, bound, (cout,)).astype(np.float32)
+
+    def bn(name, c):
+        st[name + ".weight"] = rs.uniform(0.5, 1.5, (c,)).astype(np.float32)
+        st[name + ".bias"] = (0.1 * rs.randn(c)).astype(np.float32)
+        st[name + ".running_mean"] = (0.1 * rs.randn(c)).astype(np.float32)
+        st[name + ".running_var"] = rs.uniform(0.5, 1.5, (c,)).astype(np.float32)
+        st[name + ".num_batches_tracked"] = np.array(0, dtype=np.int64)
+
+    conv("classifier.0", width, width, 1)
+    bn("classifier.2", width)
+    conv("classifier.4", num_classes, width, 1)
+    for side in ("left", "right"):
+        p = side + "_query_conv"
+        conv(p + ".0", width, width, 3)
+        bn(p + ".2", width)
+        conv(p + ".4", width, width, 3)
+        bn(p + ".5", width)
+    return st
+
+
 def make_raw_events(n_events: int, seed: int = 0, t0: float = 0.0, duration: float = 5.0e6,
                     extra_columns: int = 0, unique_times: bool = False) -> np.ndarray:
     """A raw event stream, float64 ``[n_events, 4 + extra_columns]`` = (x, y, t, polarity, ...), time ordered:

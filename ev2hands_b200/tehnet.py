@@ -24,7 +24,83 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _capi
+from . import pointnet2_utils as _pu
 from .pointnet2_utils import PointNetFeaturePropagation, PointNetSetAbstraction, PointNetSetAbstractionMsg
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# segmentation classifier + per-hand query convolutions + attention on the CUDA kernels
+# (eval mode, no autograd; training keeps the PyTorch modules).  Reference: TEHNet.py:135-166 (modules), :188-192 (use).
+# ---------------------------------------------------------------------------------------------------------------
+def _bn_affine(bn):
+    """eval-mode BatchNorm1d as y = a x + b (fp64 on the device)"""
+    a = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+    return a, bn.bias.double() - bn.running_mean.double() * a
+
+
+def _pack_conv1d(w, bias, mode):
+    """Conv1d weight [Cout, Cin, T] (+ bias [Cout]), fp64 -> (packed tensor-core image, padded fp32 bias, T, Cin, Cout)"""
+    cout, cin, taps = w.shape
+    rows, cols = (taps * cin + 15) // 16 * 16, (cout + 127) // 128 * 128
+    wt = torch.zeros((rows, cols), dtype=torch.float32, device=w.device)
+    wt[:taps * cin, :cout] = w.permute(2, 1, 0).reshape(taps * cin, cout).float()      # row t * Cin + ci = W[:, ci, t]
+    b = torch.zeros((cols,), dtype=torch.float32, device=w.device)
+    b[:cout] = bias.float()
+    return {"packed": _capi.tc_pack(wt, taps * cin, cout, mode), "bias": b, "taps": taps, "cin": cin, "cout": cout}
+
+
+class _HeadWeights:
+    """folded + packed weights of the classifier and the two query convolutions, per (device, arithmetic mode),
+    rebuilt when any source tensor changed (data_ptr / _version), like pointnet2_utils._FoldedMLP"""
+
+    def __init__(self):
+        self.cache = {}
+
+    @staticmethod
+    def _key(net):
+        k = []
+        for seq in (net.classifier, net.left_query_conv, net.right_query_conv):
+            for t in list(seq.parameters()) + list(seq.buffers()):
+                k.append((t.data_ptr(), t._version))
+        return tuple(k)
+
+    def get(self, net, mode):
+        dev = net.classifier[0].weight.device
+        key = self._key(net)
+        with _pu._CACHE_LOCK:
+            hit = self.cache.get((dev, mode))
+            if hit is not None and hit[0] == key:
+                return hit[1]
+        with torch.no_grad():
+            out = {}
+            c1, bn, c2 = net.classifier[0], net.classifier[2], net.classifier[4]
+            a, b = _bn_affine(bn)
+            out["cls1"] = _pack_conv1d(c1.weight.double(), c1.bias.double(), mode)
+            # Conv -> ReLU -> BN -> (Dropout) -> Conv with kernel size 1: the BatchNorm folds into the second convolution
+            w2 = c2.weight.double()[:, :, 0]
+            out["cls2"] = _pack_conv1d((w2 * a[None, :]).unsqueeze(-1), c2.bias.double() + w2 @ b, mode)
+            for side, seq in (("left", net.left_query_conv), ("right", net.right_query_conv)):
+                q1, bn1, q2, bn2 = seq[0], seq[2], seq[4], seq[5]
+                a1, b1 = _bn_affine(bn1)
+                a2, b2 = _bn_affine(bn2)
+                d = {"q1": _pack_conv1d(q1.weight.double(), q1.bias.double(), mode),
+                     # the BatchNorm after the ReLU cannot fold into the next 3-tap convolution (its zero padding is applied
+                     # AFTER the BatchNorm): it is applied in the first convolution's epilogue instead
+                     "post_a": a1.float().contiguous(), "post_b": b1.float().contiguous(),
+                     # Conv -> BN folds as usual
+                     "q2": _pack_conv1d(q2.weight.double() * a2[:, None, None], q2.bias.double() * a2 + b2, mode)}
+                out[side] = d
+        with _pu._CACHE_LOCK:
+            self.cache[(dev, mode)] = (key, out)
+        return out
+
+
+def _conv_rows(x, M, ld_x, L, rows_per_seq, relu, post=None):
+    y = torch.empty((M, _pu._pad4(L["cout"])), dtype=torch.float32, device=x.device)
+    _capi.conv1d_tc(x, M, ld_x, L["cin"], L["taps"], rows_per_seq, L["packed"], L["bias"], L["cout"], relu,
+                    None if post is None else post[0], None if post is None else post[1], y, y.shape[1], 0, L["mode"])
+    return y
 
 
 class AttentionBlock(nn.Module):
@@ -94,6 +170,34 @@ class TEHNet(nn.Module):
                                  nn.Conv1d(256, 256, 3, 1, 1), nn.BatchNorm1d(256))
         self.left_query_conv = query_conv()
         self.right_query_conv = query_conv()
+        self._head_weights = _HeadWeights()
+
+    def _heads_cuda(self, l0_points):
+        """classifier, query convolutions and attention of both hands on the tensor-core / CUDA kernels:
+        l0_points [B,256,N] -> (class_logits [B,C,N], left features [B,C,N], right features [B,C,N])"""
+        B, D, N = l0_points.shape
+        M = B * N
+        prec = _pu.get_mlp_precision()
+        mode = _pu._layer_mode({"tf32x3": _capi.TC_TF32X3, "bf16": _capi.TC_BF16}[prec])
+        W = self._head_weights.get(self, mode)
+        rec = getattr(l0_points, "_ev2h_fp_rows", None)
+        if rec is not None and rec[3] == l0_points._version and rec[2] == D:
+            x, ld = rec[0].view(M, rec[1]), rec[1]                      # the decoder's own rows
+        else:
+            x, ld = _pu._to_rows(l0_points).view(M, D), D
+        for L in (W["cls1"], W["cls2"], W["left"]["q1"], W["left"]["q2"], W["right"]["q1"], W["right"]["q2"]):
+            L["mode"] = mode
+        h = _conv_rows(x, M, ld, W["cls1"], N, relu=True)
+        logits = _conv_rows(h, M, h.shape[1], W["cls2"], N, relu=False)                 # [M, pad4(C)]
+        C = W["cls2"]["cout"]
+        seg = torch.empty((B, C, N), dtype=torch.float32, device=x.device)
+        _capi.transpose(logits, (N * logits.shape[1], logits.shape[1], 1), B, N, C, seg, C * N, N, 0)
+        feats = []
+        for side in ("left", "right"):
+            q = _conv_rows(x, M, ld, W[side]["q1"], N, relu=True, post=(W[side]["post_a"], W[side]["post_b"]))
+            q = _conv_rows(q, M, q.shape[1], W[side]["q2"], N, relu=False)
+            feats.append(_capi.class_attention(logits, logits.shape[1], q, q.shape[1], x, ld, B, N, C, D, D ** -0.5))
+        return seg, feats[0], feats[1]
 
     def trunk(self, xyz):
         """everything up to the per-hand attention features: -> (l0_xyz, class_logits, left_feat, right_feat)"""
@@ -107,6 +211,11 @@ class TEHNet(nn.Module):
         l2_points = self.fp3(l2_xyz, l3_xyz, l2_points, l3_points)
         l1_points = self.fp2(l1_xyz, l2_xyz, l1_points, l2_points)
         l0_points = self.fp1(l0_xyz, l1_xyz, None, l1_points)
+        if (l0_points.is_cuda and not _pu._wants_autograd(self, l0_points) and _pu.get_mlp_precision() in ("tf32x3", "bf16")
+                and self.classifier[0].kernel_size == (1,) and l0_points.shape[1] % 32 == 0):
+            with torch.no_grad():
+                seg_out, left, right = self._heads_cuda(l0_points)
+            return l0_xyz, seg_out, left, right
         seg_out = self.classifier(l0_points)
         left = self.attention_block(seg_out, l0_points, self.left_query_conv(l0_points))
         right = self.attention_block(seg_out, l0_points, self.right_query_conv(l0_points))

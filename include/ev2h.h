@@ -245,6 +245,28 @@ EV2H_API int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cou
 EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
                                  const float *bias, int Cout, int pool_rows, float *y, int ld_y,
                                  int y_col_off, int mode, ev2h_stream_t stream);
+/* ---- Conv1d over rows on the tensor cores ---------------------------------
+ * Replaces nn.Conv1d(Cin, Cout, kernel_size = taps, stride 1, padding = taps / 2) [+ ReLU] [+ BatchNorm1d (eval)
+ * AFTER the ReLU] of the segmentation classifier and the per-hand query convolutions (reference TEHNet.py:135-166,
+ * applied at :188-192) on point-major rows: x_rows [M, ld_x] holds M / rows_per_seq sequences of rows_per_seq
+ * positions x Cin channels; y[r] = act(sum_t W_t x[r + t - taps/2] + b) * post_scale + post_shift, rows outside a
+ * sequence counting as zero (the convolution's zero padding).  The shifted rows are gathered by the kernel's loaders;
+ * no im2col buffer exists.  w_packed = ev2h_tc_pack_weights_kc image of the [taps * Cin, Cout] matrix whose row
+ * t * Cin + ci is W[:, ci, t] (kc 32, row_align 16); post_scale / post_shift may be NULL.  taps in {1, 3, 5}. */
+EV2H_API int ev2h_conv1d_tc(const float *x_rows, int64_t M, int ld_x, int Cin, int taps, int rows_per_seq, const void *w_packed,
+                            const float *bias, int Cout, int relu, const float *post_scale, const float *post_shift,
+                            float *y, int ld_y, int y_col_off, int mode, ev2h_stream_t stream);
+
+/* ---- class-wise attention pooling ------------------------------------------
+ * Replaces AttentionBlock.forward (reference TEHNet.py:9-27): sim[b,c,d] = scale * sum_n key[b,n,c] query[b,n,d],
+ * softmax over the C classes, context[b,c,n] = sum_d softmax[b,c,d] value[b,n,d].  Rows are point-major:
+ * key_rows [B*N, ld_k] (C <= 8 columns), query_rows [B*N, ld_q], value_rows [B*N, ld_v] (D columns, D % 32 == 0,
+ * D <= 1024); partial [B, 8, C, D] fp32 workspace; out_cf [B, C, N] channel-first, the layout the hand regressor's
+ * set abstraction takes its features in (TEHNet.py:194-195).  Deterministic (fixed summation order), exact fp32. */
+EV2H_API int ev2h_class_attention_f32(const float *key_rows, int ld_k, const float *query_rows, int ld_q,
+                                      const float *value_rows, int ld_v, int B, int N, int C, int D, float scale,
+                                      float *partial, float *out_cf, ev2h_stream_t stream);
+
 /* ---- fused grouping + shared MLP + max-pool for ONE radius scale (tensor cores) ------------
  * Replaces the body of the per-radius loop of PointNetSetAbstractionMsg.forward
  * (pointnet2_utils.py:243-257): gather of the K neighbours of every centre, the three

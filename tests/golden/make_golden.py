@@ -241,6 +241,21 @@ def main():
             tr["grad." + n] = p.grad.numpy()
     np.savez_compressed(os.path.join(HERE, "train_sa2.npz"), **tr)
 
+    # ---- 8. the heads after the decoder: classifier, per-hand query convolutions, attention
+    # (TEHNet.py:188-192) on seeded point features ---------------------------------------------------------------
+    hst = synth.random_head_state(seed=600)
+    missing = net.load_state_dict(to_t(hst), strict=False)
+    assert not missing.unexpected_keys
+    feat = torch.from_numpy(np.random.RandomState(66).randn(2, 256, 2048).astype(np.float32))
+    with torch.no_grad():
+        seg_out = net.classifier(feat)
+        left_f = net.attention_block(seg_out, feat, net.left_query_conv(feat))
+        right_f = net.attention_block(seg_out, feat, net.right_query_conv(feat))
+        lq = net.left_query_conv(feat)
+    np.savez_compressed(os.path.join(HERE, "heads.npz"), weight_seed=np.array(600), feature_seed=np.array(66),
+                        seg_out=seg_out.numpy(), left_features=left_f.numpy(), right_features=right_f.numpy(),
+                        left_query_every8=lq.numpy()[:, :, ::8])
+
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -455,3 +455,64 @@ def test_tehnet_training_step_runs_end_to_end(monkeypatch):
         out = net(batch["events"], hands)
     assert out["class_logits"].shape == (3, 4, 2048) and out["left"]["vertices"].shape == (3, 778, 3)
     assert out["right"]["j3d"].shape == (3, 21, 3) and torch.isfinite(out["class_logits"]).all()
+
+
+# ------------------------------------------------------------------ N2: classifier + query convolutions + attention ----
+def _tehnet_with_heads(golden_heads, monkeypatch):
+    monkeypatch.setenv("ERPC", "1")
+    from ev2hands_b200 import tehnet
+    net = tehnet.TEHNet(n_pose_params=6)
+    st = synth.random_head_state(seed=int(golden_heads["weight_seed"]))
+    res = net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=False)
+    assert not res.unexpected_keys
+    return net.to(DEV).eval()
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32x3", 1e-5), ("bf16", 1e-2)])
+def test_heads_golden(golden, monkeypatch, prec, tol):
+    """the segmentation classifier, both query convolutions (3-tap Conv1d gathered by the kernel's
+    loaders, BatchNorm after the ReLU in the epilogue) and the class-wise attention, against the reference's own
+    modules (tests/golden/heads.npz, TEHNet.py:188-192)."""
+    g = golden("heads")
+    net = _tehnet_with_heads(g, monkeypatch)
+    feat = dev(np.random.RandomState(int(g["feature_seed"])).randn(2, 256, 2048).astype(np.float32))
+    old = e2h.get_mlp_precision()
+    try:
+        e2h.set_mlp_precision(prec)
+        with torch.no_grad():
+            seg, left, right = net._heads_cuda(feat)
+    finally:
+        e2h.set_mlp_precision(old)
+    assert seg.shape == (2, 4, 2048) and left.shape == (2, 4, 2048) and right.shape == (2, 4, 2048)
+    assert rel_err(seg, g["seg_out"]) <= tol
+    assert rel_err(left, g["left_features"]) <= tol
+    assert rel_err(right, g["right_features"]) <= tol
+
+
+def test_heads_kernels_vs_torch_modules_on_odd_shapes(monkeypatch):
+    """conv1d_tc and class_attention against the PyTorch modules they replace, sequence lengths that are not a
+    multiple of the 128-row tile (the convolution's zero padding must follow the SEQUENCE, not the tile)."""
+    torch.manual_seed(5)
+    B, N, Cin, Cout = 3, 200, 64, 96
+    x = torch.randn(B, Cin, N, device=DEV)
+    conv = torch.nn.Conv1d(Cin, Cout, 3, 1, 1).to(DEV)
+    from ev2hands_b200 import tehnet
+    rows = x.permute(0, 2, 1).contiguous().view(B * N, Cin)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = torch.relu(conv(x)) * 1.5 - 0.25
+        L = tehnet._pack_conv1d(conv.weight.detach().double(), conv.bias.detach().double(), _capi.TC_F16X3)
+        L["mode"] = _capi.TC_F16X3
+        post = (torch.full((Cout,), 1.5, device=DEV), torch.full((Cout,), -0.25, device=DEV))
+        got = tehnet._conv_rows(rows, B * N, Cin, L, N, relu=True, post=post)
+        assert rel_err(got.view(B, N, -1)[:, :, :Cout].permute(0, 2, 1), want) <= 1e-5
+        key, val, qry = torch.randn(B, 4, N, device=DEV), torch.randn(B, 64, N, device=DEV), torch.randn(B, 64, N, device=DEV)
+        want_a = tehnet.AttentionBlock()(key, val, qry)
+        r = lambda t: t.permute(0, 2, 1).contiguous().view(B * N, -1)      # noqa: E731
+        got_a = _capi.class_attention(r(key), 4, r(qry), 64, r(val), 64, B, N, 4, 64, 64 ** -0.5)
+        assert rel_err(got_a, want_a) <= 1e-5
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
