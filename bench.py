@@ -306,7 +306,7 @@ def time_training_config(device, rank, world, steps, barrier):
             d.record()
             barrier()
             ar_ms = c.elapsed_time(d) / 5
-        out = {"step_ms": step_ms, "allreduce_ms": ar_ms, "grad_bytes": red.bytes, "params": n_params, "loss": float(loss),
+        out = {"step_ms": step_ms, "allreduce_ms": ar_ms, "grad_bytes": red.bytes, "params": n_params, "loss": float(loss.detach()),
                "buckets": len(red.buckets), "local_batch": hi - lo}
         red.remove()
         del net, opt, red

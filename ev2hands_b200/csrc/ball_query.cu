@@ -133,7 +133,10 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
             if (i0 + 32 * w < i1) {
                 fl[w] = flagw[(i0 >> 5) + w];
                 const int pbase = (i0 >> 1) + 16 * w;
-#pragma unroll 4
+                // fully unrolled and branch-free: the hit bits are immediates and every radius costs one compare and one
+                // predicated OR per point (with a "skip if outside the largest radius" branch 83 % of the points took
+                // the hit path with ~2 of 32 lanes active: ncu, profiles/r02_geom16k_ncu_summary.txt)
+#pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     const float4 a = ptsA[pbase + (j >> 1)], c = ptsB[pbase + (j >> 1)];
                     // sqdist_expanded for two points at once: x*x', two FMAs, * -2, + |q|^2, + |p|^2 (geom.cuh)
@@ -145,15 +148,10 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
                     t = add2f(t, pack2f(c.z, c.w));
                     float d0, d1;
                     unpack2f(t, d0, d1);
-                    if (!(d0 > prm.r2_max)) {
 #pragma unroll
-                        for (int k = 0; k < NS; ++k)
-                            if (!(d0 > prm.r2[k])) m[k] |= 1u << j;          // group_idx[sqrdists > r**2] = N  (:102)
-                    }
-                    if (!(d1 > prm.r2_max)) {
-#pragma unroll
-                        for (int k = 0; k < NS; ++k)
-                            if (!(d1 > prm.r2[k])) m[k] |= 2u << j;
+                    for (int k = 0; k < NS; ++k) {
+                        if (!(d0 > prm.r2[k])) m[k] |= 1u << j;              // group_idx[sqrdists > r**2] = N  (:102)
+                        if (!(d1 > prm.r2[k])) m[k] |= 2u << j;
                     }
                 }
             }

@@ -18,97 +18,6 @@ namespace ev2h {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-template <int T, int P, int RP>      // RP = points per thread whose coordinates stay in registers (P: all; fewer for very long windows)
-__global__ void __launch_bounds__(T, 1)
-fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
-           const int64_t *__restrict__ start, int N, int S,
-           int32_t *__restrict__ out_idx, float *__restrict__ out_rows, float *__restrict__ out_cf) {
-    constexpr int NP = T * P;
-    constexpr int W = T / 32;
-    extern __shared__ float fps_smem[];
-    float *sx = fps_smem, *sy = fps_smem + NP, *sz = fps_smem + 2 * NP;
-    __shared__ unsigned long long slot[2][32];
-
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *base = xyz + (int64_t)b * sb;
-
-    float x[RP > 0 ? RP : 1], y[RP > 0 ? RP : 1], z[RP > 0 ? RP : 1];
-    float best[P];
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-        const int i = tid + j * T;
-        float px = 0.f, py = 0.f, pz = 0.f;
-        // Padding slots (i >= N) sit at the origin with best = 0: they can never
-        // beat a real point (real values are >= 0 and real indices are smaller).
-        best[j] = 0.f;
-        if (i < N) {
-            px = base[(int64_t)i * sn];
-            py = base[sc + (int64_t)i * sn];
-            pz = base[2 * sc + (int64_t)i * sn];
-            best[j] = 1e10f;   // torch.ones(B, N) * 1e10, pointnet2_utils.py:74
-        }
-        sx[i] = px; sy[i] = py; sz[i] = pz;
-        if (j < RP) { x[j] = px; y[j] = py; z[j] = pz; }
-    }
-    // device-resident start indices cannot be validated on the host without a sync: clamp (the host binding
-    // range-checks host tensors and raises like the reference's indexing would, pointnet2_utils.py:77)
-    const int64_t st0 = start[b];
-    int cur = st0 < 0 ? 0 : (st0 >= N ? N - 1 : (int)st0);
-    __syncthreads();
-
-    for (int s = 0; s < S; ++s) {
-        const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
-        if (tid == 0) {
-            if (out_idx) out_idx[(int64_t)b * S + s] = cur;
-            if (out_rows) {
-                float *o = out_rows + ((int64_t)b * S + s) * 3;
-                o[0] = cx; o[1] = cy; o[2] = cz;
-            }
-            if (out_cf) {
-                float *o = out_cf + (int64_t)b * 3 * S + s;
-                o[0] = cx; o[S] = cy; o[2 * (int64_t)S] = cz;
-            }
-        }
-        unsigned bv = 0u, bi = 0u;
-#pragma unroll
-        for (int j = 0; j < P; ++j) {
-            float px, py, pz;
-            if (j < RP) { px = x[j]; py = y[j]; pz = z[j]; }
-            else { const int i = tid + j * T; px = sx[i]; py = sy[i]; pz = sz[i]; }
-            const float dx = __fsub_rn(px, cx), dy = __fsub_rn(py, cy), dz = __fsub_rn(pz, cz);
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const float m = d < best[j] ? d : best[j];   // distance[mask] = dist[mask], :81-82
-            best[j] = m;
-            const unsigned vb = __float_as_uint(m);
-            if (j == 0 || vb > bv) { bv = vb; bi = (unsigned)(tid + j * T); }   // ascending j == ascending index
-        }
-        unsigned m = __reduce_max_sync(kFull, bv);
-        unsigned wi = __reduce_min_sync(kFull, bv == m ? bi : 0xffffffffu);
-        if (W > 1) {
-            if (lane == 0) slot[s & 1][warp] = ((unsigned long long)m << 32) | wi;
-            __syncthreads();
-            unsigned em = 0u, ei = 0xffffffffu;
-            if (lane < W) {
-                const unsigned long long e = slot[s & 1][lane];
-                em = (unsigned)(e >> 32); ei = (unsigned)e;
-            }
-            m = __reduce_max_sync(kFull, em);
-            wi = __reduce_min_sync(kFull, em == m ? ei : 0xffffffffu);
-        }
-        cur = (int)wi;
-    }
-}
-
-// ---- long windows: one window over a thread-block CLUSTER ---------------------------------------------------
-// N > 4096 does not fit one CTA's registers (the single-CTA kernel then re-reads 196 KB of coordinates from shared
-// memory per iteration: 3.1 us per dependent iteration at N = 16384).  Here CS CTAs of one cluster own NP = T * P
-// consecutive points each, coordinates and running minima in registers; per iteration every CTA finds its local
-// winner as above, then PUSHES the record (distance bits, index, x, y, z) into slot[rank] of every CTA of the cluster
-// through distributed shared memory - st.async with mbarrier complete_tx, so the stores themselves signal the
-// destination's barrier - and every CTA picks the global winner from the CS records: first index of the maximum, as
-// before.  Two record buffers / barriers alternate by iteration parity: a CTA can be at most one iteration ahead of
-// its peers (it needs their record of iteration s to start s + 1), so buffer s & 1 is never overwritten while read.
-// Distances use packed fp32x2 arithmetic (two IEEE operations per instruction, bit-identical to the scalar ones).
 namespace cl {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t cta_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -141,6 +50,111 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; a
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 }  // namespace cl
+
+template <int T, int P, int RP>      // RP = points per thread whose coordinates stay in registers (P: all; fewer for very long windows)
+__global__ void __launch_bounds__(T, 1)
+fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
+           const int64_t *__restrict__ start, int N, int S,
+           int32_t *__restrict__ out_idx, float *__restrict__ out_rows, float *__restrict__ out_cf) {
+    constexpr int NP = T * P;
+    constexpr int W = T / 32;
+    extern __shared__ float fps_smem[];
+    float *sx = fps_smem, *sy = fps_smem + NP, *sz = fps_smem + 2 * NP;
+    __shared__ unsigned long long slot[2][32];
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *base = xyz + (int64_t)b * sb;
+
+    static_assert(RP % 2 == 0 && P % 2 == 0, "register-resident points are kept as packed pairs");
+    // register-resident coordinates as packed pairs (points j, j + 1): the distance runs on fp32x2 instructions, two IEEE
+    // operations each, bit-identical to the scalar ones
+    uint64_t x2[RP > 0 ? RP / 2 : 1], y2[RP > 0 ? RP / 2 : 1], z2[RP > 0 ? RP / 2 : 1];
+    float best[P];
+#pragma unroll
+    for (int j = 0; j < P; j += 2) {
+        float px[2], py[2], pz[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = tid + (j + u) * T;
+            px[u] = py[u] = pz[u] = 0.f;
+            // Padding slots (i >= N) sit at the origin with best = 0: they can never
+            // beat a real point (real values are >= 0 and real indices are smaller).
+            best[j + u] = 0.f;
+            if (i < N) {
+                px[u] = base[(int64_t)i * sn];
+                py[u] = base[sc + (int64_t)i * sn];
+                pz[u] = base[2 * sc + (int64_t)i * sn];
+                best[j + u] = 1e10f;   // torch.ones(B, N) * 1e10, pointnet2_utils.py:74
+            }
+            sx[i] = px[u]; sy[i] = py[u]; sz[i] = pz[u];
+        }
+        if (j < RP) { x2[j / 2] = cl::pack2(px[0], px[1]); y2[j / 2] = cl::pack2(py[0], py[1]); z2[j / 2] = cl::pack2(pz[0], pz[1]); }
+    }
+    // device-resident start indices cannot be validated on the host without a sync: clamp (the host binding
+    // range-checks host tensors and raises like the reference's indexing would, pointnet2_utils.py:77)
+    const int64_t st0 = start[b];
+    int cur = st0 < 0 ? 0 : (st0 >= N ? N - 1 : (int)st0);
+    __syncthreads();
+
+    for (int s = 0; s < S; ++s) {
+        const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+        if (tid == 0) {
+            if (out_idx) out_idx[(int64_t)b * S + s] = cur;
+            if (out_rows) {
+                float *o = out_rows + ((int64_t)b * S + s) * 3;
+                o[0] = cx; o[1] = cy; o[2] = cz;
+            }
+            if (out_cf) {
+                float *o = out_cf + (int64_t)b * 3 * S + s;
+                o[0] = cx; o[S] = cy; o[2 * (int64_t)S] = cz;
+            }
+        }
+        unsigned bv = 0u, bi = 0u;
+        const uint64_t cx2 = cl::pack2(cx, cx), cy2 = cl::pack2(cy, cy), cz2 = cl::pack2(cz, cz);
+#pragma unroll
+        for (int j = 0; j < P; j += 2) {
+            uint64_t px2, py2, pz2;
+            if (j < RP) { px2 = x2[j / 2]; py2 = y2[j / 2]; pz2 = z2[j / 2]; }
+            else {
+                const int i0 = tid + j * T, i1 = i0 + T;
+                px2 = cl::pack2(sx[i0], sx[i1]); py2 = cl::pack2(sy[i0], sy[i1]); pz2 = cl::pack2(sz[i0], sz[i1]);
+            }
+            const uint64_t dx = cl::sub2(px2, cx2), dy = cl::sub2(py2, cy2), dz = cl::sub2(pz2, cz2);
+            float d0, d1;
+            cl::unpack2(cl::add2(cl::add2(cl::mul2(dx, dx), cl::mul2(dy, dy)), cl::mul2(dz, dz)), d0, d1);   // (dx^2 + dy^2) + dz^2, un-fused
+            const float m0 = d0 < best[j] ? d0 : best[j], m1 = d1 < best[j + 1] ? d1 : best[j + 1];          // distance[mask] = dist[mask], :81-82
+            best[j] = m0; best[j + 1] = m1;
+            const unsigned v0 = __float_as_uint(m0), v1 = __float_as_uint(m1);
+            if (j == 0 || v0 > bv) { bv = v0; bi = (unsigned)(tid + j * T); }   // ascending j == ascending index
+            if (v1 > bv) { bv = v1; bi = (unsigned)(tid + (j + 1) * T); }
+        }
+        unsigned m = __reduce_max_sync(kFull, bv);
+        unsigned wi = __reduce_min_sync(kFull, bv == m ? bi : 0xffffffffu);
+        if (W > 1) {
+            if (lane == 0) slot[s & 1][warp] = ((unsigned long long)m << 32) | wi;
+            __syncthreads();
+            unsigned em = 0u, ei = 0xffffffffu;
+            if (lane < W) {
+                const unsigned long long e = slot[s & 1][lane];
+                em = (unsigned)(e >> 32); ei = (unsigned)e;
+            }
+            m = __reduce_max_sync(kFull, em);
+            wi = __reduce_min_sync(kFull, em == m ? ei : 0xffffffffu);
+        }
+        cur = (int)wi;
+    }
+}
+
+// ---- long windows: one window over a thread-block CLUSTER ---------------------------------------------------
+// N > 4096 does not fit one CTA's registers (the single-CTA kernel then re-reads 196 KB of coordinates from shared
+// memory per iteration: 3.1 us per dependent iteration at N = 16384).  Here CS CTAs of one cluster own NP = T * P
+// consecutive points each, coordinates and running minima in registers; per iteration every CTA finds its local
+// winner as above, then PUSHES the record (distance bits, index, x, y, z) into slot[rank] of every CTA of the cluster
+// through distributed shared memory - st.async with mbarrier complete_tx, so the stores themselves signal the
+// destination's barrier - and every CTA picks the global winner from the CS records: first index of the maximum, as
+// before.  Two record buffers / barriers alternate by iteration parity: a CTA can be at most one iteration ahead of
+// its peers (it needs their record of iteration s to start s + 1), so buffer s & 1 is never overwritten while read.
+// Distances use packed fp32x2 arithmetic (two IEEE operations per instruction, bit-identical to the scalar ones).
 
 template <int T, int P, int CS>
 __global__ void __launch_bounds__(T, 1)

@@ -65,7 +65,7 @@ constexpr int FZ_MAX_PRODUCERS = 3;       // up to two loader groups + the epilo
 // next chunk (about half of its time per chunk), so those instances run TWO issuer warps that take alternate K
 // chunks of a layer: one thread's hand-shakes overlap the other's UMMAs.  (Two CTAs per SM overlap each other.)
 __host__ __device__ constexpr int fz_issuers(int occ) { return occ == 1 ? 2 : 1; }
-__host__ __device__ constexpr int fz_threads(int lg, int occ) { return 32 * (5 + 4 * lg + fz_issuers(occ)); }
+__host__ __device__ constexpr int fz_threads_ni(int lg, int ni) { return 32 * (5 + 4 * lg + ni); }
 
 enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1, FZ_MODE_MIXED = 2, FZ_MODE_F16X3 = 3 };
 __host__ __device__ constexpr bool fz_two_byte(int mode) { return mode == FZ_MODE_BF16 || mode == FZ_MODE_F16X3; }
@@ -130,7 +130,7 @@ struct Ring {
 // lifetime) and, for n >= ring size, the wait for the issuer's grant of that slot.  `bits` holds one
 // phase bit per slot, toggled every time this producer consumes a grant.
 __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs, int ring, uint32_t &bits, int tag) {
-    const int slot = (int)(ring == 2 ? (n_abs & 1u) : ring == 4 ? (n_abs & 3u) : (n_abs % 3u));          // the operand ring has 2, 3 or 4 slots
+    const int slot = (int)(ring == 2 ? (n_abs & 1u) : ring == 4 ? (n_abs & 3u) : ring == 6 ? (n_abs % 6u) : (n_abs % 3u));   // the operand ring has 2, 3, 4 or 6 slots
     if (n_abs >= (uint32_t)ring) {
         tc::mbar_wait(my_grants + slot, (bits >> slot) & 1u, tag);
         bits ^= 1u << slot;
@@ -138,12 +138,11 @@ __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs,
     return slot;
 }
 
-template <int MODE, int KC, int LG, int OCC>
-__global__ void __launch_bounds__(fz_threads(LG, OCC), OCC)
+template <int MODE, int KC, int LG, int OCC, int NI>
+__global__ void __launch_bounds__(fz_threads_ni(LG, NI), OCC)
 sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
-    constexpr int THREADS = fz_threads(LG, OCC);
-    constexpr int NI = fz_issuers(OCC);
+    constexpr int THREADS = fz_threads_ni(LG, NI);
     constexpr int EB = fz_two_byte(MODE) ? 2 : 4;
     constexpr int PARTS = MODE == FZ_MODE_BF16 ? 1 : 2;
     constexpr int A_PART = FZ_BLOCK_M * KC * EB;         // per precision part: 16 KB (tf32, KC 32) ... 8 KB
@@ -876,12 +875,12 @@ static FusedPlan fused_plan(int mode, const int32_t *cout) {
     return pl;
 }
 
-template <int MODE, int KC, int LG, int OCC>
+template <int MODE, int KC, int LG, int OCC, int NI = fz_issuers(OCC)>
 static int launch_fused(const FusedParams &p, size_t smem, unsigned grid, cudaStream_t st) {
-    auto k = sa_fused_tc_kernel<MODE, KC, LG, OCC>;
+    auto k = sa_fused_tc_kernel<MODE, KC, LG, OCC, NI>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_sa_msg_fused_tc: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
-    k<<<grid, fz_threads(LG, OCC), smem, st>>>(p);
+    k<<<grid, fz_threads_ni(LG, NI), smem, st>>>(p);
     return check_launch("ev2h_sa_msg_fused_tc");
 }
 
@@ -964,8 +963,10 @@ static int sa_msg_fused_impl(
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
     p.rowmap = rowmap; p.blockgroup = blockgroup; p.n_rows_dev = n_rows_dev;
     p.per_point = per_point ? 1 : 0; p.pts8 = pts8; p.D = D; p.range_flag = range_flag;
-    static const int pool_in_loader = [] { const char *e = getenv("EV2H_POOL_LOADER"); return (e && e[0] == '1') ? 1 : 0; }();
-    p.pool_loader = pool_in_loader;
+    // EV2H_POOL_LOADER: 1 = the loader warps pool layer 3 in every launch, 2 = only in per-point launches (sa2: cheap loaders,
+    // seven hand-off chunks and two pool blocks per tile in the epilogue warps), 0 / unset = the epilogue warps pool
+    static const int pool_in_loader = [] { const char *e = getenv("EV2H_POOL_LOADER"); return e ? atoi(e) : 0; }();
+    p.pool_loader = (pool_in_loader == 1 || (pool_in_loader == 2 && per_point)) ? 1 : 0;
     if (!per_point) {
         // layer-1 weights into the parameter block: channel pairs interleaved, [pair][k][2], so one 64-bit word feeds one packed FMA
         for (int ch = 0; ch < c1; ++ch) {
@@ -1002,10 +1003,17 @@ static int sa_msg_fused_impl(
     // at least 2 slots each; a third operand slot when affordable; weights get the rest (prefetched furthest ahead)
     p.sa = 2;
     if (budget - 3 * p.a_slot_bytes >= 3 * p.b_slot_bytes) p.sa = 3;
-    if (fz_issuers(occ) == 2) p.sa = budget - 4 * p.a_slot_bytes >= 4 * p.b_slot_bytes ? 4 : 2;      // a slot belongs to one issuer
+    // one-CTA-per-SM instances: two issuer warps (round 1) or one (EV2H_FUSED_NI=1; with the elected-lane issue of round 2
+    // a single issuer no longer needs ~1.5 k cycles per chunk, and the turn / init_done hand-shakes disappear)
+    static const int ni_env = [] { const char *e = getenv("EV2H_FUSED_NI"); return e ? atoi(e) : 0; }();
+    const int ni = (occ == 1 && ni_env == 1 && mode == FZ_MODE_F16X3) ? 1 : fz_issuers(occ);
+    if (ni == 2) p.sa = budget - 4 * p.a_slot_bytes >= 4 * p.b_slot_bytes ? 4 : 2;      // a slot belongs to one issuer
+    // with the pool in the loader warps layer 3 of a tile starts only after the previous tile's pool: a deeper operand ring
+    // lets the hand-off run further ahead of it
+    if (ni == 2 && p.pool_loader && p.sa == 4 && budget - 6 * p.a_slot_bytes >= 4 * p.b_slot_bytes) p.sa = 6;
     p.sb = (budget - p.sa * p.a_slot_bytes) / p.b_slot_bytes;
     if (p.sb > FZ_MAX_RING) p.sb = FZ_MAX_RING;
-    if (fz_issuers(occ) == 2) p.sb &= ~1;
+    if (ni == 2) p.sb &= ~1;
     if (p.sb < 2) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: rings do not fit in shared memory");
     const size_t smem = (size_t)p.sa * p.a_slot_bytes + (size_t)p.sb * p.b_slot_bytes + tail;
 
@@ -1031,6 +1039,7 @@ static int sa_msg_fused_impl(
         if (pl.occ == 2 && occ == 2 && lg2) return launch_fused<FZ_MODE_F16X3, 32, 2, 2>(p, smem, grid, st);
         if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_F16X3, 32, 1, 2>(p, smem, grid, st)
                                          : launch_fused<FZ_MODE_F16X3, 32, 1, 1>(p, smem, grid, st);
+        if (ni == 1) return launch_fused<FZ_MODE_F16X3, 32, 2, 1, 1>(p, smem, grid, st);
         return launch_fused<FZ_MODE_F16X3, 32, 2, 1>(p, smem, grid, st);
     }
     if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_BF16, 32, 1, 2>(p, smem, grid, st)

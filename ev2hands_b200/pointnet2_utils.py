@@ -513,8 +513,12 @@ class PointNetSetAbstractionMsg(nn.Module):
             c1_total = sum(w[0] for w, f in zip(widths, fused) if f)
             P = torch.empty((B * N, c1_total), dtype=torch.float32, device=xyz.device)
             C = torch.empty((B * S, c1_total), dtype=torch.float32, device=xyz.device)
-            ctr4 = torch.zeros((B * S, 4), dtype=torch.float32, device=xyz.device)
-            ctr4[:, :3] = centres_rows.reshape(B * S, 3)
+            if c_total % 4 == 0:
+                # this layer's output rows already hold [features | centre xyz | 0]: the centre GEMM reads the xyz columns in place
+                ctr4, ld_ctr = out_rows.view(B * S, ld_out)[:, c_total:], ld_out
+            else:
+                ctr4, ld_ctr = torch.zeros((B * S, 4), dtype=torch.float32, device=xyz.device), 4
+                ctr4[:, :3] = centres_rows.reshape(B * S, 3)
             # every fused scale's first layer in ONE GEMM: the folded weights side by side (same input rows)
             firsts = [layers[0] for layers, f in zip(all_layers, fused) if f]
             # keyed on the refold generation of every source stack (an address can be handed out again by the caching
@@ -545,7 +549,7 @@ class PointNetSetAbstractionMsg(nn.Module):
                 _capi.linear_tc_no_relu(x_pts, B * N, ld_pts, D + 3, cat["packed"][lmode], cat["bias"], c1_total, P, c1_total, 0, lmode)
             else:
                 _capi.linear_no_relu(x_pts, B * N, ld_pts, D + 3, cat["wt"], cat["bias"], c1_total, P, c1_total, 0)
-            _capi.linear_no_relu(ctr4, B * S, 4, 3, cat["wt_xyz"], cat["zero_bias"], c1_total, C, c1_total, 0)
+            _capi.linear_no_relu(ctr4, B * S, ld_ctr, 3, cat["wt_xyz"], cat["zero_bias"], c1_total, C, c1_total, 0)
             col = 0
             for layers, f in zip(all_layers, fused):
                 p_cols.append(col if f else None)
