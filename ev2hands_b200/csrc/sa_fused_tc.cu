@@ -56,7 +56,7 @@ namespace ev2h {
 constexpr int FZ_BLOCK_M = 128;
 constexpr int FZ_GEMMS = 2;               // layers 2 and 3
 constexpr int FZ_MAX_RING = 8;
-constexpr int FZ_MAX_PRODUCERS = 3;       // up to two loader groups + the epilogue warps
+constexpr int FZ_MAX_PRODUCERS = 4;       // up to two loader groups + up to two sets of epilogue warps
 // Template parameters of the kernel:
 //   KC  channels per K chunk (32, or 16 to halve the ring footprint so two CTAs share an SM)
 //   LG  loader groups of 4 warps;  threads = 32 * (6 + 4 LG): loaders, weight streamer, issuer, 4 epilogue warps
@@ -65,7 +65,7 @@ constexpr int FZ_MAX_PRODUCERS = 3;       // up to two loader groups + the epilo
 // next chunk (about half of its time per chunk), so those instances run TWO issuer warps that take alternate K
 // chunks of a layer: one thread's hand-shakes overlap the other's UMMAs.  (Two CTAs per SM overlap each other.)
 __host__ __device__ constexpr int fz_issuers(int occ) { return occ == 1 ? 2 : 1; }
-__host__ __device__ constexpr int fz_threads_ni(int lg, int ni) { return 32 * (5 + 4 * lg + ni); }
+__host__ __device__ constexpr int fz_threads_e(int lg, int ni, int es) { return 32 * (1 + 4 * lg + ni + 4 * es); }
 
 enum { FZ_MODE_BF16 = 0, FZ_MODE_TF32X3 = 1, FZ_MODE_MIXED = 2, FZ_MODE_F16X3 = 3 };
 __host__ __device__ constexpr bool fz_two_byte(int mode) { return mode == FZ_MODE_BF16 || mode == FZ_MODE_F16X3; }
@@ -138,11 +138,14 @@ __device__ __forceinline__ int acquire_slot(uint64_t *my_grants, uint32_t n_abs,
     return slot;
 }
 
-template <int MODE, int KC, int LG, int OCC, int NI>
-__global__ void __launch_bounds__(fz_threads_ni(LG, NI), OCC)
+//   ES  sets of 4 epilogue warps (1 or 2).  The epilogue warps are the serial resource of a tile (hand-off of layer 2's
+//       accumulator chunk by chunk, then the pool of layer 3): with two sets, set e takes the hand-off chunks c with
+//       c % 2 == e and pools 128-channel block e (or, with one block, every other tile).
+template <int MODE, int KC, int LG, int OCC, int NI, int ES>
+__global__ void __launch_bounds__(fz_threads_e(LG, NI, ES), OCC)
 sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(128) uint8_t fz_smem[];
-    constexpr int THREADS = fz_threads_ni(LG, NI);
+    constexpr int THREADS = fz_threads_e(LG, NI, ES);
     constexpr int EB = fz_two_byte(MODE) ? 2 : 4;
     constexpr int PARTS = MODE == FZ_MODE_BF16 ? 1 : 2;
     constexpr int A_PART = FZ_BLOCK_M * KC * EB;         // per precision part: 16 KB (tf32, KC 32) ... 8 KB
@@ -193,7 +196,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
         }
         for (int s = 0; s < p.sb; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
         for (int g = 0; g < FZ_GEMMS; ++g) {
-            tc::mbar_init(acc_full + g, NI); tc::mbar_init(acc_empty + g, g == 1 && p.pool_loader && LG == 2 && p.mb3 == 2 ? 256 : 128); tc::mbar_init(init_done + g, 1);
+            tc::mbar_init(acc_full + g, NI); tc::mbar_init(acc_empty + g, g == 0 ? 128 * ES : ((p.pool_loader ? LG : ES) == 2 && p.mb3 == 2 ? 256 : 128)); tc::mbar_init(init_done + g, 1);
             tc::mbar_init(turn + g, 1); tc::mbar_init(acc_full1_alt + g, NI);
         }
         tc::fence_mbar_init();
@@ -274,9 +277,10 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     // the pool of tile i now overlaps the hand-off of tile i + 1.  With two loader groups and two 128-channel blocks
     // group g pools block g; with one block the groups alternate tiles.
     const bool pool_loader = p.pool_loader != 0;
-    const int pool_groups = (pool_loader && LG == 2 && p.mb3 == 2) ? 2 : 1;
-    const bool pool_alt = pool_loader && LG == 2 && p.mb3 == 1;      // the two loader groups pool alternate tiles
-    auto pools_tile = [&](uint32_t it_, int grp_) { return pool_loader && (LG == 1 || pool_groups == 2 || (int)(it_ % LG) == grp_); };
+    const int pool_sets = pool_loader ? LG : ES;                      // warp sets that share the pool: loader groups or epilogue sets
+    const int pool_groups = (pool_sets == 2 && p.mb3 == 2) ? 2 : 1;   // 2: set g pools 128-channel block g of every tile
+    const bool pool_alt = pool_sets == 2 && p.mb3 == 1;               // one block: the two sets pool alternate tiles
+    auto pools_tile = [&](uint32_t it_, int set_) { return pool_sets == 1 || pool_groups == 2 || (int)(it_ & 1u) == set_; };
     auto pool_tile = [&](uint32_t it, int64_t tile, int q, int mb_lo, int mb_hi, bool ptrace) {
         // layer 3 (transposed accumulator): lane = output channel, columns = the tile's rows.  The max over the K rows
         // of a group = per-thread max over K columns; bias and ReLU commute with the max (both monotone) and are
@@ -481,10 +485,10 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                     if (tid == 0) FZ_TRACE(1, 3, it, kc);
                 }
                 // this tile's rows are on their way: pool the previous tile while its successor's layer 2 runs
-                if (it > 0 && pools_tile(it - 1, grp))
+                if (pool_loader && it > 0 && pools_tile(it - 1, grp))
                     pool_tile(it - 1, tile - gridDim.x, wq, pool_groups == 2 ? grp : 0, pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
             }
-            if (it > 0 && pools_tile(it - 1, grp))
+            if (pool_loader && it > 0 && pools_tile(it - 1, grp))
                 pool_tile(it - 1, (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x, wq, pool_groups == 2 ? grp : 0,
                           pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
         } else {
@@ -574,7 +578,10 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
             };
 
             int32_t p_cur[4], c_cur[4], p_nxt[4], c_nxt[4];      // row indices fit 32 bits (B * N, B * S < 2^31 is checked on the host)
-            float4 v0[NV], v1[NV];                  // P rows of my first two chunks of the coming tile
+            // P rows of my first two chunks of the coming tile (only the first one with two epilogue sets: the second
+            // buffer costs 32 registers that the 608-thread instance does not have)
+            constexpr bool PF2 = ES == 1;
+            float4 v0[NV], v1[PF2 ? NV : 1];
             int kc0 = -1, kc1 = -1;
             auto prefetch = [&](int64_t tile, uint32_t it) {
                 kc0 = kc1 = -1;
@@ -583,7 +590,10 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 for (int kc = 0; kc < nc0; ++kc) {
                     if (!mine(it, kc)) continue;
                     if (kc0 < 0) { kc0 = kc; load_p(p_nxt, kc, v0); }
-                    else if (kc1 < 0) { kc1 = kc; load_p(p_nxt, kc, v1); }
+                    else if (PF2 && kc1 < 0) {
+                        kc1 = kc;
+                        if constexpr (PF2) load_p(p_nxt, kc, v1);
+                    }
                 }
             };
             prefetch(blockIdx.x, 0);
@@ -595,14 +605,16 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 for (int kc = 0; kc < nc0; ++kc) {
                     if (!mine(it, kc)) continue;
                     if (kc == u0) emit(p_cur, c_cur, it, kc, v0);
-                    else if (kc == u1) emit(p_cur, c_cur, it, kc, v1);
+                    else if (PF2 && kc == u1) {
+                        if constexpr (PF2) emit(p_cur, c_cur, it, kc, v1);
+                    }
                     else { float4 vj[NV]; load_p(p_cur, kc, vj); emit(p_cur, c_cur, it, kc, vj); }
                 }
                 prefetch(tile + gridDim.x, it + 1);     // my rows are out: fetch the next tile's P rows now
-                if (it > 0 && pools_tile(it - 1, grp))  // ... and pool the previous tile under their latency
+                if (pool_loader && it > 0 && pools_tile(it - 1, grp))  // ... and pool the previous tile under their latency
                     pool_tile(it - 1, tile - gridDim.x, wq, pool_groups == 2 ? grp : 0, pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
             }
-            if (it > 0 && pools_tile(it - 1, grp))
+            if (pool_loader && it > 0 && pools_tile(it - 1, grp))
                 pool_tile(it - 1, (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x, wq, pool_groups == 2 ? grp : 0,
                           pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
         }
@@ -724,7 +736,8 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                         const uint32_t x0 = a_base + a_slot * a_slot_d, w0 = b_base + b_slot * b_slot_d;
                         const uint32_t acc0 = c > 0 ? 1u : 0u;
                         // the producer that fills this operand slot next: a loader group or the epilogue warps
-                        const uint32_t next_prod = g_q < (uint32_t)nc0 ? (LG == 1 ? 0u : (g_it * (uint32_t)nc0 + g_q) % LG) : (uint32_t)LG;
+                        const uint32_t next_prod = g_q < (uint32_t)nc0 ? (LG == 1 ? 0u : (g_it * (uint32_t)nc0 + g_q) % LG)
+                                                                       : (uint32_t)LG + (ES == 1 ? 0u : ((g_q - (uint32_t)nc0) & 1u));
                         if (tc::elect_one()) {
                         if (c + 1 < nch[g] || ksl[g] == (uint32_t)K_STEPS) {
 #pragma unroll
@@ -769,7 +782,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                     }
                     // this issuer's UMMAs into accumulator g are done (all of them with NI == 1)
                     if (tc::elect_one())
-                        tc::umma_commit_u32(g == 1 && p.pool_loader && LG == 2 && mb3 == 1 ? tc::smem_u32(acc_full1_alt) + 8 * (it & 1) : acc_full_u + 8 * g);
+                        tc::umma_commit_u32(g == 1 && (p.pool_loader ? LG : ES) == 2 && mb3 == 1 ? tc::smem_u32(acc_full1_alt) + 8 * (it & 1) : acc_full_u + 8 * g);
                     __syncwarp();
                 }
             }
@@ -778,7 +791,8 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
     } else {
         // =============================== epilogue warps ===============================
         const int q = warp & 3, r = q * 32 + lane;       // TMEM lane quadrant of a warp is warp_id % 4
-        uint64_t *my_grants = a_grant + LG * FZ_MAX_RING;
+        const int eset = (warp - EPI_WARP0) >> 2;        // epilogue set: hand-off chunks c with c % ES == eset
+        uint64_t *my_grants = a_grant + (LG + eset) * FZ_MAX_RING;
         uint32_t bits = 0;
         uint32_t it = 0;
         const bool eprof = warp == EPI_WARP0 && lane == 0;    // the thread that writes this role's trace events
@@ -811,11 +825,11 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 // stored (tcgen05.wait::ld waits for every outstanding load, so exactly one is outstanding at a wait)
                 uint32_t ra[16], rb[16];
                 float v[16];
-                tc::tmem_ld16(t_addr, ra);
-                for (int c = 0; c < nc1; ++c) {
+                if (eset < nc1) tc::tmem_ld16(t_addr + eset * KC, ra);
+                for (int c = eset; c < nc1; c += ES) {
                     tc::tmem_ld_wait();                                       // ra: columns c * KC .. + 15
                     if constexpr (KC == 32) tc::tmem_ld16(t_addr + c * KC + 16, rb);
-                    else if (c + 1 < nc1) tc::tmem_ld16(t_addr + (c + 1) * KC, rb);
+                    else if (c + ES < nc1) tc::tmem_ld16(t_addr + (c + ES) * KC, rb);
                     act16(ra, c * KC, v);
                     if (eprof) FZ_TRACE(4, 2, it, c);
                     const int slot = acquire_slot(my_grants, it * Q + (uint32_t)(nc0 + c), p.sa, bits, 70);
@@ -824,7 +838,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                     store_row_16(st, r, 0, v);
                     if constexpr (KC == 32) {
                         tc::tmem_ld_wait();                                   // rb: columns c * KC + 16 .. + 31
-                        if (c + 1 < nc1) tc::tmem_ld16(t_addr + (c + 1) * KC, ra);
+                        if (c + ES < nc1) tc::tmem_ld16(t_addr + (c + ES) * KC, ra);
                         act16(rb, c * KC + 16, v);
                         store_row_16(st, r, 16, v);
                     } else {
@@ -838,7 +852,8 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 0);
             }
-            if (!pool_loader) pool_tile(it, tile, q, 0, p.mb3, eprof);
+            if (!pool_loader && pools_tile(it, eset))
+                pool_tile(it, tile, q, pool_groups == 2 ? eset : 0, pool_groups == 2 ? eset + 1 : p.mb3, eprof);
         }
     }
 
@@ -875,12 +890,12 @@ static FusedPlan fused_plan(int mode, const int32_t *cout) {
     return pl;
 }
 
-template <int MODE, int KC, int LG, int OCC, int NI = fz_issuers(OCC)>
+template <int MODE, int KC, int LG, int OCC, int NI = fz_issuers(OCC), int ES = 1>
 static int launch_fused(const FusedParams &p, size_t smem, unsigned grid, cudaStream_t st) {
-    auto k = sa_fused_tc_kernel<MODE, KC, LG, OCC, NI>;
+    auto k = sa_fused_tc_kernel<MODE, KC, LG, OCC, NI, ES>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_sa_msg_fused_tc: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
-    k<<<grid, fz_threads_ni(LG, NI), smem, st>>>(p);
+    k<<<grid, fz_threads_e(LG, NI, ES), smem, st>>>(p);
     return check_launch("ev2h_sa_msg_fused_tc");
 }
 
@@ -996,7 +1011,7 @@ static int sa_msg_fused_impl(
 
     p.a_slot_bytes = PARTS * FZ_BLOCK_M * KC * EB;
     p.b_slot_bytes = PARTS * max_n * KC * EB;
-    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 5 * FZ_GEMMS) * 8 + 16 + boff * 4;
+    const int tail = ((3 + FZ_MAX_PRODUCERS) * FZ_MAX_RING + 5 * FZ_GEMMS) * 8 + 16 + boff * 4;      // barriers, TMEM slot, biases
     int occ = pl.occ;
     int budget = (occ == 2 ? 113 : 227) * 1024 - tail - 512;
     if (occ == 2 && budget < 2 * p.a_slot_bytes + 2 * p.b_slot_bytes) { occ = 1; budget = 227 * 1024 - tail - 512; }
@@ -1036,6 +1051,10 @@ static int sa_msg_fused_impl(
     }
     if (mode == FZ_MODE_F16X3) {
         static const bool lg2 = [] { const char *e = getenv("EV2H_FUSED_LG2"); return e && e[0] == '1'; }();   // experiment: two loader groups at two CTAs per SM (448 threads, 72 registers)
+        // two sets of epilogue warps: EV2H_FUSED_ES = 1 (one set everywhere), 2 (two sets in the one-CTA-per-SM instances), 3 (also at two CTAs per SM)
+        static const int es_env = [] { const char *e = getenv("EV2H_FUSED_ES"); return e ? atoi(e) : 1; }();
+        if (es_env >= 2 && ni == 2 && !(pl.occ == 2)) return launch_fused<FZ_MODE_F16X3, 32, 2, 1, 2, 2>(p, smem, grid, st);
+        if (es_env >= 3 && pl.occ == 2 && occ == 2) return launch_fused<FZ_MODE_F16X3, 32, 1, 2, 1, 2>(p, smem, grid, st);
         if (pl.occ == 2 && occ == 2 && lg2) return launch_fused<FZ_MODE_F16X3, 32, 2, 2>(p, smem, grid, st);
         if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_F16X3, 32, 1, 2>(p, smem, grid, st)
                                          : launch_fused<FZ_MODE_F16X3, 32, 1, 1>(p, smem, grid, st);

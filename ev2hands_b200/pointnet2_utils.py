@@ -60,6 +60,22 @@ _DEDUP = os.environ.get("EV2H_DEDUP", "1") != "0"
 # The per-layer tensor-core kernel (sa3, the decoder, sa2's per-point first layer) uses the same split products as the
 # fused kernel for "tf32x3"; EV2H_LINEAR_MIXED=0 keeps three tf32 products there.
 _LINEAR_MIXED = os.environ.get("EV2H_LINEAR_MIXED", "1") != "0"
+# The fused launches of a layer's radius scales are independent (same inputs, different output columns): issued on
+# separate streams the tail of one persistent launch (pipeline drain, last partial wave) could overlap the start of the
+# next.  Measured on B200 (B = 64, graph replay): 1.664 ms with, 1.638 ms without - no gain, so it is off by default.
+_SCALE_STREAMS = os.environ.get("EV2H_SCALE_STREAMS", "0") == "1"
+_scale_streams = {}
+
+
+def _scale_stream(device, i):
+    key = (device, threading.get_ident(), i)
+    with _CACHE_LOCK:
+        st = _scale_streams.get(key)
+        if st is None:
+            st = _scale_streams[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 # Evaluate layer 1 per point (instead of per gathered row) also for narrow inputs; experiment switch.
 _PER_POINT_ALWAYS = os.environ.get("EV2H_PER_POINT", "0") == "1"
 
@@ -562,9 +578,16 @@ class PointNetSetAbstractionMsg(nn.Module):
         feats_rows = None
         ld_x = _pad4(D + 3)
         k_off = col = 0
+        main_stream = torch.cuda.current_stream(xyz.device)
+        forked = []
+        n_fused_seen = 0
         for i, K in enumerate(self.nsample_list):
             layers = all_layers[i]
             if fused[i]:
+                launch_stream = main_stream
+                if _SCALE_STREAMS and sum(fused) > 1 and n_fused_seen > 0 and not _capi.LOG.timing:
+                    launch_stream = _scale_stream(xyz.device, n_fused_seen)
+                n_fused_seen += 1
                 use = layers[1:]      # layer 1: per point (wide inputs) or in the loader warps (<= 8 channels)
                 kc = _capi.fused_kc(fmode, [L["cout"] for L in use])
                 packed = []
@@ -575,12 +598,16 @@ class PointNetSetAbstractionMsg(nn.Module):
                         L["packed"][key] = _capi.tc_pack(L["wt"], L["cin"], L["cout"], fmode, kc, key[2])
                     packed.append(L["packed"][key])
                 w1_host, b1_host = (None, None) if per_point else _host_first_layer(layers[0])
-                _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D, w1_host, b1_host,
-                                   P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
-                                   C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
-                                   layers[0]["cout"], [L["cout"] for L in use], packed, [L["bias"] for L in use],
-                                   out_rows, ld_out, col, fmode,
-                                   compact=None if compact is None else (compact[0][i], compact[1][i], compact[2][i:i + 1]))
+                if launch_stream is not main_stream:
+                    launch_stream.wait_stream(main_stream)        # behind everything issued so far (inputs, packed weights)
+                    forked.append(launch_stream)
+                with torch.cuda.stream(launch_stream):
+                    _capi.sa_msg_fused(ball, k_off, centres_rows, B, N, S, K, pts8, D, w1_host, b1_host,
+                                       P, 0 if P is None else P.shape[1], p_cols[i] if per_point else 0,
+                                       C, 0 if C is None else C.shape[1], p_cols[i] if per_point else 0,
+                                       layers[0]["cout"], [L["cout"] for L in use], packed, [L["bias"] for L in use],
+                                       out_rows, ld_out, col, fmode,
+                                       compact=None if compact is None else (compact[0][i], compact[1][i], compact[2][i:i + 1]))
             else:
                 if feats_rows is None and rows_in is not None:
                     feats_rows = rows_in.rows[:, :, :D].contiguous()
@@ -597,6 +624,8 @@ class PointNetSetAbstractionMsg(nn.Module):
                     _mlp_rows(x, M, ld_x, layers, K, out_rows[b0:b0 + nb], ld_out, col)
             k_off += K
             col += layers[-1]["cout"]
+        for st in forked:
+            main_stream.wait_stream(st)
         return _LevelRows(out_rows, c_total, geom["new_xyz"])
 
     def _forward_autograd(self, xyz, points, strides, centres_rows, ball):
