@@ -107,7 +107,6 @@ struct FusedParams {
     // rings
     int sa, sb, a_slot_bytes, b_slot_bytes;
     int32_t *range_flag;                         // optional: bit 0 set when an F16X3 operand left the fp16 range
-    int pool_loader;                             // 1: the loader warps pool layer 3 (experiment), 0: the epilogue warps do
     long long *dbg;     // optional trace buffer (EV2H_FUSED_TRACE builds only, tools/fused_trace.py)
 };
 
@@ -196,7 +195,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
         }
         for (int s = 0; s < p.sb; ++s) { tc::mbar_init(b_full + s, 1); tc::mbar_init(b_empty + s, 1); }
         for (int g = 0; g < FZ_GEMMS; ++g) {
-            tc::mbar_init(acc_full + g, NI); tc::mbar_init(acc_empty + g, g == 0 ? 128 * ES : ((p.pool_loader ? LG : ES) == 2 && p.mb3 == 2 ? 256 : 128)); tc::mbar_init(init_done + g, 1);
+            tc::mbar_init(acc_full + g, NI); tc::mbar_init(acc_empty + g, g == 0 ? 128 * ES : (ES == 2 && p.mb3 == 2 ? 256 : 128)); tc::mbar_init(init_done + g, 1);
             tc::mbar_init(turn + g, 1); tc::mbar_init(acc_full1_alt + g, NI);
         }
         tc::fence_mbar_init();
@@ -271,13 +270,11 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
         }
     };
 
-    // ---- max-pool of a tile's layer-3 accumulator.  Runs in the LOADER warps (warp w of a loader group owns TMEM lane
-    // quadrant w % 4, like an epilogue warp): the epilogue warps are the serial bottleneck of a tile (round-2 timeline:
-    // hand-off 5.2 k + pool 3.7 k cycles per tile in the same four warps, loaders mostly waiting for slot grants), so
-    // the pool of tile i now overlaps the hand-off of tile i + 1.  With two loader groups and two 128-channel blocks
-    // group g pools block g; with one block the groups alternate tiles.
-    const bool pool_loader = p.pool_loader != 0;
-    const int pool_sets = pool_loader ? LG : ES;                      // warp sets that share the pool: loader groups or epilogue sets
+    // ---- max-pool of a tile's layer-3 accumulator (epilogue warps, after the tile's hand-off).  With two epilogue sets and
+    // two 128-channel blocks set e pools block e; with one block the sets alternate tiles.  (Round 2 also tried the pool
+    // in the LOADER warps, to overlap it with the next tile's hand-off: slower in every variant - DESIGN.md section 4 -
+    // and removed.)
+    const int pool_sets = ES;                                         // epilogue warp sets that share the pool
     const int pool_groups = (pool_sets == 2 && p.mb3 == 2) ? 2 : 1;   // 2: set g pools 128-channel block g of every tile
     const bool pool_alt = pool_sets == 2 && p.mb3 == 1;               // one block: the two sets pool alternate tiles
     auto pools_tile = [&](uint32_t it_, int set_) { return pool_sets == 1 || pool_groups == 2 || (int)(it_ & 1u) == set_; };
@@ -291,7 +288,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
         const int my_gid = (compact && lane < 16 && (tile * 16 + lane) * 8 < M) ? __ldg(p.blockgroup + tile * 16 + lane) : -1;   // -1: past the end
         if (pool_alt) tc::mbar_wait(acc_full1_alt + (it & 1), (it >> 1) & 1, 62);
         else tc::mbar_wait(acc_full + 1, it & 1, 61);
-        if (ptrace) { if (pool_loader) FZ_TRACE(1, 5, it, 0); else FZ_TRACE(4, 5, it, 0); }
+        if (ptrace) FZ_TRACE(4, 5, it, 0);
         tc::tc_fence_after();
         const int64_t rows_left = M - m0;                       // rows >= M do not exist (last tile)
         for (int mb = mb_lo; mb < mb_hi; ++mb) {
@@ -374,7 +371,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
             }
             if (compact) flush(true);
         }
-        if (ptrace) { if (pool_loader) FZ_TRACE(1, 6, it, 0); else FZ_TRACE(4, 6, it, 0); }
+        if (ptrace) FZ_TRACE(4, 6, it, 0);
     };
 
     if (is_loader) {
@@ -484,13 +481,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                     tc::mbar_arrive(a_full + slot);
                     if (tid == 0) FZ_TRACE(1, 3, it, kc);
                 }
-                // this tile's rows are on their way: pool the previous tile while its successor's layer 2 runs
-                if (pool_loader && it > 0 && pools_tile(it - 1, grp))
-                    pool_tile(it - 1, tile - gridDim.x, wq, pool_groups == 2 ? grp : 0, pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
             }
-            if (pool_loader && it > 0 && pools_tile(it - 1, grp))
-                pool_tile(it - 1, (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x, wq, pool_groups == 2 ? grp : 0,
-                          pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
         } else {
             // ---- per-point mode: relu(P[p] - C[s]); octet lane mapping, P rows prefetched a tile ahead ----
             // 8 consecutive lanes = 8 consecutive rows of ONE 16-byte operand chunk (conflict-free store),
@@ -611,12 +602,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                     else { float4 vj[NV]; load_p(p_cur, kc, vj); emit(p_cur, c_cur, it, kc, vj); }
                 }
                 prefetch(tile + gridDim.x, it + 1);     // my rows are out: fetch the next tile's P rows now
-                if (pool_loader && it > 0 && pools_tile(it - 1, grp))  // ... and pool the previous tile under their latency
-                    pool_tile(it - 1, tile - gridDim.x, wq, pool_groups == 2 ? grp : 0, pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
             }
-            if (pool_loader && it > 0 && pools_tile(it - 1, grp))
-                pool_tile(it - 1, (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x, wq, pool_groups == 2 ? grp : 0,
-                          pool_groups == 2 ? grp + 1 : p.mb3, tid == 0);
         }
     } else if (warp == STREAMER_WARP) {
         // =============================== weight streamer ===============================
@@ -782,7 +768,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                     }
                     // this issuer's UMMAs into accumulator g are done (all of them with NI == 1)
                     if (tc::elect_one())
-                        tc::umma_commit_u32(g == 1 && (p.pool_loader ? LG : ES) == 2 && mb3 == 1 ? tc::smem_u32(acc_full1_alt) + 8 * (it & 1) : acc_full_u + 8 * g);
+                        tc::umma_commit_u32(g == 1 && ES == 2 && mb3 == 1 ? tc::smem_u32(acc_full1_alt) + 8 * (it & 1) : acc_full_u + 8 * g);
                     __syncwarp();
                 }
             }
@@ -852,7 +838,7 @@ sa_fused_tc_kernel(const __grid_constant__ FusedParams p) {
                 tc::tc_fence_before();
                 tc::mbar_arrive(acc_empty + 0);
             }
-            if (!pool_loader && pools_tile(it, eset))
+            if (pools_tile(it, eset))
                 pool_tile(it, tile, q, pool_groups == 2 ? eset : 0, pool_groups == 2 ? eset + 1 : p.mb3, eprof);
         }
     }
@@ -978,10 +964,6 @@ static int sa_msg_fused_impl(
     p.B = B; p.N = N; p.S = S; p.K = K; p.idx = idx; p.idx_ld = idx_ld; p.k_off = k_off; p.centres = centres_rows;
     p.rowmap = rowmap; p.blockgroup = blockgroup; p.n_rows_dev = n_rows_dev;
     p.per_point = per_point ? 1 : 0; p.pts8 = pts8; p.D = D; p.range_flag = range_flag;
-    // EV2H_POOL_LOADER: 1 = the loader warps pool layer 3 in every launch, 2 = only in per-point launches (sa2: cheap loaders,
-    // seven hand-off chunks and two pool blocks per tile in the epilogue warps), 0 / unset = the epilogue warps pool
-    static const int pool_in_loader = [] { const char *e = getenv("EV2H_POOL_LOADER"); return e ? atoi(e) : 0; }();
-    p.pool_loader = (pool_in_loader == 1 || (pool_in_loader == 2 && per_point)) ? 1 : 0;
     if (!per_point) {
         // layer-1 weights into the parameter block: channel pairs interleaved, [pair][k][2], so one 64-bit word feeds one packed FMA
         for (int ch = 0; ch < c1; ++ch) {
@@ -1023,12 +1005,18 @@ static int sa_msg_fused_impl(
     static const int ni_env = [] { const char *e = getenv("EV2H_FUSED_NI"); return e ? atoi(e) : 0; }();
     const int ni = (occ == 1 && ni_env == 1 && mode == FZ_MODE_F16X3) ? 1 : fz_issuers(occ);
     if (ni == 2) p.sa = budget - 4 * p.a_slot_bytes >= 4 * p.b_slot_bytes ? 4 : 2;      // a slot belongs to one issuer
-    // with the pool in the loader warps layer 3 of a tile starts only after the previous tile's pool: a deeper operand ring
-    // lets the hand-off run further ahead of it
-    if (ni == 2 && p.pool_loader && p.sa == 4 && budget - 6 * p.a_slot_bytes >= 4 * p.b_slot_bytes) p.sa = 6;
     p.sb = (budget - p.sa * p.a_slot_bytes) / p.b_slot_bytes;
     if (p.sb > FZ_MAX_RING) p.sb = FZ_MAX_RING;
     if (ni == 2) p.sb &= ~1;
+    {   // experiment switches: ring depths (operand ring for two-CTA / one-CTA instances), checked against the budget below
+        static const int sa2 = [] { const char *e = getenv("EV2H_FUSED_SA_OCC2"); return e ? atoi(e) : 0; }();
+        static const int sa1 = [] { const char *e = getenv("EV2H_FUSED_SA_OCC1"); return e ? atoi(e) : 0; }();
+        const int want = occ == 2 ? sa2 : sa1;
+        if (want >= 2 && want <= FZ_MAX_RING && (want == 2 || want == 3 || want == 4 || want == 6) && (ni == 1 || want % 2 == 0)) {
+            const int sb_new = (budget - want * p.a_slot_bytes) / p.b_slot_bytes;
+            if (sb_new >= 2) { p.sa = want; p.sb = sb_new > FZ_MAX_RING ? FZ_MAX_RING : sb_new; if (ni == 2) p.sb &= ~1; }
+        }
+    }
     if (p.sb < 2) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_sa_msg_fused_tc: rings do not fit in shared memory");
     const size_t smem = (size_t)p.sa * p.a_slot_bytes + (size_t)p.sb * p.b_slot_bytes + tail;
 
@@ -1050,12 +1038,6 @@ static int sa_msg_fused_impl(
         return launch_fused<FZ_MODE_TF32X3, 32, 2, 1>(p, smem, grid, st);
     }
     if (mode == FZ_MODE_F16X3) {
-        static const bool lg2 = [] { const char *e = getenv("EV2H_FUSED_LG2"); return e && e[0] == '1'; }();   // experiment: two loader groups at two CTAs per SM (448 threads, 72 registers)
-        // two sets of epilogue warps: EV2H_FUSED_ES = 1 (one set everywhere), 2 (two sets in the one-CTA-per-SM instances), 3 (also at two CTAs per SM)
-        static const int es_env = [] { const char *e = getenv("EV2H_FUSED_ES"); return e ? atoi(e) : 1; }();
-        if (es_env >= 2 && ni == 2 && !(pl.occ == 2)) return launch_fused<FZ_MODE_F16X3, 32, 2, 1, 2, 2>(p, smem, grid, st);
-        if (es_env >= 3 && pl.occ == 2 && occ == 2) return launch_fused<FZ_MODE_F16X3, 32, 1, 2, 1, 2>(p, smem, grid, st);
-        if (pl.occ == 2 && occ == 2 && lg2) return launch_fused<FZ_MODE_F16X3, 32, 2, 2>(p, smem, grid, st);
         if (pl.occ == 2) return occ == 2 ? launch_fused<FZ_MODE_F16X3, 32, 1, 2>(p, smem, grid, st)
                                          : launch_fused<FZ_MODE_F16X3, 32, 1, 1>(p, smem, grid, st);
         if (ni == 1) return launch_fused<FZ_MODE_F16X3, 32, 2, 1, 1>(p, smem, grid, st);

@@ -66,11 +66,14 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parit
         : "memory");
     return ok != 0;
 }
+#ifndef EV2H_WAIT_HINT_NS
+#define EV2H_WAIT_HINT_NS 20000u      // suspend-time hint of the waits (experiment knob: -DEV2H_WAIT_HINT_NS=...)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = 0) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t spins = 0;
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    while (!mbar_try_wait_hint(bar, parity, EV2H_WAIT_HINT_NS)) {
         if ((++spins & 15u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(tag, parity);   // ~2 s
     }
 }
@@ -85,7 +88,7 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity, int
     uint32_t spins = 0;
     for (;;) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(EV2H_WAIT_HINT_NS) : "memory");
         if (ok) return;
         if ((++spins & 15u) == 0 && clock64() - t0 > 4000000000LL) mbar_timeout(tag, parity);   // ~2 s
     }

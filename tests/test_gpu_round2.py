@@ -516,3 +516,26 @@ def test_heads_kernels_vs_torch_modules_on_odd_shapes(monkeypatch):
         assert rel_err(got_a, want_a) <= 1e-5
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+# ------------------------------------------------------------------ fp16-split numeric range flag ---------------
+def test_fp16_split_overflow_raises_the_range_flag():
+    """the default fp32-level mode splits operands into fp16 pairs: an activation beyond the fp16 range must not pass
+    silently - the fused kernel raises a device flag that check_numeric_range() reads and clears"""
+    enc = _encoder_with((61, 62, 63))
+    ev = dev(synth.make_windows(2, 2048, seed=77))
+    s1 = torch.from_numpy(synth.make_start_indices(2, 2048, 1))
+    s2 = torch.from_numpy(synth.make_start_indices(2, 512, 2))
+    from ev2hands_b200 import pointnet2_utils as pu
+    if pu._fused_mode(_capi.TC_TF32X3) != _capi.TC_F16X3:
+        pytest.skip("the fp16 split is not the selected fp32-level arithmetic (EV2H_SPLIT)")
+    e2h.check_numeric_range(DEV)                               # clear
+    with torch.no_grad():
+        ok_out = enc(ev, fps_starts=(s1, s2))
+    assert torch.isfinite(ok_out).all() and e2h.check_numeric_range(DEV)
+    big = ev.clone()
+    big[:, 3:, :] *= 3.0e6                                     # event counts far outside any real window: layer-1 outputs ~1e6
+    with torch.no_grad():
+        enc(big, fps_starts=(s1, s2))
+    assert not e2h.check_numeric_range(DEV)                    # flagged ...
+    assert e2h.check_numeric_range(DEV)                        # ... and cleared by the read
