@@ -63,6 +63,10 @@ _SIGNATURES = {
     "ev2h_three_interp_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp],
     "ev2h_window_aggregate_f64": [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "ev2h_window_sample_f32": [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "ev2h_fps_range_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "ev2h_ball_query_compact_range_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          ctypes.POINTER(c_f), ctypes.POINTER(ctypes.c_int32), c_vp, c_vp, c_vp,
+                                          ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp],
     "ev2h_conv1d_tc": [c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp],
     "ev2h_class_attention_f32": [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp],
     "ev2h_group_max_f32": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
@@ -208,6 +212,45 @@ def fps(xyz: torch.Tensor, strides, start: torch.Tensor, B: int, N: int, S: int,
             _check(lib().ev2h_fps_f32(_p(xyz), strides[0], strides[1], strides[2], _p(start), B, N, S,
                                   _p(idx), _p(rows), _p(cf), _stream(xyz)), "ev2h_fps_f32")
     return idx, rows, cf
+
+
+def device_starts(start: torch.Tensor, B: int, N: int, dev) -> torch.Tensor:
+    """FPS start indices as an int64 device tensor (range-checked when they come from the host, see fps())"""
+    if tuple(start.shape) != (B,):
+        raise RuntimeError("FPS start indices must have shape [%d], got %s" % (B, tuple(start.shape)))
+    if start.is_cuda:
+        return start.to(device=dev, dtype=torch.int64).contiguous()
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("FPS start indices are host tensors (or were drawn on the host) during CUDA-graph capture: "
+                           "pass device-resident fps_start / fps_starts tensors and refill them between replays")
+    start = start.to(dtype=torch.int64).contiguous()
+    if B > 0 and (int(start.min()) < 0 or int(start.max()) >= N):
+        raise IndexError("FPS start index out of range [0, %d)" % N)
+    return start.pin_memory().to(dev, non_blocking=True)
+
+
+def fps_range(xyz, strides, start_dev, B, N, S, s_begin, s_end, state_best, state_cur, idx, rows, cf):
+    """samples [s_begin, s_end) of a farthest point sampling into the preallocated outputs (ev2h_fps_range_f32)"""
+    with torch.cuda.device(xyz.device):
+        with _timed("ev2h_fps_f32"):
+            _check(lib().ev2h_fps_range_f32(_p(xyz), strides[0], strides[1], strides[2], _p(start_dev), B, N, S, s_begin, s_end,
+                                            _p(state_best), _p(state_cur), _p(idx), _p(rows), _p(cf), _stream(xyz)), "ev2h_fps_range_f32")
+
+
+def ball_query_compact_range(xyz, strides, centres_rows, B, N, S, s_begin, s_count, reset_rows, radii, nsamples, out, first_flag,
+                             uniq, rowmaps, blockgroups, n_rows):
+    """ball query + compacted row lists of the centres [s_begin, s_begin + s_count) into preallocated outputs"""
+    ns = len(radii)
+    r2 = (c_f * ns)(*[radius_sq_f32(r) for r in radii])
+    ks = (ctypes.c_int32 * ns)(*[int(k) for k in nsamples])
+    a_rm = (c_vp * ns)(*[t.data_ptr() for t in rowmaps])
+    a_bg = (c_vp * ns)(*[t.data_ptr() for t in blockgroups])
+    with torch.cuda.device(xyz.device):
+        with _timed("ev2h_ball_query_f32"):
+            _check(lib().ev2h_ball_query_compact_range_f32(_p(xyz), strides[0], strides[1], strides[2], _p(centres_rows), B, N, S,
+                                                           s_begin, s_count, 1 if reset_rows else 0, ns, r2, ks, _p(out), _p(first_flag),
+                                                           _p(uniq), a_rm, a_bg, _p(n_rows), _stream(xyz)),
+                   "ev2h_ball_query_compact_range_f32")
 
 
 def radius_sq_f32(radius: float) -> float:

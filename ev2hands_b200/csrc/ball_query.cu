@@ -56,7 +56,7 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
                   const float *__restrict__ centres, int N, int S, BallParams prm,
                   int32_t *__restrict__ out, int32_t *__restrict__ cnt_out,
                   const uint8_t *__restrict__ first_flag, int32_t *__restrict__ uniq_out, int32_t *__restrict__ ucnt_out,
-                  BallCompact comp) {
+                  BallCompact comp, int s_base, int s_end) {
     // Optional second list (first_flag != nullptr): the same first-K hits without exact duplicates of an earlier
     // point (first_flag[b,n] = 0), in index order, for the row compaction; ucnt_out = its length.
     // The flag travels in the sign bit of the staged |p|^2 (a sum of squares is never negative), read back with fabsf.
@@ -71,8 +71,10 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
     __shared__ int first_s[kBqSegs][NS][kBqCentres];    // first hit of this tile per (range, radius, centre), N if none
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    const int s = blockIdx.x * kBqCentres + lane;
-    const bool live = s < S;
+    // this launch covers the centres [s_base, s_end) of every window (the whole layer, or a range of it while the
+    // sampling of the later centres is still running, see ev2h_ball_query_compact_range_f32)
+    const int s = s_base + blockIdx.x * kBqCentres + lane;
+    const bool live = s < s_end;
     const float *base = xyz + (int64_t)b * sb;
 
     float qx = 0.f, qy = 0.f, qz = 0.f;
@@ -238,8 +240,8 @@ ball_query_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t
         __syncthreads();
         const int32_t *lists = dedup ? uniq_out : out;
         for (int cidx = seg; cidx < kBqCentres; cidx += kBqSegs) {
-            const int sc_ = blockIdx.x * kBqCentres + cidx;
-            if (sc_ >= S) break;
+            const int sc_ = s_base + blockIdx.x * kBqCentres + cidx;
+            if (sc_ >= s_end) break;
             const int64_t g = (int64_t)b * S + sc_;
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
@@ -322,7 +324,7 @@ static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c,
                            const float *radius_sq_host, const int32_t *nsample_host,
                            int32_t *out_idx, int32_t *out_cnt, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
                            int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
-                           ev2h_stream_t stream);
+                           ev2h_stream_t stream, int s_begin = 0, int s_count = -1, int reset_rows = 1);
 
 extern "C" int ev2h_ball_query_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                                    const float *centres_rows, int B, int N, int S, int n_scales,
@@ -365,14 +367,32 @@ extern "C" int ev2h_ball_query_compact_f32(const float *xyz, int64_t stride_b, i
                            out_idx, nullptr, first_flag, uniq_scratch, nullptr, rowmap_host, blockgroup_host, n_rows_dev, stream);
 }
 
+extern "C" int ev2h_ball_query_compact_range_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                                 const float *centres_rows, int B, int N, int S, int s_begin, int s_count, int reset_rows,
+                                                 int n_scales, const float *radius_sq_host, const int32_t *nsample_host,
+                                                 int32_t *out_idx, const uint8_t *first_flag, int32_t *uniq_scratch,
+                                                 int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
+                                                 ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(rowmap_host && blockgroup_host && n_rows_dev, "ev2h_ball_query_compact_range_f32: null argument");
+    EV2H_REQUIRE((first_flag == nullptr) == (uniq_scratch == nullptr), "ev2h_ball_query_compact_range_f32: first_flag and uniq_scratch go together");
+    EV2H_REQUIRE((int64_t)B * S * 128 < 2147483647LL, "ev2h_ball_query_compact_range_f32: too many groups for 32-bit row offsets");
+    return ball_query_impl(xyz, stride_b, stride_c, stride_n, centres_rows, B, N, S, n_scales, radius_sq_host, nsample_host,
+                           out_idx, nullptr, first_flag, uniq_scratch, nullptr, rowmap_host, blockgroup_host, n_rows_dev, stream,
+                           s_begin, s_count, reset_rows);
+}
+
 static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                            const float *centres_rows, int B, int N, int S, int n_scales,
                            const float *radius_sq_host, const int32_t *nsample_host,
                            int32_t *out_idx, int32_t *out_cnt, const uint8_t *first_flag, int32_t *out_uniq, int32_t *out_ucnt,
                            int32_t *const *rowmap_host, int32_t *const *blockgroup_host, int32_t *n_rows_dev,
-                           ev2h_stream_t stream) {
+                           ev2h_stream_t stream, int s_begin, int s_count, int reset_rows) {
     using namespace ev2h;
     EV2H_REQUIRE(xyz && centres_rows && out_idx && radius_sq_host && nsample_host, "ev2h_ball_query_f32: null argument");
+    if (s_count < 0) s_count = S - s_begin;
+    EV2H_REQUIRE(s_begin >= 0 && s_count > 0 && s_begin + s_count <= S && s_begin % kBqCentres == 0,
+                 "ev2h_ball_query_f32: centre range [%d, %d) of %d (the start must be a multiple of %d)", s_begin, s_begin + s_count, S, kBqCentres);
     EV2H_REQUIRE(B > 0 && N > 0 && S > 0, "ev2h_ball_query_f32: B, N, S must be positive");
     EV2H_REQUIRE(B <= 65535, "ev2h_ball_query_f32: B=%d exceeds 65535 windows per call", B);
     if (n_scales < 1 || n_scales > kMaxScales)
@@ -403,17 +423,20 @@ static int ball_query_impl(const float *xyz, int64_t stride_b, int64_t stride_c,
             comp.blockgroup[i] = blockgroup_host[i];
         }
         comp.n_rows = n_rows_dev;
-        cudaError_t e = cudaMemsetAsync(n_rows_dev, 0, sizeof(int32_t) * n_scales, as_stream(stream));
-        if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_ball_query_compact_f32: memset: %s", cudaGetErrorString(e));
+        if (reset_rows) {
+            cudaError_t e = cudaMemsetAsync(n_rows_dev, 0, sizeof(int32_t) * n_scales, as_stream(stream));
+            if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_ball_query_compact_f32: memset: %s", cudaGetErrorString(e));
+        }
     }
-    dim3 grid((S + kBqCentres - 1) / kBqCentres, B);
+    dim3 grid((s_count + kBqCentres - 1) / kBqCentres, B);
+    const int s_end = s_begin + s_count;
     constexpr int kBqThreads = kBqCentres * kBqSegs;
     cudaStream_t st = as_stream(stream);
     switch (n_scales) {
-        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
-        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
-        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
-        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp); break;
+        case 1: ball_query_kernel<1><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp, s_begin, s_end); break;
+        case 2: ball_query_kernel<2><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp, s_begin, s_end); break;
+        case 3: ball_query_kernel<3><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp, s_begin, s_end); break;
+        default: ball_query_kernel<4><<<grid, kBqThreads, 0, st>>>(xyz, stride_b, stride_c, stride_n, centres_rows, N, S, prm, out_idx, out_cnt, first_flag, out_uniq, out_ucnt, comp, s_begin, s_end); break;
     }
     return check_launch("ev2h_ball_query_f32");
 }

@@ -55,12 +55,16 @@ template <int T, int P, int RP>      // RP = points per thread whose coordinates
 __global__ void __launch_bounds__(T, 1)
 fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
            const int64_t *__restrict__ start, int N, int S,
-           int32_t *__restrict__ out_idx, float *__restrict__ out_rows, float *__restrict__ out_cf) {
+           int32_t *__restrict__ out_idx, float *__restrict__ out_rows, float *__restrict__ out_cf,
+           int s_begin, int s_end, float *__restrict__ state_best, int32_t *__restrict__ state_cur) {
+    // Samples s_begin .. s_end - 1 of S.  A sampling can be cut into several launches (ev2h_fps_range_f32): the running
+    // minimum distances and the next centre travel through state_best [B, N] / state_cur [B], so that the ball query of
+    // the centres already chosen runs beside the rest of the sampling.  One launch: s_begin = 0, s_end = S, no state.
     constexpr int NP = T * P;
     constexpr int W = T / 32;
     extern __shared__ float fps_smem[];
     float *sx = fps_smem, *sy = fps_smem + NP, *sz = fps_smem + 2 * NP;
-    __shared__ unsigned long long slot[2][32];
+    __shared__ __align__(16) unsigned long long slot[2][32];
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *base = xyz + (int64_t)b * sb;
@@ -94,9 +98,18 @@ fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
     // range-checks host tensors and raises like the reference's indexing would, pointnet2_utils.py:77)
     const int64_t st0 = start[b];
     int cur = st0 < 0 ? 0 : (st0 >= N ? N - 1 : (int)st0);
+    constexpr bool kResume = T <= 512;       // the 1024-thread instances (N > 4096, 64 registers) are never cut into ranges
+    if (kResume && s_begin > 0) {            // resume: minima and next centre of the previous launch
+        cur = state_cur[b];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int i = tid + j * T;
+            if (i < N) best[j] = state_best[(int64_t)b * N + i];
+        }
+    }
     __syncthreads();
 
-    for (int s = 0; s < S; ++s) {
+    for (int s = s_begin; s < s_end; ++s) {
         const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
         if (tid == 0) {
             if (out_idx) out_idx[(int64_t)b * S + s] = cur;
@@ -142,6 +155,14 @@ fps_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
             wi = __reduce_min_sync(kFull, em == m ? ei : 0xffffffffu);
         }
         cur = (int)wi;
+    }
+    if (kResume && s_end < S && state_best != nullptr) {        // more launches follow
+        if (tid == 0) state_cur[b] = cur;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int i = tid + j * T;
+            if (i < N) state_best[(int64_t)b * N + i] = best[j];
+        }
     }
 }
 
@@ -278,18 +299,44 @@ static int launch_fps_cluster(const float *xyz, int64_t sb, int64_t sc, int64_t 
 
 template <int T, int P, int R>
 static int launch_fps(const float *xyz, int64_t sb, int64_t sc, int64_t sn, const int64_t *start,
-                      int B, int N, int S, int32_t *oi, float *orows, float *ocf, cudaStream_t st) {
+                      int B, int N, int S, int32_t *oi, float *orows, float *ocf, cudaStream_t st,
+                      int s_begin = 0, int s_end = -1, float *state_best = nullptr, int32_t *state_cur = nullptr) {
+    if (s_end < 0) s_end = S;
     const size_t smem = (size_t)3 * T * P * sizeof(float);
     auto k = fps_kernel<T, P, R>;
     if (smem + 1024 > 48 * 1024) {   // static slots count against the 48 KB default limit
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "fps: smem attribute: %s", cudaGetErrorString(e));
     }
-    k<<<B, T, smem, st>>>(xyz, sb, sc, sn, start, N, S, oi, orows, ocf);
+    k<<<B, T, smem, st>>>(xyz, sb, sc, sn, start, N, S, oi, orows, ocf, s_begin, s_end, state_best, state_cur);
     return check_launch("ev2h_fps_f32");
 }
 
 }  // namespace ev2h
+
+/* A sampling in several launches: samples [s_begin, s_end) of S; state_best [B, N] fp32 and state_cur [B] int32 carry the
+ * running minimum distances and the next centre from one launch to the next (written when s_end < S, read when
+ * s_begin > 0).  Same results, bit for bit, as one ev2h_fps_f32 call.  N <= 4096 (the register-resident kernels). */
+extern "C" int ev2h_fps_range_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                  const int64_t *start_idx, int B, int N, int S, int s_begin, int s_end,
+                                  float *state_best, int32_t *state_cur, int32_t *out_idx,
+                                  float *out_centres_rows, float *out_centres_cf, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(xyz && start_idx && state_best && state_cur, "ev2h_fps_range_f32: null argument");
+    EV2H_REQUIRE(B > 0 && N > 0 && S > 0 && 0 <= s_begin && s_begin < s_end && s_end <= S, "ev2h_fps_range_f32: bad range [%d, %d) of %d", s_begin, s_end, S);
+    if (N > 4096) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_fps_range_f32: N=%d (supported: up to 4096 points per window)", N);
+    cudaStream_t st = as_stream(stream);
+#define EV2H_FPSR(T, P, R) \
+    return launch_fps<T, P, R>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st, \
+                               s_begin, s_end, state_best, state_cur)
+    if (N <= 128) EV2H_FPSR(32, 4, 4);
+    if (N <= 256) EV2H_FPSR(64, 4, 4);
+    if (N <= 512) EV2H_FPSR(128, 4, 4);
+    if (N <= 1024) EV2H_FPSR(256, 4, 4);
+    if (N <= 2048) EV2H_FPSR(256, 8, 8);
+    EV2H_FPSR(512, 8, 8);
+#undef EV2H_FPSR
+}
 
 extern "C" int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
                             const int64_t *start_idx, int B, int N, int S, int32_t *out_idx,
@@ -305,7 +352,14 @@ extern "C" int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c
     if (N <= 256) EV2H_FPS(64, 4, 4);
     if (N <= 512) EV2H_FPS(128, 4, 4);
     if (N <= 1024) EV2H_FPS(256, 4, 4);
-    if (N <= 2048) EV2H_FPS(256, 8, 8);      // 128 / 512 / 1024 threads per window measured 0.173 / 0.197 / 0.235 ms vs 0.179 ms (B = 64)
+    if (N <= 2048) {
+        static const int t2048 = [] { const char *e = getenv("EV2H_FPS_THREADS"); return e ? atoi(e) : 256; }();    // experiment knob
+        if (t2048 == 128) EV2H_FPS(128, 16, 16);
+        if (t2048 == 512) EV2H_FPS(512, 4, 4);
+        EV2H_FPS(256, 8, 8);                 // round 1: 128 / 512 / 1024 threads per window measured 0.173 / 0.197 / 0.235 ms vs 0.179 ms (B = 64);
+                                             // round 2 (packed math): 128 threads 0.163 vs 0.149 ms; every thread scanning the 8 warp keys itself
+                                             // instead of two more warp reductions: 0.170 ms
+    }
     if (N <= 4096) EV2H_FPS(512, 8, 8);
     // Longer windows.  A cluster of 2 / 4 CTAs per window keeps everything in registers and halves the time of a
     // dependent iteration (0.8 us instead of 1.5 us at N = 16384), but holds a quarter of the windows per SM: it wins
@@ -321,6 +375,6 @@ extern "C" int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c
         return launch_fps_cluster<512, 8, 4>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st);
     }
     if (N <= 8192) EV2H_FPS(1024, 8, 8);
-    EV2H_FPS(1024, 16, 8);                   // 8 of a thread's 16 points in registers (64 registers per thread at 1024 threads), the rest re-read from shared memory
+    EV2H_FPS(1024, 16, 6);                   // 6 of a thread's 16 points in registers (64 registers per thread at 1024 threads), the rest re-read from shared memory
 #undef EV2H_FPS
 }

@@ -80,7 +80,9 @@ class SetAbstractionEncoder(nn.Module):
         if s2 is None:
             s2 = torch.randint(0, self.sa1.npoint, (B,), dtype=torch.long)
         with torch.no_grad():
-            g1 = self.sa1._fps(l0_xyz, s1)
+            # sa1's front end: sampling in ranges with the ball query of each finished range on a side stream, when it applies
+            piped = self.sa1._pipelined_ok(l0_xyz, events.shape[1])
+            g1 = self.sa1._fps_ball_pipelined(l0_xyz, events, events.shape[1], s1) if piped else self.sa1._fps(l0_xyz, s1)
             l1_xyz = g1["new_xyz"]
             d1 = sum(convs[-1].out_channels for convs in self.sa1.conv_blocks)
             if _GEOM_STREAM:
@@ -90,11 +92,13 @@ class SetAbstractionEncoder(nn.Module):
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     g2 = self.sa2._ball(self.sa2._fps(l1_xyz, s2), l1_xyz, None, d1, fused=True)
-                self.sa1._ball(g1, l0_xyz, events, events.shape[1], fused=True)
+                if not piped:
+                    self.sa1._ball(g1, l0_xyz, events, events.shape[1], fused=True)
                 _, r1 = self.sa1.forward_rows(l0_xyz, events, geom=g1)
                 main.wait_stream(side)
             else:
-                self.sa1._ball(g1, l0_xyz, events, events.shape[1], fused=True)
+                if not piped:
+                    self.sa1._ball(g1, l0_xyz, events, events.shape[1], fused=True)
                 _, r1 = self.sa1.forward_rows(l0_xyz, events, geom=g1)
                 g2 = self.sa2._ball(self.sa2._fps(l1_xyz, s2), l1_xyz, None, d1, fused=True)
             l2_xyz, r2 = self.sa2.forward_rows(l1_xyz, r1, geom=g2)

@@ -76,6 +76,15 @@ def _scale_stream(device, i):
     return st
 
 
+# Front-end pipelining: farthest point sampling is S strictly sequential iterations on B CTAs, and the ball query of a
+# centre needs none of the later centres.  The sampling is cut into EV2H_FPS_SPLITS ranges (resumable kernel) and the
+# ball query of each range runs on a second stream beside the sampling of the next; the point records and duplicate
+# flags, which need no centre at all, run beside the first range.  0 / 1 = one sampling launch, then the ball query.
+# Bit-identical (tests), but SLOWER on B200 at B = 64: 1.705 ms per step with 4 ranges, 1.693 with 2, 1.788 with 8,
+# against 1.633 without - the ball query's CTAs share SMs with the sampling's, whose dependent iterations are the critical
+# path, and slow them by more than the overlap hides.  Off by default.
+_FPS_SPLITS = int(os.environ.get("EV2H_FPS_SPLITS", "0"))
+
 # Evaluate layer 1 per point (instead of per gathered row) also for narrow inputs; experiment switch.
 _PER_POINT_ALWAYS = os.environ.get("EV2H_PER_POINT", "0") == "1"
 
@@ -443,6 +452,58 @@ class PointNetSetAbstractionMsg(nn.Module):
         fps_idx, centres_rows, new_xyz = _capi.fps(xyz, strides, fps_start, B, N, self.npoint)
         return {"strides": strides, "fps_idx": fps_idx, "centres_rows": centres_rows, "new_xyz": new_xyz}
 
+    def _pipelined_ok(self, xyz, D):
+        """can the FPS / ball-query front end of this layer be pipelined (see _FPS_SPLITS)?"""
+        B, _, N = xyz.shape
+        if _FPS_SPLITS < 2 or not (_FUSED_ENABLED and _COMPACT and _mlp_precision in ("tf32x3", "bf16")) or _capi.LOG.timing:
+            return False
+        if N > 4096 or self.npoint % (32 * _FPS_SPLITS) != 0 or not all(k % 8 == 0 for k in self.nsample_list):
+            return False
+        # only while the sampling leaves SMs idle (one CTA per window): with more windows than SMs there is nothing to overlap with
+        return B <= torch.cuda.get_device_properties(xyz.device).multi_processor_count
+
+    def _fps_ball_pipelined(self, xyz, points, D, fps_start):
+        """FPS in ranges on the current stream, the ball query (+ compacted row lists) of each finished range on a side
+        stream -> the same geometry record _ball(_fps(...)) gives (bit-identical indices; the ORDER of the groups in the
+        compacted row lists differs, as it already does from run to run: rows are reserved with atomics)."""
+        B, _, N = xyz.shape
+        S = self.npoint
+        dev = xyz.device
+        if fps_start is None:
+            fps_start = torch.randint(0, N, (B,), dtype=torch.long)      # same draw, same (CPU) generator, as pointnet2_utils.py:75
+        strides = _capi.cf_strides(xyz)
+        start_dev = _capi.device_starts(fps_start, B, N, dev)
+        ns = len(self.nsample_list)
+        k_total = int(sum(self.nsample_list))
+        fps_idx = torch.empty((B, S), dtype=torch.int32, device=dev)
+        centres_rows = torch.empty((B, S, 3), dtype=torch.float32, device=dev)
+        new_xyz = torch.empty((B, 3, S), dtype=torch.float32, device=dev)
+        state_best = torch.empty((B, N), dtype=torch.float32, device=dev)
+        state_cur = torch.empty((B,), dtype=torch.int32, device=dev)
+        ball = torch.empty((B, S, k_total), dtype=torch.int32, device=dev)
+        dedup = _DEDUP and D + 3 <= 8 and N <= 4096
+        uniq = torch.empty_like(ball) if dedup else None
+        rowmaps = [torch.empty((B * S * int(k),), dtype=torch.int32, device=dev) for k in self.nsample_list]
+        blockgroups = [torch.empty((B * S * int(k) // 8,), dtype=torch.int32, device=dev) for k in self.nsample_list]
+        n_rows = torch.empty((ns,), dtype=torch.int32, device=dev)
+        main, side = torch.cuda.current_stream(dev), _scale_stream(dev, 9)
+        side.wait_stream(main)
+        pts8 = first = None
+        with torch.cuda.stream(side):
+            if dedup:
+                pts8 = self._pts8(xyz, points, strides)
+                first = _capi.first_occurrence(pts8)
+        seg = S // _FPS_SPLITS
+        for i in range(_FPS_SPLITS):
+            _capi.fps_range(xyz, strides, start_dev, B, N, S, i * seg, (i + 1) * seg, state_best, state_cur, fps_idx, centres_rows, new_xyz)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _capi.ball_query_compact_range(xyz, strides, centres_rows, B, N, S, i * seg, seg, i == 0, self.radius_list,
+                                               self.nsample_list, ball, first, uniq, rowmaps, blockgroups, n_rows)
+        main.wait_stream(side)
+        return {"strides": strides, "fps_idx": fps_idx, "centres_rows": centres_rows, "new_xyz": new_xyz, "pts8": pts8,
+                "compact": (rowmaps, blockgroups, n_rows), "ball": ball}
+
     def _ball(self, geom, xyz, points, D, fused):
         """Ball query of every scale (plus the compacted row lists of the fused path) on the current stream;
         ``points`` is only needed for narrow inputs (the 32-byte gather records), ``D`` = feature channels."""
@@ -488,7 +549,10 @@ class PointNetSetAbstractionMsg(nn.Module):
                 # wide inputs are consumed as rows; narrow ones (gather records) want the channel-first tensor
                 points = None if (D + 3 > 8 or _PER_POINT_ALWAYS) else rows_in.cf()
             if geom is None:
-                geom = self._ball(self._fps(xyz, fps_start), xyz, points, D, fused=True)
+                if self._pipelined_ok(xyz, D):
+                    geom = self._fps_ball_pipelined(xyz, points, D, fps_start)
+                else:
+                    geom = self._ball(self._fps(xyz, fps_start), xyz, points, D, fused=True)
             self.last_fps_idx, self.last_ball_idx = geom["fps_idx"], geom["ball"]        # exposed for parity tests
             return geom["new_xyz"], self._forward_fused(xyz, points, rows_in, D, geom)
 

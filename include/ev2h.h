@@ -245,6 +245,26 @@ EV2H_API int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cou
 EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
                                  const float *bias, int Cout, int pool_rows, float *y, int ld_y,
                                  int y_col_off, int mode, ev2h_stream_t stream);
+/* ---- sampling and ball query in ranges (front-end pipelining) ---------------------------------------
+ * The S iterations of farthest_point_sample are strictly sequential (pointnet2_utils.py:76-83) and only B CTAs wide,
+ * but the ball query of centre s needs nothing of the centres after it.  ev2h_fps_range_f32 runs samples
+ * [s_begin, s_end) of S and carries the running minimum distances / the next centre to the following call through
+ * state_best [B, N] fp32 / state_cur [B] int32 (written when s_end < S, read when s_begin > 0); the outputs are the
+ * same arrays ev2h_fps_f32 writes, bit for bit.  ev2h_ball_query_compact_range_f32 is ev2h_ball_query_compact_f32 for
+ * the centres [s_begin, s_begin + s_count) only (s_begin a multiple of 32); reset_rows = 0 keeps appending to the
+ * compacted row lists of an earlier range.  Issued on two streams, the ball query of one range runs beside the
+ * sampling of the next.  N <= 4096. */
+EV2H_API int ev2h_fps_range_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                const int64_t *start_idx, int B, int N, int S, int s_begin, int s_end,
+                                float *state_best, int32_t *state_cur, int32_t *out_idx,
+                                float *out_centres_rows, float *out_centres_cf, ev2h_stream_t stream);
+EV2H_API int ev2h_ball_query_compact_range_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                               const float *centres_rows, int B, int N, int S, int s_begin, int s_count,
+                                               int reset_rows, int n_scales, const float *radius_sq_host,
+                                               const int32_t *nsample_host, int32_t *out_idx, const uint8_t *first_flag,
+                                               int32_t *uniq_scratch, int32_t *const *rowmap_host,
+                                               int32_t *const *blockgroup_host, int32_t *n_rows_dev, ev2h_stream_t stream);
+
 /* ---- Conv1d over rows on the tensor cores ---------------------------------
  * Replaces nn.Conv1d(Cin, Cout, kernel_size = taps, stride 1, padding = taps / 2) [+ ReLU] [+ BatchNorm1d (eval)
  * AFTER the ReLU] of the segmentation classifier and the per-hand query convolutions (reference TEHNet.py:135-166,

@@ -539,3 +539,38 @@ def test_fp16_split_overflow_raises_the_range_flag():
         enc(big, fps_starts=(s1, s2))
     assert not e2h.check_numeric_range(DEV)                    # flagged ...
     assert e2h.check_numeric_range(DEV)                        # ... and cleared by the read
+
+
+# ------------------------------------------------------------------ pipelined front end ------------------------
+def test_pipelined_sampling_and_ball_query_are_bit_identical(monkeypatch):
+    """the sampling cut into ranges (resumable kernel) with the ball query of each finished range on a side stream
+    must give exactly the indices, centres and features of one sampling launch followed by one ball query"""
+    from ev2hands_b200 import pointnet2_utils as pu
+    enc = _encoder_with((71, 72, 73))
+    ev = dev(synth.make_windows(5, 2048, seed=99))
+    s1 = torch.from_numpy(synth.make_start_indices(5, 2048, 3))
+    s2 = torch.from_numpy(synth.make_start_indices(5, 512, 4))
+    outs = {}
+    for splits in (0, 2, 4):
+        monkeypatch.setattr(pu, "_FPS_SPLITS", splits)
+        with torch.no_grad():
+            out, lv = enc(ev, fps_starts=(s1, s2), return_levels=True)
+        torch.cuda.synchronize()
+        outs[splits] = (out.clone(), enc.sa1.last_fps_idx.clone(), enc.sa1.last_ball_idx.clone(), lv["l1_xyz"].clone(), lv["l1_points"].clone())
+    for splits in (2, 4):
+        for a, b in zip(outs[0], outs[splits]):
+            assert torch.equal(a, b), splits
+    # the C-ABI range entry alone, odd split points, against the C oracle
+    xyz = np.ascontiguousarray(synth.make_windows(3, 1000, seed=5)[:, :3].transpose(0, 2, 1))
+    start = synth.make_start_indices(3, 1000, 7)
+    want = c_oracle.fps(xyz, 100, start)
+    xd = dev(xyz)
+    idx = torch.empty((3, 100), dtype=torch.int32, device=DEV)
+    rows = torch.empty((3, 100, 3), dtype=torch.float32, device=DEV)
+    best = torch.empty((3, 1000), dtype=torch.float32, device=DEV)
+    cur = torch.empty((3,), dtype=torch.int32, device=DEV)
+    sd = torch.from_numpy(start).to(DEV)
+    for lo, hi in ((0, 1), (1, 37), (37, 99), (99, 100)):
+        _capi.fps_range(xd, _capi.rows_strides(xd), sd, 3, 1000, 100, lo, hi, best, cur, idx, rows, None)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert torch.equal(rows, torch.gather(xd, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)))
