@@ -21,6 +21,7 @@ c_int, c_i64, c_f, c_d, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, cty
 # name -> argtypes (restype is always int except where noted); mirrors include/ev2h.h
 _SIGNATURES = {
     "ev2h_fps_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "ev2h_fps_variant_f32": [c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "ev2h_ball_query_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int,
                             ctypes.POINTER(c_f), ctypes.POINTER(ctypes.c_int32), c_vp, c_vp],
     "ev2h_square_distance_f32": [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp],
@@ -183,8 +184,9 @@ def rows_strides(xyz_rows: torch.Tensor):
 
 
 def fps(xyz: torch.Tensor, strides, start: torch.Tensor, B: int, N: int, S: int,
-        want_rows=True, want_cf=True):
-    """-> (idx int32 [B,S], centres_rows [B,S,3] | None, centres_cf [B,3,S] | None)"""
+        want_rows=True, want_cf=True, variant: int = 0):
+    """-> (idx int32 [B,S], centres_rows [B,S,3] | None, centres_cf [B,3,S] | None); variant: kernel for N > 4096
+    (ev2h_fps_variant_f32: 1 exhaustive, 2 cluster, 3 pruned; 0 = the library's choice)"""
     _need_cuda_f32(xyz, "xyz")
     dev = xyz.device
     if tuple(start.shape) != (B,):
@@ -209,8 +211,12 @@ def fps(xyz: torch.Tensor, strides, start: torch.Tensor, B: int, N: int, S: int,
     cf = torch.empty((B, 3, S), dtype=torch.float32, device=dev) if want_cf else None
     with torch.cuda.device(dev):
         with _timed("ev2h_fps_f32"):
-            _check(lib().ev2h_fps_f32(_p(xyz), strides[0], strides[1], strides[2], _p(start), B, N, S,
-                                  _p(idx), _p(rows), _p(cf), _stream(xyz)), "ev2h_fps_f32")
+            if variant:
+                _check(lib().ev2h_fps_variant_f32(int(variant), _p(xyz), strides[0], strides[1], strides[2], _p(start), B, N, S,
+                                                  _p(idx), _p(rows), _p(cf), _stream(xyz)), "ev2h_fps_variant_f32")
+            else:
+                _check(lib().ev2h_fps_f32(_p(xyz), strides[0], strides[1], strides[2], _p(start), B, N, S,
+                                          _p(idx), _p(rows), _p(cf), _stream(xyz)), "ev2h_fps_f32")
     return idx, rows, cf
 
 

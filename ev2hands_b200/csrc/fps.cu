@@ -279,6 +279,300 @@ fps_cluster_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_
     cl::cluster_sync();                      // nobody exits while a peer may still push into its shared memory
 }
 
+// ---- long windows, large batches: one CTA per window with SPATIAL PRUNING -----------------------------------
+// A new centre c can only lower the running minimum of a point p if |p - c|^2 < min[p].  The window's points are
+// therefore bucketed once (12-bit Morton cell of the normalised coordinates, counting sort in shared memory) so that 128
+// consecutive sorted positions - four points per lane of one warp - are a spatially compact BUCKET with an exact
+// bounding box.  Per iteration lane j of a warp tests bucket j of the warp: if the distance from c to the box is >= the
+// largest running minimum inside (an upper bound kept from the bucket's last update), no point of it can change and
+// the lanes' cached candidates for it stand.  The bound is evaluated with the SAME un-fused
+// operation sequence as the point distance on per-axis gaps that are <= the point's in magnitude, and IEEE rounding
+// is monotonic, so box distance <= every computed point distance: skipping is exact and the output is bit-identical
+// to the exhaustive kernels (tests: against the C oracle and the exhaustive kernel).  At N = 16384, S = 512 an
+// iteration updates 11.5 % of the buckets on average (tools/fps_prune_stats.py) and costs 0.81 us instead of 1.3 us -
+// what remains is the dependent chain centre -> box test -> bucket update -> reductions -> barrier.  Ties are broken
+// on the ORIGINAL index (carried per point), as torch.max does.
+// Windows with a non-finite coordinate run without pruning (same arithmetic as the exhaustive kernel).
+#ifdef EV2H_FPS_STATS
+__device__ unsigned long long g_fps_stats[4];     // [0] warp iterations, [1] warp ranges entered, [2] buckets updated
+#define EV2H_FPS_COUNT(i, n) do { if (lane == 0) atomicAdd(&g_fps_stats[i], (unsigned long long)(n)); } while (0)
+#else
+#define EV2H_FPS_COUNT(i, n) do { } while (0)
+#endif
+
+template <int P>
+__global__ void __launch_bounds__(512, 1)
+fps_pruned_kernel(const float *__restrict__ xyz, int64_t sb, int64_t sc, int64_t sn,
+                  const int64_t *__restrict__ start, int N, int S,
+                  int32_t *__restrict__ out_idx, float *__restrict__ out_rows, float *__restrict__ out_cf) {
+    constexpr int T = 512, NP = T * P, W = T / 32, NB = P / 4, CELLS = 4096;
+    static_assert(P % 4 == 0 && NP <= 65536, "four points per lane and bucket; 16-bit positions");
+    extern __shared__ float fps_smem[];
+    float *sx = fps_smem, *sy = fps_smem + NP, *sz = fps_smem + 2 * NP;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(fps_smem + 3 * NP);                  // [CELLS]
+    float4 *box = reinterpret_cast<float4 *>(hist + CELLS);                             // [W * NB][2]: (min xyz, -), (max xyz, -)
+    uint16_t *tmp_idx = reinterpret_cast<uint16_t *>(sz);                               // sorted position -> original index, until sz is filled
+    __shared__ __align__(8) uint2 slot[2][W];
+    __shared__ float red[6][W];
+    __shared__ uint32_t wsum[W];
+    __shared__ int s_flags[2];                                                          // [0] all coordinates finite, [1] position of the start point
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *base = xyz + (int64_t)b * sb;
+    const int64_t st0 = start[b];
+    const int first = st0 < 0 ? 0 : (st0 >= N ? N - 1 : (int)st0);
+
+    for (int i = tid; i < CELLS; i += T) hist[i] = 0u;
+    if (tid == 0) { s_flags[0] = 1; s_flags[1] = 0; }
+    // ---- pass 0: bounding box of the window --------------------------------------------------------------------
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool finite = true;
+#pragma unroll 4
+    for (int j = 0; j < P; ++j) {
+        const int i = tid + j * T;
+        if (i < N) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = base[c * sc + (int64_t)i * sn];
+                mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
+                finite = finite && (fabsf(v) <= 3.402823466e38f);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(kFull, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(kFull, mx[c], o));
+        }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { red[c][warp] = mn[c]; red[3 + c][warp] = mx[c]; }
+    }
+    __syncthreads();
+    if (!finite) s_flags[0] = 0;
+    float lo[3], scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float a = red[c][0], z = red[3 + c][0];
+#pragma unroll
+        for (int w = 1; w < W; ++w) { a = fminf(a, red[c][w]); z = fmaxf(z, red[3 + c][w]); }
+        lo[c] = a;
+        scale[c] = z > a ? 16.f / (z - a) : 0.f;
+    }
+    // ---- pass 1: Morton cell of every point, histogram ---------------------------------------------------------
+    uint32_t key2[P / 2];                     // two 16-bit cell keys, later two 16-bit sorted positions
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int i = tid + j * T;
+        uint32_t key = 0u;
+        if (i < N) {
+            uint32_t q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int v = (int)((base[c * sc + (int64_t)i * sn] - lo[c]) * scale[c]);     // float -> int saturates, NaN -> 0
+                q[c] = (uint32_t)(v < 0 ? 0 : (v > 15 ? 15 : v));
+            }
+#pragma unroll
+            for (int bit = 0; bit < 4; ++bit)
+                key |= (((q[0] >> bit) & 1u) << (3 * bit)) | (((q[1] >> bit) & 1u) << (3 * bit + 1)) | (((q[2] >> bit) & 1u) << (3 * bit + 2));
+            atomicAdd(&hist[key], 1u);
+        }
+        if (j & 1) key2[j / 2] |= key << 16; else key2[j / 2] = key;
+    }
+    __syncthreads();
+    // ---- exclusive scan of the histogram: thread t owns cells 8t .. 8t + 7 ----------------------------------------
+    {
+        uint32_t c8[8], tot = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c8[k] = hist[tid * 8 + k]; tot += c8[k]; }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t off = inc - tot;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hist[tid * 8 + k] = off; off += c8[k]; }
+    }
+    __syncthreads();
+    // ---- pass 2a: sorted position of every point (any order inside a cell: results do not depend on it); the original
+    //      index of every position goes through the (still unused) sz region to the thread that will own the position ----
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int i = tid + j * T;
+        const uint32_t key = (j & 1) ? (key2[j / 2] >> 16) : (key2[j / 2] & 0xffffu);
+        uint32_t pos = (uint32_t)i;                                                    // padding keeps its slot behind the N real points
+        if (i < N) pos = atomicAdd(&hist[key], 1u);
+        tmp_idx[pos] = (uint16_t)(i < N ? i : 0xffff);
+        if (j & 1) key2[j / 2] = (key2[j / 2] & 0xffffu) | (pos << 16); else key2[j / 2] = (key2[j / 2] & 0xffff0000u) | pos;
+        if (i == first) s_flags[1] = (int)pos;
+    }
+    __syncthreads();
+    // Bucket g = 128 consecutive sorted positions.  Buckets are dealt to the warps round robin (g = j * W + warp): the
+    // buckets a new centre touches are neighbours on the Morton curve, so they land in DIFFERENT warps and are updated in
+    // parallel.  A lane's points: bucket j (0 .. NB-1) of its warp, slots k = 0..3 -> position (j * W + warp) * 128 + k * 32 + lane
+    uint32_t idp[P / 2];                      // original indices, two per register (0xffff = padding)
+    float best[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int pos = ((q >> 2) * W + warp) * 128 + (q & 3) * 32 + lane;
+        const uint32_t id = tmp_idx[pos];
+        if (q & 1) idp[q / 2] |= id << 16; else idp[q / 2] = id;
+        best[q] = id == 0xffffu ? 0.f : 1e10f;                                       // torch.ones(B, N) * 1e10, pointnet2_utils.py:74; padding can never win
+    }
+    __syncthreads();
+    // ---- pass 2b: coordinates into sorted order --------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int i = tid + j * T;
+        const uint32_t pos = (j & 1) ? (key2[j / 2] >> 16) : (key2[j / 2] & 0xffffu);
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < N) { x = base[(int64_t)i * sn]; y = base[sc + (int64_t)i * sn]; z = base[2 * sc + (int64_t)i * sn]; }
+        sx[pos] = x; sy[pos] = y; sz[pos] = z;
+    }
+    __syncthreads();
+    // ---- bounding boxes of the buckets (real points only) -------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        float a[3] = {INFINITY, INFINITY, INFINITY}, z[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int q = j * 4 + k, pos = (j * W + warp) * 128 + k * 32 + lane;
+            const uint32_t id = (q & 1) ? (idp[q / 2] >> 16) : (idp[q / 2] & 0xffffu);
+            if (id != 0xffffu) {
+                a[0] = fminf(a[0], sx[pos]); z[0] = fmaxf(z[0], sx[pos]);
+                a[1] = fminf(a[1], sy[pos]); z[1] = fmaxf(z[1], sy[pos]);
+                a[2] = fminf(a[2], sz[pos]); z[2] = fmaxf(z[2], sz[pos]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a[c] = fminf(a[c], __shfl_xor_sync(kFull, a[c], o));
+                z[c] = fmaxf(z[c], __shfl_xor_sync(kFull, z[c], o));
+            }
+        if (lane == 0) {
+            box[(warp * NB + j) * 2] = make_float4(a[0], a[1], a[2], 0.f);
+            box[(warp * NB + j) * 2 + 1] = make_float4(z[0], z[1], z[2], 0.f);
+        }
+    }
+    __syncthreads();
+    const bool prune = s_flags[0] != 0;
+    int cur = first, curpos = s_flags[1];
+    // Lane j < NB keeps bucket j's box and an UPPER BOUND of the largest running minimum inside (running minima only
+    // fall, so the value of the last update stays valid) and tests it against the new centre: one ballot gives the
+    // warp's touched buckets.  Candidates are (value bits, key) with key = original index << 16 | sorted position: the
+    // index decides ties (indices are unique, so comparing keys compares indices) and the position rides along, so
+    // "first index of the maximum, and where its coordinates are" is one max and one min reduction.
+    float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
+    if (lane < NB) { blo = box[(warp * NB + lane) * 2]; bhi = box[(warp * NB + lane) * 2 + 1]; }
+    float my_bmax = 0.f;
+    unsigned lv[NB], lk[NB];                   // per lane and bucket: the lane's best
+    auto better = [](unsigned v, unsigned k, unsigned bv, unsigned bk) { return v > bv || (v == bv && k < bk); };
+    auto point_key = [&](int q, unsigned pos) {        // q compile-time
+        return __byte_perm(idp[q / 2], pos, (q & 1) ? 0x3254 : 0x1054);
+    };
+    auto lane_best = [&](int j, unsigned p0) {           // best of the lane's four points of bucket j -> lv[j], lk[j]
+        const unsigned k0 = point_key(j * 4, p0), k1 = point_key(j * 4 + 1, p0 + 32), k2 = point_key(j * 4 + 2, p0 + 64), k3 = point_key(j * 4 + 3, p0 + 96);
+        const unsigned v0 = __float_as_uint(best[j * 4]), v1 = __float_as_uint(best[j * 4 + 1]);
+        const unsigned v2 = __float_as_uint(best[j * 4 + 2]), v3 = __float_as_uint(best[j * 4 + 3]);
+        const bool t01 = better(v1, k1, v0, k0), t23 = better(v3, k3, v2, k2);
+        const unsigned va = t01 ? v1 : v0, ka = t01 ? k1 : k0, vb = t23 ? v3 : v2, kb = t23 ? k3 : k2;
+        const bool t = better(vb, kb, va, ka);
+        lv[j] = t ? vb : va; lk[j] = t ? kb : ka;
+    };
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        lane_best(j, (unsigned)((j * W + warp) * 128 + lane));
+        const unsigned m = __reduce_max_sync(kFull, lv[j]);              // 1e10 with a real point, 0 for a bucket of padding
+        if (lane == j) my_bmax = __uint_as_float(m);
+    }
+    unsigned wmax = 0u, wkey = 0xffffffffu;
+    bool stale = true;                          // the warp's summary must be (re)built
+
+    // gap between c and [a, z] on one axis: 0 inside, else the rounded difference to the nearer face (<= |p - c| of every p inside)
+    auto gap = [](float c, float a, float z) { return fmaxf(fmaxf(__fsub_rn(a, c), __fsub_rn(c, z)), 0.f); };
+
+    for (int s = 0; s < S; ++s) {
+        const float cx = sx[curpos], cy = sy[curpos], cz = sz[curpos];
+        if (tid == 0) {
+            if (out_idx) out_idx[(int64_t)b * S + s] = cur;
+            if (out_rows) { float *o = out_rows + ((int64_t)b * S + s) * 3; o[0] = cx; o[1] = cy; o[2] = cz; }
+            if (out_cf) { float *o = out_cf + (int64_t)b * 3 * S + s; o[0] = cx; o[S] = cy; o[2 * (int64_t)S] = cz; }
+        }
+        if (s + 1 == S) break;
+        float lb = -1.f;
+        if (prune) {
+            const float gx = gap(cx, blo.x, bhi.x), gy = gap(cy, blo.y, bhi.y), gz = gap(cz, blo.z, bhi.z);
+            lb = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        }
+        const unsigned touched = __ballot_sync(kFull, lane < NB && lb < my_bmax);
+        EV2H_FPS_COUNT(0, 1);
+        if (touched != 0u || stale) {            // warp-uniform
+            EV2H_FPS_COUNT(1, 1);
+            const uint64_t cx2 = cl::pack2(cx, cx), cy2 = cl::pack2(cy, cy), cz2 = cl::pack2(cz, cz);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (touched & (1u << j)) {       // warp-uniform: some running minimum of the bucket may drop
+                    EV2H_FPS_COUNT(2, 1);
+                    const int p0 = (j * W + warp) * 128 + lane;
+#pragma unroll
+                    for (int k = 0; k < 4; k += 2) {
+                        const int q = j * 4 + k;
+                        const uint64_t px2 = cl::pack2(sx[p0 + k * 32], sx[p0 + k * 32 + 32]);
+                        const uint64_t py2 = cl::pack2(sy[p0 + k * 32], sy[p0 + k * 32 + 32]);
+                        const uint64_t pz2 = cl::pack2(sz[p0 + k * 32], sz[p0 + k * 32 + 32]);
+                        const uint64_t dx = cl::sub2(px2, cx2), dy = cl::sub2(py2, cy2), dz = cl::sub2(pz2, cz2);
+                        float d0, d1;
+                        cl::unpack2(cl::add2(cl::add2(cl::mul2(dx, dx), cl::mul2(dy, dy)), cl::mul2(dz, dz)), d0, d1);   // (dx^2 + dy^2) + dz^2, un-fused
+                        best[q] = d0 < best[q] ? d0 : best[q];                                                           // distance[mask] = dist[mask], :81-82
+                        best[q + 1] = d1 < best[q + 1] ? d1 : best[q + 1];
+                    }
+                    lane_best(j, (unsigned)p0);
+                    const unsigned m = __reduce_max_sync(kFull, lv[j]);
+                    if (lane == j) my_bmax = __uint_as_float(m);
+                }
+            }
+            // the warp's candidate: tournament over the lane's buckets, then one max and one min reduction
+            unsigned tv[NB], tk[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) { tv[j] = lv[j]; tk[j] = lk[j]; }
+#pragma unroll
+            for (int w = NB / 2; w > 0; w >>= 1)
+#pragma unroll
+                for (int j = 0; j < w; ++j) {
+                    const bool t = better(tv[j + w], tk[j + w], tv[j], tk[j]);
+                    tv[j] = t ? tv[j + w] : tv[j]; tk[j] = t ? tk[j + w] : tk[j];
+                }
+            wmax = __reduce_max_sync(kFull, tv[0]);
+            wkey = __reduce_min_sync(kFull, tv[0] == wmax ? tk[0] : 0xffffffffu);
+            stale = false;
+        }
+        if (lane == 0) slot[s & 1][warp] = make_uint2(wmax, wkey);
+        __syncthreads();
+        unsigned em = 0u, ek = 0xffffffffu;
+        if (lane < W) { const uint2 e = slot[s & 1][lane]; em = e.x; ek = e.y; }
+        const unsigned m = __reduce_max_sync(kFull, em);
+        const unsigned key = __reduce_min_sync(kFull, em == m ? ek : 0xffffffffu);
+        cur = (int)(key >> 16); curpos = (int)(key & 0xffffu);
+    }
+}
+
+template <int P>
+static int launch_fps_pruned(const float *xyz, int64_t sb, int64_t sc, int64_t sn, const int64_t *start,
+                             int B, int N, int S, int32_t *oi, float *orows, float *ocf, cudaStream_t st) {
+    const size_t smem = (size_t)3 * 512 * P * sizeof(float) + 4096 * sizeof(uint32_t) + (size_t)16 * (P / 4) * 2 * sizeof(float4);
+    auto k = fps_pruned_kernel<P>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "fps: smem attribute: %s", cudaGetErrorString(e));
+    k<<<B, 512, smem, st>>>(xyz, sb, sc, sn, start, N, S, oi, orows, ocf);
+    return check_launch("ev2h_fps_f32");
+}
+
 template <int T, int P, int CS>
 static int launch_fps_cluster(const float *xyz, int64_t sb, int64_t sc, int64_t sn, const int64_t *start,
                               int B, int N, int S, int32_t *oi, float *orows, float *ocf, cudaStream_t st) {
@@ -338,14 +632,11 @@ extern "C" int ev2h_fps_range_f32(const float *xyz, int64_t stride_b, int64_t st
 #undef EV2H_FPSR
 }
 
-extern "C" int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
-                            const int64_t *start_idx, int B, int N, int S, int32_t *out_idx,
-                            float *out_centres_rows, float *out_centres_cf, ev2h_stream_t stream) {
-    using namespace ev2h;
-    EV2H_REQUIRE(xyz && start_idx, "ev2h_fps_f32: null input");
-    EV2H_REQUIRE(B > 0 && N > 0 && S > 0, "ev2h_fps_f32: B, N, S must be positive (got %d, %d, %d)", B, N, S);
-    if (N > 16384) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_fps_f32: N=%d exceeds 16384 points per window", N);
-    cudaStream_t st = as_stream(stream);
+namespace ev2h {
+// variant: 0 = automatic, 1 = exhaustive single-CTA kernels, 2 = cluster kernel (N > 4096), 3 = pruned kernel (N > 4096)
+static int fps_dispatch(int variant, const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                        const int64_t *start_idx, int B, int N, int S, int32_t *out_idx,
+                        float *out_centres_rows, float *out_centres_cf, cudaStream_t st) {
 #define EV2H_FPS(T, P, R) \
     return launch_fps<T, P, R>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st)
     if (N <= 128) EV2H_FPS(32, 4, 4);
@@ -361,20 +652,67 @@ extern "C" int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c
                                              // instead of two more warp reductions: 0.170 ms
     }
     if (N <= 4096) EV2H_FPS(512, 8, 8);
-    // Longer windows.  A cluster of 2 / 4 CTAs per window keeps everything in registers and halves the time of a
-    // dependent iteration (0.8 us instead of 1.5 us at N = 16384), but holds a quarter of the windows per SM: it wins
-    // while the batch is latency bound (all clusters resident at once) and loses at large batches (measured at
-    // B = 256, N = 16384: 2.86 ms against 1.58 ms), where one CTA per window keeps every SM busy.
-    static const int cluster_mode = [] { const char *e = getenv("EV2H_FPS_CLUSTER"); return e ? atoi(e) : -1; }();   // 0 / 1 force, default auto
-    int sms = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int cs = N <= 8192 ? 2 : 4;
-    const bool use_cluster = cluster_mode == 1 || (cluster_mode != 0 && (int64_t)B * cs <= sms);
-    if (use_cluster) {
-        if (cs == 2) return launch_fps_cluster<512, 8, 2>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st);
+    // Longer windows: three kernels, same bits (tests/test_gpu_round2.py::test_fps_long_window_kernels_agree_with_the_oracle).
+    //  * pruned (default): one CTA per window, points bucketed spatially, buckets that the new centre cannot change are
+    //    skipped - exact (see fps_pruned_kernel).  N = 16384, S = 512: 0.48 ms up to 148 windows, 0.94 ms at B = 256.
+    //  * exhaustive single CTA: 1024 threads, part of the coordinates re-read from shared memory every iteration
+    //    (0.66 / 1.31 ms for the same shapes).
+    //  * cluster of 2 / 4 CTAs per window: everything in registers, exhaustive, the local winners exchanged through
+    //    distributed shared memory.  0.37 ms at N = 16384 while all clusters are resident at once (B * 4 <= SMs) - the
+    //    fastest there and used for it - but a quarter of the windows per SM: 0.72 ms at B = 64, 2.86 ms at B = 256.
+    static const int cluster_mode = [] { const char *e = getenv("EV2H_FPS_CLUSTER"); return e ? atoi(e) : -1; }();  // 0 never, 1 whenever resident, default: N > 8192 and resident
+    static const int prune_mode = [] { const char *e = getenv("EV2H_FPS_PRUNE"); return e ? atoi(e) : 1; }();       // 0: never prune
+    if (variant == 0) {
+        int sms = 148;
+        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        const int cs0 = N <= 8192 ? 2 : 4;
+        const bool resident = (int64_t)B * cs0 <= sms;
+        if (resident && (cluster_mode == 1 || (cluster_mode < 0 && N > 8192))) variant = 2;
+        else variant = prune_mode != 0 ? 3 : 1;
+    }
+    if (variant == 2) {
+        if (N <= 8192) return launch_fps_cluster<512, 8, 2>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st);
         return launch_fps_cluster<512, 8, 4>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st);
+    }
+    if (variant == 3) {
+        if (N <= 8192) return launch_fps_pruned<16>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st);
+        return launch_fps_pruned<32>(xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, st);
     }
     if (N <= 8192) EV2H_FPS(1024, 8, 8);
     EV2H_FPS(1024, 16, 6);                   // 6 of a thread's 16 points in registers (64 registers per thread at 1024 threads), the rest re-read from shared memory
 #undef EV2H_FPS
 }
+}  // namespace ev2h
+
+extern "C" int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                            const int64_t *start_idx, int B, int N, int S, int32_t *out_idx,
+                            float *out_centres_rows, float *out_centres_cf, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(xyz && start_idx, "ev2h_fps_f32: null input");
+    EV2H_REQUIRE(B > 0 && N > 0 && S > 0, "ev2h_fps_f32: B, N, S must be positive (got %d, %d, %d)", B, N, S);
+    if (N > 16384) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_fps_f32: N=%d exceeds 16384 points per window", N);
+    return fps_dispatch(0, xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, as_stream(stream));
+}
+
+/* ev2h_fps_f32 with the kernel for long windows (N > 4096) chosen by the caller: 1 exhaustive, 2 thread-block cluster,
+ * 3 spatially pruned; 0 = the library's choice.  All variants return the same bits; this entry exists for the tests that
+ * prove it and for measurements. */
+extern "C" int ev2h_fps_variant_f32(int variant, const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                    const int64_t *start_idx, int B, int N, int S, int32_t *out_idx,
+                                    float *out_centres_rows, float *out_centres_cf, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(xyz && start_idx, "ev2h_fps_variant_f32: null input");
+    EV2H_REQUIRE(B > 0 && N > 0 && S > 0, "ev2h_fps_variant_f32: B, N, S must be positive (got %d, %d, %d)", B, N, S);
+    EV2H_REQUIRE(variant >= 0 && variant <= 3, "ev2h_fps_variant_f32: variant %d (0 .. 3)", variant);
+    if (N > 16384) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_fps_variant_f32: N=%d exceeds 16384 points per window", N);
+    return fps_dispatch(variant, xyz, stride_b, stride_c, stride_n, start_idx, B, N, S, out_idx, out_centres_rows, out_centres_cf, as_stream(stream));
+}
+
+#ifdef EV2H_FPS_STATS
+extern "C" __attribute__((visibility("default"))) int ev2h_debug_fps_stats(unsigned long long *out4, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out4, ev2h::g_fps_stats, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(ev2h::g_fps_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -71,6 +71,15 @@ EV2H_API int ev2h_fps_f32(const float *xyz, int64_t stride_b, int64_t stride_c, 
                  const int64_t *start_idx, int B, int N, int S,
                  int32_t *out_idx, float *out_centres_rows, float *out_centres_cf,
                  ev2h_stream_t stream);
+/* ev2h_fps_f32 with the kernel for long windows (4096 < N <= 16384) chosen by the caller: 1 = exhaustive single CTA,
+ * 2 = one thread-block cluster per window (distributed shared memory), 3 = spatially pruned (points bucketed by Morton
+ * cell; a bucket whose bounding box is at least as far from the new centre as its largest running minimum is skipped -
+ * exact, because the bound uses the point distance's own rounding sequence); 0 = the library's choice (2 while N > 8192
+ * and every cluster is resident at once, else 3).  Every variant
+ * returns the same bits; the entry exists for the tests that prove it and for measurements.  N <= 4096: variant ignored. */
+EV2H_API int ev2h_fps_variant_f32(int variant, const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                  const int64_t *start_idx, int B, int N, int S, int32_t *out_idx,
+                                  float *out_centres_rows, float *out_centres_cf, ev2h_stream_t stream);
 
 /* ---- multi-radius ball query --------------------------------------------------
  * Replaces query_ball_point (pointnet2_utils.py:87-107) for every radius of a

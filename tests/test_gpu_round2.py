@@ -574,3 +574,48 @@ def test_pipelined_sampling_and_ball_query_are_bit_identical(monkeypatch):
         _capi.fps_range(xd, _capi.rows_strides(xd), sd, 3, 1000, 100, lo, hi, best, cur, idx, rows, None)
     assert np.array_equal(idx.cpu().numpy(), want)
     assert torch.equal(rows, torch.gather(xd, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)))
+
+
+# ------------------------------------------------------------------ FPS kernels for long windows -------------
+def _long_window_cases():
+    rs = np.random.RandomState(5)
+    ev = synth.make_windows(3, 16384, seed=71)                          # clustered, ~40 % exact copies: ties everywhere
+    yield "events16384", np.ascontiguousarray(ev[:, :3].transpose(0, 2, 1)), 512
+    ev = synth.make_windows(2, 9000, seed=72)                           # ragged length: padded positions in the last buckets
+    yield "events9000", np.ascontiguousarray(ev[:, :3].transpose(0, 2, 1)), 300
+    ev = synth.make_windows(2, 5000, seed=73, mode="uniform")
+    yield "uniform5000", np.ascontiguousarray(ev[:, :3].transpose(0, 2, 1)), 700
+    lattice = rs.randint(0, 12, size=(2, 12000, 3)).astype(np.float32) / 4.0   # 1728 distinct points: equal distances between
+    yield "lattice12000", lattice, 2000                                        # DIFFERENT points, and more samples than points
+    flat = np.zeros((1, 6000, 3), np.float32)
+    flat[..., 0] = rs.rand(1, 6000).astype(np.float32)                         # degenerate extent on two axes
+    yield "line6000", flat, 64
+    same = np.full((1, 4500, 3), 0.25, np.float32)                             # one point 4500 times
+    yield "same4500", same, 16
+
+
+@pytest.mark.parametrize("name,xyz,s", list(_long_window_cases()), ids=lambda v: v if isinstance(v, str) else "")
+def test_fps_long_window_kernels_agree_with_the_oracle(name, xyz, s):
+    """exhaustive, cluster and spatially pruned kernels (ev2h_fps_variant_f32) all return the C oracle's indices"""
+    b, n = xyz.shape[:2]
+    start = synth.make_start_indices(b, n, seed=n)
+    want = c_oracle.fps(xyz, s, start)
+    x = dev(xyz)
+    for variant in (1, 2, 3, 0):
+        idx, rows, cf = _capi.fps(x, _capi.rows_strides(x), torch.from_numpy(start), b, n, s, variant=variant)
+        got = idx.cpu().numpy()
+        assert np.array_equal(got, want), "variant %d differs from the oracle at %s" % (variant, np.argwhere(got != want)[:3])
+        picked = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3))
+        assert torch.equal(rows, picked) and torch.equal(cf, picked.permute(0, 2, 1))
+
+
+def test_fps_pruned_kernel_with_non_finite_coordinates_matches_the_exhaustive_kernel():
+    ev = synth.make_windows(2, 8000, seed=74)
+    xyz = np.ascontiguousarray(ev[:, :3].transpose(0, 2, 1))
+    xyz[0, 17, 1] = np.inf
+    xyz[1, 4000, 0] = np.nan
+    x = dev(xyz)
+    start = torch.from_numpy(synth.make_start_indices(2, 8000, seed=3))
+    a = _capi.fps(x, _capi.rows_strides(x), start, 2, 8000, 128, variant=1)[0]
+    b = _capi.fps(x, _capi.rows_strides(x), start, 2, 8000, 128, variant=3)[0]
+    assert torch.equal(a, b)
