@@ -218,13 +218,20 @@ linear_tc_kernel(const TcParams p) {
                 }
             }
         };
-        int stage = 0;
-        uint32_t phase = 0;
+        // Stage ownership: the number of stages is a multiple of TC_LOADER_GROUPS (host), so stage n % stages is always
+        // filled by group n % TC_LOADER_GROUPS and a group waits on the "empty" barriers of its OWN stages only.  Its
+        // wait for the phase that frees chunk n then can never be more than one phase behind the barrier (the next
+        // completion needs this very group's fill).  Round 1 let every group walk all stages and wait on the other
+        // group's barriers too; an observer that reached its try_wait after the stage had been filled, consumed AND
+        // released again saw the parity flipped back and blocked for good - one CTA in ~10^5 tiles, found when the
+        // training path ran the kernel over 2 M rows (the time-bounded wait trapped instead of hanging the GPU).
         float4 v[8];
         if ((uint32_t)grp < total) issue_loads((uint32_t)grp, v);
-        for (uint32_t n = 0; n < total; ++n) {
+        for (uint32_t n = (uint32_t)grp; n < total; n += TC_LOADER_GROUPS) {
             {
-                if ((int)(n % TC_LOADER_GROUPS) == grp) {
+                const int stage = (int)(n % (uint32_t)stages);
+                const uint32_t phase = (n / (uint32_t)stages) & 1u;
+                {
                     const int64_t tile = blockIdx.x + (int64_t)(n / (uint32_t)p.n_kc) * gridDim.x;
                     const int kc = (int)(n % (uint32_t)p.n_kc);
                     const int nb = (int)(tile % p.n_blocks);
@@ -302,12 +309,7 @@ linear_tc_kernel(const TcParams p) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = vn[i];
                     }
-                } else {
-                    // walk the other group's chunks too: a parity wait is only meaningful while the
-                    // waiter is at most one phase ahead of the barrier
-                    tc::mbar_wait(empty_bar + stage, phase ^ 1);
                 }
-                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 4) {
@@ -592,6 +594,7 @@ static int linear_tc_impl(const float *x, int64_t M, int ld_x, int Cin, const vo
     const int tail_bytes = (2 * TC_MAX_STAGES + 4) * 8 + 16 + (3 * p.n_blocks * p.n_blk + 2 * 4 * p.n_blk) * 4;
     int stages = (227 * 1024 - tail_bytes - 1024) / stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    stages -= stages % TC_LOADER_GROUPS;                     // a stage always belongs to the same loader group (see the loaders)
     if (stages < 2) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_linear_relu_tc: stage of %d bytes does not fit twice", stage_bytes);
     p.stages = stages;
     p.debug = g_tc_debug;

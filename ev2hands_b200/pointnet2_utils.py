@@ -177,12 +177,12 @@ class _GroupGather(torch.autograd.Function):
     def forward(ctx, feats_rows, xyz, strides, N, centres_rows, idx, k_off, K):
         B, S, _ = centres_rows.shape
         D = 0 if feats_rows is None else feats_rows.shape[2]
-        ld = D + 3
-        out = torch.empty((B, S, K, ld), dtype=torch.float32, device=centres_rows.device)
+        ld = _pad4(D + 3)                    # 16-byte rows: the tensor-core layer kernels read them in place
+        out = (torch.empty if ld == D + 3 else torch.zeros)((B, S, K, ld), dtype=torch.float32, device=centres_rows.device)
         _capi.group_gather(xyz, strides, feats_rows, D, centres_rows, idx, k_off, B, N, S, K, out, ld)
         ctx.save_for_backward(idx)
         ctx.meta = (k_off, B, N, S, K, D)
-        return out
+        return out if ld == D + 3 else out[..., :D + 3]
 
     @staticmethod
     def backward(ctx, grad):
@@ -210,6 +210,113 @@ class _GroupMax(torch.autograd.Function):
     def backward(ctx, grad_out):
         (arg,) = ctx.saved_tensors
         return _capi.group_max_bwd(grad_out, arg, ctx.K)
+
+
+# --------------------------------------------------------------------------------------
+# training-mode shared MLP on point rows
+# --------------------------------------------------------------------------------------
+# bn(conv(x)) in training mode needs statistics over every position of the batch between two layers, so the layers
+# cannot be fused like in eval mode; but a 1x1 convolution over [B, C, K, S] is a GEMM over the B*S*K rows and
+# BatchNorm2d's statistics are per-channel means over those rows.  Keeping the grouped tensor as rows [M, C] - the
+# layout the gather kernel writes - turns conv / dgrad / wgrad into three plain GEMMs (cuBLAS) and drops the
+# [B,S,K,C] -> [B,C,K,S] copy of every scale; cuDNN's fp32 1x1 convolutions (wgrad above all) were 60 % of the step
+# (tools/train_profile.py).  EV2H_TRAIN_ROWS=0 restores the channel-first conv2d path.
+_TRAIN_ROWS = os.environ.get("EV2H_TRAIN_ROWS", "1") != "0"
+
+
+def _bn_rows(x2d, bn):
+    """nn.BatchNorm{1,2}d.forward on rows [M, C] (positions x channels): same statistics, running-stat update and
+    momentum rule as torch.nn.modules.batchnorm._BatchNorm.forward over [B, C, ...]"""
+    eaf = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        eaf = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
+    use_batch = bn.training or (bn.running_mean is None and bn.running_var is None)
+    return F.batch_norm(x2d, bn.running_mean if (not bn.training or bn.track_running_stats) else None,
+                        bn.running_var if (not bn.training or bn.track_running_stats) else None,
+                        bn.weight, bn.bias, use_batch, eaf, bn.eps)
+
+
+# Forward and input-gradient GEMMs of those layers on the tcgen05 layer kernel (ev2h_linear_tc) with fp32-level split
+# arithmetic - the forward in the inference path's mode, the input gradient with the tf32 / bf16 split, whose operands
+# keep fp32's exponent range (gradients span many orders of magnitude; fp16 parts would flush the small ones).  The
+# weight gradient dW = dY^T X contracts over the M rows and stays a cuBLAS GEMM.  OFF by default (EV2H_TRAIN_TC=1 turns
+# it on): the step gets 15 % faster (113 against 132 ms at batch 32), but the split products are good to ~2e-6 of an
+# output and the weight gradients in front of a batch-statistics BatchNorm are differences of large sums - they come out
+# within 3e-3 of the reference's autograd instead of 3e-6 with fp32 GEMMs (tests: strict bar for the default, 1e-2 for
+# this path).  Far closer than the tf32 convolutions PyTorch runs by default, but not the fp32 parity this repo promises.
+_TRAIN_TC = os.environ.get("EV2H_TRAIN_TC", "0") == "1"
+
+
+def _rows_ok(t):
+    """[M, C] fp32 rows the layer kernel can read in place: unit column stride, 16-byte aligned rows"""
+    return (t.dim() == 2 and t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0)
+
+
+def _pack_dense(w_t, mode):
+    """dense [Cin, Cout] matrix (y = x @ w_t) -> (packed tensor-core image, Cin, Cout)"""
+    cin, cout = w_t.shape
+    wt = torch.zeros(((cin + 15) // 16 * 16, (cout + 127) // 128 * 128), dtype=torch.float32, device=w_t.device)
+    wt[:cin, :cout] = w_t
+    return _capi.tc_pack(wt, cin, cout, mode)
+
+
+class _LinearRowsTC(torch.autograd.Function):
+    """y = x W^T + b over rows [M, Cin] -> [M, Cout] (a 1x1 convolution over the grouped tensor)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        M, cin = x.shape
+        cout = weight.shape[0]
+        mode = _layer_mode(_capi.TC_TF32X3)
+        packed = _pack_dense(weight.detach().t(), mode)
+        b = torch.zeros(((cout + 127) // 128 * 128,), dtype=torch.float32, device=x.device)
+        if bias is not None:
+            b[:cout] = bias.detach()
+        y = torch.empty((M, cout), dtype=torch.float32, device=x.device)
+        _capi.linear_tc_no_relu(x, M, x.stride(0), cin, packed, b, cout, y, cout, 0, mode)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        M, cin = x.shape
+        cout = weight.shape[0]
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            if _capi.tc_supported(cin, 0) and cin % 4 == 0 and cout <= 1024:
+                mode = _capi.TC_TF32X3 if _TF32X3_PURE else _capi.TC_TF32_BF16C
+                packed = _pack_dense(weight.detach(), mode)                    # dX = dY W: contraction over Cout
+                zero = torch.zeros(((cin + 127) // 128 * 128,), dtype=torch.float32, device=dy.device)
+                dx = torch.empty((M, cin), dtype=torch.float32, device=dy.device)
+                _capi.linear_tc_no_relu(dy, M, cout, cout, packed, zero, cin, dx, cin, 0, mode)
+            else:
+                dx = dy @ weight
+        if ctx.needs_input_grad[1]:
+            dw = dy.t() @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def _linear_rows(x2d, weight, bias):
+    cout, cin = weight.shape
+    if (_TRAIN_TC and _mlp_precision in ("tf32x3",) and _rows_ok(x2d) and _capi.tc_supported(cout, 0) and cout % 4 == 0
+            and cin <= 1024):
+        return _LinearRowsTC.apply(x2d, weight, bias)
+    return F.linear(x2d, weight, bias)
+
+
+def _mlp_train_rows(x2d, convs, bns):
+    """relu(bn(conv(.))) stack on rows [M, Cin] -> [M, Cout]; the convolutions have 1x1 / k = 1 kernels"""
+    for conv, bn in zip(convs, bns):
+        x2d = _linear_rows(x2d, conv.weight.view(conv.out_channels, -1), conv.bias)
+        x2d = F.relu(_bn_rows(x2d, bn))
+    return x2d
 
 
 # --------------------------------------------------------------------------------------
@@ -699,10 +806,15 @@ class PointNetSetAbstractionMsg(nn.Module):
         k_off = 0
         for i, K in enumerate(self.nsample_list):
             g = _GroupGather.apply(feats_rows, xyz.detach(), strides, N, centres_rows, ball, k_off, K)  # [B,S,K,D+3]
-            g = g.permute(0, 3, 2, 1).contiguous()                                                  # [B,D+3,K,S]
-            for conv, bn in zip(self.conv_blocks[i], self.bn_blocks[i]):
-                g = F.relu(bn(conv(g)))
-            pooled.append(_GroupMax.apply(g))
+            if _TRAIN_ROWS:
+                Bg, Sg = g.shape[:2]
+                h = _mlp_train_rows(g.flatten(0, 2), self.conv_blocks[i], self.bn_blocks[i])      # a view, also of padded rows
+                pooled.append(h.view(Bg, Sg, K, h.shape[-1]).max(dim=2)[0].permute(0, 2, 1))    # torch.max(x, 2)[0], :257
+            else:
+                g = g.permute(0, 3, 2, 1).contiguous()                                              # [B,D+3,K,S]
+                for conv, bn in zip(self.conv_blocks[i], self.bn_blocks[i]):
+                    g = F.relu(bn(conv(g)))
+                pooled.append(_GroupMax.apply(g))
             k_off += K
         return torch.cat(pooled, dim=1)
 
@@ -779,7 +891,12 @@ class PointNetSetAbstraction(nn.Module):
         return out.view(B, c_out, 1)
 
     def _group_all_autograd(self, xyz, points):
-        g = xyz.unsqueeze(-1) if points is None else torch.cat([xyz, points], dim=1).unsqueeze(-1)   # [B,C,N,1]
+        g = xyz if points is None else torch.cat([xyz, points], dim=1)                               # [B,C,N]
+        if _TRAIN_ROWS:
+            B, C, N = g.shape
+            h = _mlp_train_rows(g.permute(0, 2, 1).reshape(B * N, C), self.mlp_convs, self.mlp_bns)
+            return h.view(B, N, h.shape[-1]).max(dim=1)[0].unsqueeze(-1)                              # [B,C',1]
+        g = g.unsqueeze(-1)                                                                          # [B,C,N,1]
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             g = F.relu(bn(conv(g)))
         return _GroupMax.apply(g)
@@ -897,6 +1014,9 @@ class PointNetFeaturePropagation(nn.Module):
                               i3.unsqueeze(-1).expand(B, N, 3, f2.shape[-1]))
             up = (nb * w.unsqueeze(-1)).sum(dim=2)
         h = up if points1 is None else torch.cat([points1.transpose(1, 2), up], dim=-1)
+        if _TRAIN_ROWS:
+            h = _mlp_train_rows(h.reshape(B * N, h.shape[-1]), self.mlp_convs, self.mlp_bns)
+            return h.view(B, N, h.shape[-1]).transpose(1, 2)
         h = h.transpose(1, 2)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             h = F.relu(bn(conv(h)))

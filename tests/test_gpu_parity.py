@@ -403,7 +403,17 @@ def test_group_max_forward_backward_vs_torch():
     assert torch.equal(xa.grad, xb.grad)
 
 
-def test_train_mode_forward_backward_matches_torch_autograd():
+@pytest.fixture
+def strict_fp32():
+    """stock torch ops as an fp32 reference: cuDNN / cuBLAS may otherwise run convolutions and GEMMs in plain tf32"""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_train_mode_forward_backward_matches_torch_autograd(strict_fp32):
     torch.manual_seed(0)
     m = e2h.PointNetSetAbstractionMsg(32, [0.4, 0.8], [8, 16], 6, [[16, 24], [16, 32]]).to(DEV).train()
     B, N = 3, 256
@@ -443,8 +453,16 @@ def test_train_mode_forward_backward_matches_torch_autograd():
     out2 = torch.cat(pooled, 1)
     assert rel_err(out, out2) <= 1e-5
     (out2 * torch.linspace(0.5, 1.5, out2.numel(), device=DEV).view_as(out2)).sum().backward()
-    for n, p in ref.named_parameters():
-        assert rel_err(got[n], p.grad) <= 1e-4, n
+    ref_grads = dict((n, p.grad) for n, p in ref.named_parameters())
+    for n, g in ref_grads.items():
+        if n.startswith("conv_blocks") and n.endswith(".bias"):
+            # a bias in front of a train-mode BatchNorm cancels in (x - mean): its exact gradient is zero and what
+            # either side computes is rounding noise of its own summation order - compare it with the scale of the
+            # layer's weight gradient instead of with the other side's noise
+            scale = float(ref_grads[n[:-4] + "weight"].abs().max())
+            assert float(got[n].abs().max()) <= 1e-3 * scale and float(g.abs().max()) <= 1e-3 * scale, n
+        else:
+            assert rel_err(got[n], g) <= 1e-4, n
     assert rel_err(got_in, feats2.grad) <= 1e-4
     assert rel_err(got_rm, ref.bn_blocks[0][0].running_mean) <= 1e-5
 

@@ -317,11 +317,18 @@ def test_oracle_on_gpu_agrees_with_cpu_oracle_and_kernels(golden):
 
 
 # ------------------------------------------------------------------ training at the model's shapes -------------
-def test_train_step_at_model_shapes_matches_reference_autograd(golden):
+@pytest.mark.parametrize("tensor_core_gemms", [False, True])
+def test_train_step_at_model_shapes_matches_reference_autograd(golden, tensor_core_gemms, monkeypatch):
     """sa2 of the model (D = 320 feature channels, K = 64 / 128, S = 128) in train mode: forward with batch-statistics
     BatchNorm and backward through max-pool (arg-max route) and the grouping gather (scatter-add with heavy
     contention: every point is a neighbour of most centres) against the REFERENCE module's own autograd on CPU
-    (tests/golden/train_sa2.npz, made by make_golden.py from the unmodified reference)."""
+    (tests/golden/train_sa2.npz, made by make_golden.py from the unmodified reference).  Default path (fp32 GEMMs over
+    rows): strict bars.  Optional tensor-core GEMMs (EV2H_TRAIN_TC=1): forward at the same bar, gradients at 1e-2 -
+    the weight gradients in front of a batch-statistics BatchNorm are differences of large sums and amplify the split
+    products' 2e-6."""
+    import ev2hands_b200.pointnet2_utils as pu
+    monkeypatch.setattr(pu, "_TRAIN_TC", tensor_core_gemms)
+    gtol = 1e-2 if tensor_core_gemms else 2e-4
     g = golden("train_sa2")
     m = e2h.PointNetSetAbstractionMsg(128, [0.4, 0.8], [64, 128], 320, [[128, 128, 256], [128, 196, 256]])
     load_numpy_state(m, synth.random_state_for(synth.ENCODER_SPECS["sa2"], seed=int(g["weight_seed"])))
@@ -339,11 +346,11 @@ def test_train_step_at_model_shapes_matches_reference_autograd(golden):
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
     assert np.array_equal(new_xyz.detach().cpu().numpy(), g["new_xyz"])
     assert rel_err(out[:, ::4, ::4], g["out_every4"]) <= 2e-5
-    assert rel_err(feats.grad[:, :, ::8], g["grad_feats_every8"]) <= 2e-4
+    assert rel_err(feats.grad[:, :, ::8], g["grad_feats_every8"]) <= gtol
     grads = dict(m.named_parameters())
     for key in g:
         if key.startswith("grad.") and not (key.endswith(".bias") and ".conv_blocks." in "." + key):
-            assert rel_err(grads[key[5:]].grad, g[key]) <= 2e-4, key
+            assert rel_err(grads[key[5:]].grad, g[key]) <= gtol, key
     # a convolution bias in front of a batch-statistics BatchNorm has an exactly zero gradient (the mean is subtracted):
     # both sides hold rounding noise only, orders of magnitude below the weight gradients
     wmax = float(np.abs(g["grad.conv_blocks.1.1.weight"]).max())
@@ -619,3 +626,23 @@ def test_fps_pruned_kernel_with_non_finite_coordinates_matches_the_exhaustive_ke
     a = _capi.fps(x, _capi.rows_strides(x), start, 2, 8000, 128, variant=1)[0]
     b = _capi.fps(x, _capi.rows_strides(x), start, 2, 8000, 128, variant=3)[0]
     assert torch.equal(a, b)
+
+
+def test_tensor_core_layer_kernel_over_millions_of_rows():
+    """the training path runs ev2h_linear_tc over B*S*K ~ 2 M rows (110 tiles per CTA instead of the inference path's
+    handful): a loader-group hand-shake that could miss a barrier phase once in ~10^5 tiles showed up only there
+    (fixed: stage ownership).  Many tiles, three arithmetic modes, result checked on a sample."""
+    from ev2hands_b200 import pointnet2_utils as pu
+    torch.manual_seed(0)
+    M = 1 << 20
+    for cin, cout, mode in ((64, 96, _capi.TC_F16X3), (96, 64, _capi.TC_TF32_BF16C), (8, 32, _capi.TC_F16X3), (196, 256, _capi.TC_TF32X3)):
+        x = torch.randn(M, cin, device=DEV)
+        w = torch.randn(cin, cout, device=DEV) / cin ** 0.5
+        packed = pu._pack_dense(w, mode)
+        b = torch.zeros(((cout + 127) // 128 * 128,), device=DEV)
+        y = torch.empty(M, cout, device=DEV)
+        for _ in range(12):
+            _capi.linear_tc_no_relu(x, M, cin, cin, packed, b, cout, y, cout, 0, mode)
+        torch.cuda.synchronize()
+        ref = x[-4096:].double() @ w.double()
+        assert float((y[-4096:].double() - ref).abs().max() / ref.abs().max()) < 1e-5
