@@ -317,18 +317,18 @@ def test_oracle_on_gpu_agrees_with_cpu_oracle_and_kernels(golden):
 
 
 # ------------------------------------------------------------------ training at the model's shapes -------------
-@pytest.mark.parametrize("tensor_core_gemms", [False, True])
+@pytest.mark.parametrize("tensor_core_gemms", ["", "dgrad", "all"])
 def test_train_step_at_model_shapes_matches_reference_autograd(golden, tensor_core_gemms, monkeypatch):
     """sa2 of the model (D = 320 feature channels, K = 64 / 128, S = 128) in train mode: forward with batch-statistics
     BatchNorm and backward through max-pool (arg-max route) and the grouping gather (scatter-add with heavy
     contention: every point is a neighbour of most centres) against the REFERENCE module's own autograd on CPU
-    (tests/golden/train_sa2.npz, made by make_golden.py from the unmodified reference).  Default path (fp32 GEMMs over
-    rows): strict bars.  Optional tensor-core GEMMs (EV2H_TRAIN_TC=1): forward at the same bar, gradients at 1e-2 -
-    the weight gradients in front of a batch-statistics BatchNorm are differences of large sums and amplify the split
-    products' 2e-6."""
+    (tests/golden/train_sa2.npz, made by make_golden.py from the unmodified reference).  fp32 GEMMs over rows, and
+    the input-gradient GEMMs on the tensor cores (EV2H_TRAIN_TC=dgrad): strict bars.  Tensor-core forward as well
+    (EV2H_TRAIN_TC=1): forward at the same bar, gradients at 1e-2 - the weight gradients in front of a batch-statistics
+    BatchNorm are differences of large sums and amplify the forward's 2e-6."""
     import ev2hands_b200.pointnet2_utils as pu
     monkeypatch.setattr(pu, "_TRAIN_TC", tensor_core_gemms)
-    gtol = 1e-2 if tensor_core_gemms else 2e-4
+    gtol = 1e-2 if tensor_core_gemms == "all" else 2e-4
     g = golden("train_sa2")
     m = e2h.PointNetSetAbstractionMsg(128, [0.4, 0.8], [64, 128], 320, [[128, 128, 256], [128, 196, 256]])
     load_numpy_state(m, synth.random_state_for(synth.ENCODER_SPECS["sa2"], seed=int(g["weight_seed"])))
