@@ -646,3 +646,30 @@ def test_tensor_core_layer_kernel_over_millions_of_rows():
         torch.cuda.synchronize()
         ref = x[-4096:].double() @ w.double()
         assert float((y[-4096:].double() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------ ball query: more edge cases vs the C oracle ----
+@pytest.mark.parametrize("n,s,mode,radii,ks", [
+    (16384, 100, "uniform", [0.4, 0.1, 0.2], [128, 32, 64]),        # radii in any order
+    (9000, 77, "events", [0.25], [24]),                              # ragged length, one radius
+    (7000, 64, "events", [0.3, 0.3], [16, 48]),                      # equal radii
+    (6500, 40, "events", [1e-4, 5.0], [8, 200]),                     # nothing but the centre / the whole window
+])
+def test_ball_query_radius_lists_and_ragged_lengths_vs_c_oracle(n, s, mode, radii, ks):
+    b = 3
+    ev = synth.make_windows(b, n, seed=200 + n, mode=mode)
+    xyz = np.ascontiguousarray(ev[:, :3].transpose(0, 2, 1))
+    fidx = c_oracle.fps(xyz, s, synth.make_start_indices(b, n, seed=5))
+    centres = np.stack([xyz[i, fidx[i]] for i in range(b)])
+    xd = dev(xyz)
+    packed, cnt = _capi.ball_query(xd, _capi.rows_strides(xd), dev(centres), n, radii, ks, with_counts=True)
+    packed, cnt = packed.cpu().numpy(), cnt.cpu().numpy()
+    off = 0
+    for j, (r, k) in enumerate(zip(radii, ks)):
+        want = c_oracle.ball_query(r, k, xyz, centres)
+        assert np.array_equal(packed[:, :, off:off + k], want), (r, k)
+        real = (want != n).sum(-1)
+        # the reference pads with copies of the first neighbour: the real count is the number of distinct entries
+        distinct = np.array([[len(set(want[w, c])) for c in range(s)] for w in range(b)])
+        assert np.array_equal(cnt[j], np.where(real == 0, 0, distinct)), (r, k)
+        off += k
