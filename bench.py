@@ -798,8 +798,9 @@ def run_ours(args):
             "allreduce_us_alone": 1e3 * train_res["allreduce_ms"], "loss": train_res["loss"], "dtype": "f32 (TF32 off)",
             "stand_ins": "MANO layer = random MANO-shaped LBS (assets licence gated); criterion = losses.py:145-206 without loss_interpen "
                          "(mesh_intersection absent): parity of those two parts unpinned",
-            "kernels": "FPS, ball query, grouping gather + scatter-add backward, max-pool + arg-max backward: libev2h.so; conv / BatchNorm "
-                       "(batch statistics) / ReLU: cuDNN through PyTorch"}
+            "kernels": "FPS, ball query, grouping gather + scatter-add backward, input-gradient GEMMs of the 1x1 convolutions (tcgen05 layer "
+                       "kernel, tf32 / bf16 split): libev2h.so; forward and weight-gradient GEMMs over the gather kernel's row layout: cuBLAS "
+                       "fp32; BatchNorm (batch statistics) / ReLU / max over K: PyTorch; k = 3 convolutions of the heads: cuDNN"}
     if args.with_decoder:
         line["secondary"] = {"metric": "encoder + fp3/fp2/fp1 decoder event-windows/s (TEHNet.py:172-186)",
                              "value": windows / (dec_ms / 1e3), "unit": "windows/s", "ms_per_step": dec_ms / args.steps}
