@@ -122,7 +122,8 @@ extern "C" int ev2h_group_compact_i32(const int32_t *idx, int idx_ld, const int3
 // occurrence.  first[b,n] = 1 iff no point m < n of window b has the same 32-byte record.
 namespace ev2h {
 
-constexpr int kUniqSlots = 8192;          // open-addressing table per window, >= 2 x the points hashed at once
+constexpr int kUniqSlots = 8192;          // open-addressing table per window, >= 2 x the points hashed at once (windows up to 4096 points;
+                                          // longer ones take a table of the next power of two >= 2 N, up to 32768 slots = 128 KB)
 constexpr int kUniqThreads = 1024;
 
 __device__ __forceinline__ bool same_record(const uint4 *rec, int a, int b) {
@@ -131,17 +132,17 @@ __device__ __forceinline__ bool same_record(const uint4 *rec, int a, int b) {
 }
 
 __global__ void __launch_bounds__(kUniqThreads)
-first_occurrence_kernel(const float *__restrict__ pts8, int N, uint8_t *__restrict__ first) {
-    __shared__ int table[kUniqSlots];
+first_occurrence_kernel(const float *__restrict__ pts8, int N, uint8_t *__restrict__ first, int slots) {
+    extern __shared__ int table[];            // [slots], a power of two
     const uint4 *rec = reinterpret_cast<const uint4 *>(pts8 + (int64_t)blockIdx.x * N * 8);
     uint8_t *out = first + (int64_t)blockIdx.x * N;
-    for (int i = threadIdx.x; i < kUniqSlots; i += kUniqThreads) table[i] = 0x7fffffff;
+    for (int i = threadIdx.x; i < slots; i += kUniqThreads) table[i] = 0x7fffffff;
     __syncthreads();
     auto slot_of = [&](int n) {
         const uint4 a = rec[2 * n], b = rec[2 * n + 1];
         uint32_t h = a.x * 0x9E3779B1u ^ a.y * 0x85EBCA77u ^ a.z * 0xC2B2AE3Du ^ a.w * 0x27D4EB2Fu ^ b.x * 0x165667B1u;
         h ^= h >> 15;
-        return (int)(h & (kUniqSlots - 1));
+        return (int)(h & (slots - 1));
     };
     // phase 1: every record ends up in exactly one slot holding the smallest index that carries it
     for (int n = threadIdx.x; n < N; n += kUniqThreads) {
@@ -150,7 +151,7 @@ first_occurrence_kernel(const float *__restrict__ pts8, int N, uint8_t *__restri
             const int cur = atomicCAS(&table[h], 0x7fffffff, n);
             if (cur == 0x7fffffff) break;                                 // claimed an empty slot
             if (same_record(rec, cur, n)) { atomicMin(&table[h], n); break; }
-            h = (h + 1) & (kUniqSlots - 1);
+            h = (h + 1) & (slots - 1);
         }
     }
     __syncthreads();
@@ -160,7 +161,7 @@ first_occurrence_kernel(const float *__restrict__ pts8, int N, uint8_t *__restri
         for (;;) {
             const int cur = table[h];
             if (same_record(rec, cur, n)) { out[n] = cur == n ? 1 : 0; break; }
-            h = (h + 1) & (kUniqSlots - 1);
+            h = (h + 1) & (slots - 1);
         }
     }
 }
@@ -171,7 +172,14 @@ extern "C" int ev2h_first_occurrence_u8(const float *pts8, int B, int N, uint8_t
     using namespace ev2h;
     EV2H_REQUIRE(pts8 && first, "ev2h_first_occurrence_u8: null argument");
     EV2H_REQUIRE(B > 0 && N > 0 && ((uintptr_t)pts8 & 15) == 0, "ev2h_first_occurrence_u8: bad sizes or misaligned records");
-    if (2 * N > kUniqSlots) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_first_occurrence_u8: N=%d exceeds %d points per window", N, kUniqSlots / 2);
-    first_occurrence_kernel<<<(unsigned)B, kUniqThreads, 0, as_stream(stream)>>>(pts8, N, first);
+    if (N > 16384) return fail(EV2H_ERR_UNSUPPORTED, "ev2h_first_occurrence_u8: N=%d exceeds 16384 points per window", N);
+    int slots = kUniqSlots;
+    while (slots < 2 * N) slots *= 2;
+    const size_t smem = (size_t)slots * sizeof(int);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(first_occurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(EV2H_ERR_CUDA, "ev2h_first_occurrence_u8: smem attribute: %s", cudaGetErrorString(e));
+    }
+    first_occurrence_kernel<<<(unsigned)B, kUniqThreads, smem, as_stream(stream)>>>(pts8, N, first, slots);
     return check_launch("ev2h_first_occurrence_u8");
 }

@@ -591,7 +591,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         state_best = torch.empty((B, N), dtype=torch.float32, device=dev)
         state_cur = torch.empty((B,), dtype=torch.int32, device=dev)
         ball = torch.empty((B, S, k_total), dtype=torch.int32, device=dev)
-        dedup = _DEDUP and D + 3 <= 8 and N <= 4096
+        dedup = _DEDUP and D + 3 <= 8 and N <= 16384
         uniq = torch.empty_like(ball) if dedup else None
         rowmaps = [torch.empty((B * S * int(k),), dtype=torch.int32, device=dev) for k in self.nsample_list]
         blockgroups = [torch.empty((B * S * int(k) // 8,), dtype=torch.int32, device=dev) for k in self.nsample_list]
@@ -625,7 +625,7 @@ class PointNetSetAbstractionMsg(nn.Module):
             # compacted row lists come out of the ball query itself; in gather mode (narrow inputs, N <= 4096) neighbours
             # whose 32-byte record repeats an earlier point give identical rows and are listed once
             first = None
-            if _DEDUP and D + 3 <= 8 and N <= 4096:
+            if _DEDUP and D + 3 <= 8 and N <= 16384:
                 geom["pts8"] = self._pts8(xyz, points, strides)
                 first = _capi.first_occurrence(geom["pts8"])
             ball, rowmaps, blockgroups, n_rows = _capi.ball_query_compact(xyz, strides, centres_rows, N, self.radius_list,

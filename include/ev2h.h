@@ -109,7 +109,8 @@ EV2H_API int ev2h_ball_query_cnt_f32(const float *xyz, int64_t stride_b, int64_t
 
 /* first[b,n] = 1 iff no point m < n of window b has the same 32-byte record pts8[b,m,:] (bitwise).  Event
  * windows are sampled with replacement, so ~40 % of the points are exact copies of an earlier one; copies give
- * identical MLP rows and the compacted row list keeps only the first.  N <= 4096. */
+ * identical MLP rows and the compacted row list keeps only the first.  N <= 16384 (an open-addressing table of the
+ * next power of two >= 2 N slots in shared memory). */
 EV2H_API int ev2h_first_occurrence_u8(const float *pts8, int B, int N, uint8_t *first, ev2h_stream_t stream);
 /* Ball query that also emits, per centre and scale, the first-K hit list WITHOUT the hits whose first flag is 0
  * (out_uniq int32 [B,S,sum K], only the first out_ucnt[scale,b,s] entries of each block are written;

@@ -673,3 +673,35 @@ def test_ball_query_radius_lists_and_ragged_lengths_vs_c_oracle(n, s, mode, radi
         distinct = np.array([[len(set(want[w, c])) for c in range(s)] for w in range(b)])
         assert np.array_equal(cnt[j], np.where(real == 0, 0, distinct)), (r, k)
         off += k
+
+
+# ------------------------------------------------------------------ duplicate flags for long windows -----------------
+@pytest.mark.parametrize("n", [4097, 9000, 16384])
+def test_first_occurrence_on_long_windows(n):
+    rs = np.random.RandomState(n)
+    base = rs.rand(2, n // 3, 8).astype(np.float32)
+    base[:, :, 7] = 0
+    pick = rs.randint(0, n // 3, size=(2, n))
+    pts8 = np.stack([base[b][pick[b]] for b in range(2)])                 # sampling with replacement: ~2/3 exact copies
+    first = _capi.first_occurrence(dev(pts8)).cpu().numpy()
+    want = np.zeros((2, n), dtype=np.uint8)
+    for b in range(2):
+        _, idx = np.unique(pts8[b].view(np.dtype((np.void, 32))).ravel(), return_index=True)
+        want[b, idx] = 1
+    assert np.array_equal(first, want)
+
+
+def test_long_window_features_do_not_depend_on_duplicate_skipping(monkeypatch):
+    """16384-event windows: the rows of exact copies of a point are skipped (round 2: the duplicate flags now cover long
+    windows too); pooled features are bit-identical to evaluating them"""
+    import ev2hands_b200.pointnet2_utils as pu
+    enc = _encoder_with((21, 22, 23))
+    ev = dev(synth.make_windows(2, 16384, seed=77))
+    s1 = torch.from_numpy(synth.make_start_indices(2, 16384, 2))
+    s2 = torch.from_numpy(synth.make_start_indices(2, 512, 3))
+    outs = []
+    for dedup in (True, False):
+        monkeypatch.setattr(pu, "_DEDUP", dedup)
+        with torch.no_grad():
+            outs.append(enc(ev, fps_starts=(s1, s2)).clone())
+    assert torch.equal(outs[0], outs[1])
