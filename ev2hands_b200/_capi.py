@@ -29,6 +29,7 @@ _SIGNATURES = {
     "ev2h_group_gather_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_vp, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_vp, c_int, c_vp],
     "ev2h_group_gather_bwd_f32": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_point_records_f32": [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp],
     "ev2h_transpose_f32": [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_vp],
     "ev2h_fold_conv_bn_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_int, c_int, c_vp, c_vp, c_vp],
     "ev2h_linear_relu_f32": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp],
@@ -399,6 +400,19 @@ def group_gather_bwd(grad_rows, ld_grad, idx, k_off, B, N, S, K, D, grad_feats_r
         with _timed("ev2h_group_gather_bwd_f32"):
             _check(lib().ev2h_group_gather_bwd_f32(_p(grad_rows), ld_grad, _p(idx), idx.shape[-1], k_off, B, N, S, K, D,
                                                _p(grad_feats_rows), _stream(grad_rows)), "ev2h_group_gather_bwd_f32")
+
+
+def point_records(points, xyz, strides) -> torch.Tensor:
+    """[B, N, 8] records [features | xyz | 0] from channel-first points [B, D, N] (or None) and xyz [B, 3, N]"""
+    B, _, N = xyz.shape
+    D = 0 if points is None else points.shape[1]
+    out = torch.empty((B, N, 8), dtype=torch.float32, device=xyz.device)
+    ps = (0, 0, 0) if points is None else (points.stride(0), points.stride(1), points.stride(2))
+    with torch.cuda.device(xyz.device):
+        with _timed("ev2h_point_records_f32"):
+            _check(lib().ev2h_point_records_f32(_p(points), ps[0], ps[1], ps[2], D, _p(xyz), strides[0], strides[1], strides[2],
+                                                B, N, _p(out), _stream(xyz)), "ev2h_point_records_f32")
+    return out
 
 
 def transpose(src, src_strides, B, R, C, dst, dst_stride_b, dst_ld, dst_col_off=0):

@@ -137,6 +137,31 @@ static int grid_for(int64_t total, int block) {
     return (int)(g < cap ? g : cap);
 }
 
+// 32-byte point records [features (D <= 5) | x y z | 0 ...] for the gather mode of the fused kernel: one thread per point,
+// the channel planes are read coalesced and a record leaves as two 16-byte stores (a full sector).  Two batched
+// transposes into a zero-filled buffer did the same with three passes of partial-sector writes (0.34 ms for 256 windows
+// of 16384 points against 0.07 ms).
+__global__ void __launch_bounds__(256)
+point_records_kernel(const float *__restrict__ feats, int64_t fb, int64_t fc, int64_t fn, int D,
+                     const float *__restrict__ xyz, int64_t xb, int64_t xc, int64_t xn, int N, float4 *__restrict__ out, int64_t total) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {   // grid_for caps the grid
+        const int64_t b = e / N, n = e % N;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+            if (c < D) v[c] = feats[b * fb + c * fc + n * fn];
+        const float x = xyz[b * xb + n * xn], y = xyz[b * xb + xc + n * xn], z = xyz[b * xb + 2 * xc + n * xn];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {            // the coordinates follow the D features
+            if (c == D) { v[c] = x; v[c + 1] = y; v[c + 2] = z; }
+        }
+        out[2 * e] = make_float4(v[0], v[1], v[2], v[3]);
+        out[2 * e + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
 }  // namespace ev2h
 
 extern "C" int ev2h_group_gather_f32(const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
@@ -213,4 +238,19 @@ extern "C" int ev2h_group_max_bwd_f32(const float *grad_out, const int32_t *arg,
     const int64_t total = (int64_t)B * C * K * S;
     group_max_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(grad_out, arg, K, S, grad_x, total);
     return check_launch("ev2h_group_max_bwd_f32");
+}
+
+/* pts8[b, n, :] = [feats[b, 0..D, n] | xyz[b, 0..3, n] | 0 ...]: the 32-byte point records the gather mode of
+ * ev2h_sa_msg_fused_tc reads (D + 3 <= 8; feats may be NULL with D = 0).  Both inputs are channel-first with element strides. */
+extern "C" int ev2h_point_records_f32(const float *feats, int64_t feats_stride_b, int64_t feats_stride_c, int64_t feats_stride_n, int D,
+                                      const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                      int B, int N, float *pts8, ev2h_stream_t stream) {
+    using namespace ev2h;
+    EV2H_REQUIRE(xyz && pts8 && ((uintptr_t)pts8 & 15) == 0, "ev2h_point_records_f32: null or misaligned argument");
+    EV2H_REQUIRE(B > 0 && N > 0 && D >= 0 && D <= 5 && (D == 0 || feats), "ev2h_point_records_f32: bad sizes (D + 3 must fit 8 floats)");
+    const int64_t total = (int64_t)B * N;
+    point_records_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(feats, feats_stride_b, feats_stride_c, feats_stride_n, D,
+                                                                              xyz, stride_b, stride_c, stride_n, N,
+                                                                              reinterpret_cast<float4 *>(pts8), total);
+    return check_launch("ev2h_point_records_f32");
 }

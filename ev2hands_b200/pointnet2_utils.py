@@ -544,13 +544,7 @@ class PointNetSetAbstractionMsg(nn.Module):
     # ---- shared front end: FPS + ball query -----------------------------------------
     def _pts8(self, xyz, points, strides):
         """[features | xyz | 0] per point, 32 bytes: one sector per gathered neighbour (gather mode of the fused kernel)."""
-        B, _, N = xyz.shape
-        D = 0 if points is None else points.shape[1]
-        pts8 = torch.zeros((B, N, 8), dtype=torch.float32, device=xyz.device)
-        if points is not None:
-            _capi.transpose(points, (points.stride(0), points.stride(1), points.stride(2)), B, D, N, pts8, N * 8, 8, 0)
-        _capi.transpose(xyz, strides, B, 3, N, pts8, N * 8, 8, D)
-        return pts8
+        return _capi.point_records(points, xyz, strides)
 
     def _fps(self, xyz, fps_start):
         """FPS of this layer on the current stream -> geometry record (dict)."""

@@ -178,6 +178,14 @@ EV2H_API int ev2h_group_gather_bwd_f32(const float *grad_rows, int ld_grad, cons
                               int k_off, int B, int N, int S, int K, int D,
                               float *grad_feats_rows, ev2h_stream_t stream);
 
+/* ---- 32-byte point records for the gather mode of the fused kernel -----------------------------
+ * pts8[b, n, :] = [feats[b, 0..D, n] | xyz[b, 0..3, n] | 0 ...] from two channel-first tensors read through element
+ * strides (the reference's points [B, D, N] and xyz = points[:, :3, :], TEHNet.py:172-175); D + 3 <= 8, feats may be
+ * NULL with D = 0.  One record = one 32-byte sector per gathered neighbour. */
+EV2H_API int ev2h_point_records_f32(const float *feats, int64_t feats_stride_b, int64_t feats_stride_c, int64_t feats_stride_n, int D,
+                                    const float *xyz, int64_t stride_b, int64_t stride_c, int64_t stride_n,
+                                    int B, int N, float *pts8, ev2h_stream_t stream);
+
 /* ---- batched transpose between the two layouts ----------------------------------
  * dst[b*dst_stride_b + c*dst_ld + dst_col_off + r] = src[b*src_stride_b + r*src_stride_r + c*src_stride_c]
  * for r < R, c < C.  Used for cf -> rows (permute(0,2,1).contiguous(),

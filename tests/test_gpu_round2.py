@@ -705,3 +705,19 @@ def test_long_window_features_do_not_depend_on_duplicate_skipping(monkeypatch):
         with torch.no_grad():
             outs.append(enc(ev, fps_starts=(s1, s2)).clone())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("b,n,d", [(3, 2048, 5), (2, 777, 4), (2, 300, 0), (80, 16384, 5)])
+def test_point_records_kernel(b, n, d):
+    """ev2h_point_records_f32 = [features | xyz | 0] per point, from strided channel-first views; the last case has more
+    points than one grid pass covers"""
+    torch.manual_seed(n)
+    ev = torch.randn(b, 7, n, device=DEV)
+    pts = ev[:, 1:1 + d, :] if d else None
+    xyz = ev[:, 2:5, :]
+    got = _capi.point_records(pts, xyz, _capi.cf_strides(xyz))
+    want = torch.zeros(b, n, 8, device=DEV)
+    if d:
+        want[:, :, :d] = pts.permute(0, 2, 1)
+    want[:, :, d:d + 3] = xyz.permute(0, 2, 1)
+    assert torch.equal(got, want)
