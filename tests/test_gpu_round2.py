@@ -721,3 +721,25 @@ def test_point_records_kernel(b, n, d):
         want[:, :, :d] = pts.permute(0, 2, 1)
     want[:, :, d:d + 3] = xyz.permute(0, 2, 1)
     assert torch.equal(got, want)
+
+
+def test_bench_prints_the_contract_line():
+    """one short `bench.py` run through the driver's command line: ONE JSON line with the keys the contract names"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--gpus", "1", "--steps", "3", "--warmup", "3",
+                          "--no-configs", "--no-raw-events", "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["metric"] == "encoder event-windows/s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["scaling"] == "weak"
+    assert d["gpu_launches"] > 0 and d["value"] > 1000 and d["e2e"]["value"] > 1000
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
+    assert abs(d["ms_per_step"] * d["value"] / 1e3 - 64) < 0.5          # 64 windows per step
