@@ -802,8 +802,9 @@ def run_ours(args):
             "stand_ins": "MANO layer = random MANO-shaped LBS (assets licence gated); criterion = losses.py:145-206 without loss_interpen "
                          "(mesh_intersection absent): parity of those two parts unpinned",
             "kernels": "FPS, ball query, grouping gather + scatter-add backward, input-gradient GEMMs of the 1x1 convolutions (tcgen05 layer "
-                       "kernel, tf32 / bf16 split): libev2h.so; forward and weight-gradient GEMMs over the gather kernel's row layout: cuBLAS "
-                       "fp32; BatchNorm (batch statistics) / ReLU / max over K: PyTorch; k = 3 convolutions of the heads: cuDNN"}
+                       "kernel, tf32 / bf16 split), weight + bias gradients (exact fp32, deterministic), forward GEMMs of layers with >= 96 "
+                       "outputs (exact fp32): libev2h.so; narrower forward GEMMs: cuBLAS fp32; BatchNorm (batch statistics) / ReLU / max "
+                       "over K: PyTorch; k = 3 convolutions of the heads: cuDNN"}
     if args.with_decoder:
         line["secondary"] = {"metric": "encoder + fp3/fp2/fp1 decoder event-windows/s (TEHNet.py:172-186)",
                              "value": windows / (dec_ms / 1e3), "unit": "windows/s", "ms_per_step": dec_ms / args.steps}

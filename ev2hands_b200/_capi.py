@@ -29,6 +29,8 @@ _SIGNATURES = {
     "ev2h_group_gather_f32": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_vp, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_vp, c_int, c_vp],
     "ev2h_group_gather_bwd_f32": [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "ev2h_wgrad_splits": [c_i64, c_int, c_int],
+    "ev2h_wgrad_f32": [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "ev2h_point_records_f32": [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp],
     "ev2h_transpose_f32": [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_vp],
     "ev2h_fold_conv_bn_f32": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_int, c_int, c_vp, c_vp, c_vp],
@@ -400,6 +402,22 @@ def group_gather_bwd(grad_rows, ld_grad, idx, k_off, B, N, S, K, D, grad_feats_r
         with _timed("ev2h_group_gather_bwd_f32"):
             _check(lib().ev2h_group_gather_bwd_f32(_p(grad_rows), ld_grad, _p(idx), idx.shape[-1], k_off, B, N, S, K, D,
                                                _p(grad_feats_rows), _stream(grad_rows)), "ev2h_group_gather_bwd_f32")
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, want_bias: bool = False):
+    """dW [Cout, Cin] = dy^T x for fp32 rows dy [M, Cout] (contiguous) and x [M, Cin] (unit column stride);
+    want_bias: -> (dW, db) with db [Cout] = dy.sum(0) from the same pass"""
+    M, cout = dy.shape
+    cin = x.shape[1]
+    splits = lib().ev2h_wgrad_splits(M, cout, cin)
+    work = torch.empty((splits * cout * (cin + 1),), dtype=torch.float32, device=dy.device)
+    dw = torch.empty((cout, cin), dtype=torch.float32, device=dy.device)
+    db = torch.empty((cout,), dtype=torch.float32, device=dy.device) if want_bias else None
+    with torch.cuda.device(dy.device):
+        with _timed("ev2h_wgrad_f32", launches=3 if want_bias else 2):
+            _check(lib().ev2h_wgrad_f32(_p(dy), dy.stride(0), _p(x), x.stride(0), M, cout, cin, _p(work), _p(dw), _p(db), _stream(dy)),
+                   "ev2h_wgrad_f32")
+    return (dw, db) if want_bias else dw
 
 
 def point_records(points, xyz, strides) -> torch.Tensor:

@@ -245,6 +245,8 @@ def _bn_rows(x2d, bn):
 # 2e-6 moves the weight gradients in front of a batch-statistics BatchNorm - differences of large sums - to within 3e-3
 # of the reference's autograd instead of 3e-6 (measured; the input-gradient GEMM alone changes nothing at that level),
 # far closer than the tf32 convolutions PyTorch runs by default but not the fp32 parity this repo promises.
+_TRAIN_WGRAD = os.environ.get("EV2H_TRAIN_WGRAD", "1") != "0"        # weight gradients: ev2h_wgrad_f32 instead of cuBLAS
+_TRAIN_FFMA = os.environ.get("EV2H_TRAIN_FFMA", "1") != "0"          # forward GEMMs with >= 96 outputs: ev2h_linear_f32 (exact fp32)
 _TRAIN_TC = {"1": "all", "all": "all", "dgrad": "dgrad"}.get(os.environ.get("EV2H_TRAIN_TC", "dgrad"), "")   # "", "dgrad" (default), "all"
 
 
@@ -277,6 +279,17 @@ class _LinearRowsTC(torch.autograd.Function):
                 b[:cout] = bias.detach()
             y = torch.empty((M, cout), dtype=torch.float32, device=x.device)
             _capi.linear_tc_no_relu(x, M, x.stride(0), cin, packed, b, cout, y, cout, 0, mode)
+        elif _TRAIN_FFMA and _rows_ok(x) and cout % 4 == 0 and cout >= 96:
+            # exact fp32 on the CUDA cores (ev2h_linear_f32, 128 x 128 x 16 tiles): these GEMMs are tall and skinny (millions
+            # of rows, 8-323 input channels), a shape the library's SIMT kernels run at ~13 TFLOP/s; narrower outputs would
+            # waste the 128-column tile and stay with the library
+            wt = torch.zeros(((cin + 15) // 16 * 16, (cout + 127) // 128 * 128), dtype=torch.float32, device=x.device)
+            wt[:cin, :cout] = weight.detach().t()
+            b = torch.zeros((wt.shape[1],), dtype=torch.float32, device=x.device)
+            if bias is not None:
+                b[:cout] = bias.detach()
+            y = torch.empty((M, cout), dtype=torch.float32, device=x.device)
+            _capi.linear_no_relu(x, M, x.stride(0), cin, wt, b, cout, y, cout)
         else:
             y = F.linear(x, weight, bias)
         ctx.save_for_backward(x, weight)
@@ -299,9 +312,18 @@ class _LinearRowsTC(torch.autograd.Function):
                 _capi.linear_tc_no_relu(dy, M, cout, cout, packed, zero, cin, dx, cin, 0, mode)
             else:
                 dx = dy @ weight
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            dw = dy.t() @ x
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if _TRAIN_WGRAD and x.stride(1) == 1 and x.dtype == torch.float32:
+                # contraction over the M rows: slabs in exact fp32, fixed-order sum; the bias gradient (column sums of dY)
+                # comes out of the same pass over dY
+                if want_db:
+                    dw, db = _capi.wgrad(dy, x, want_bias=True)
+                else:
+                    dw = _capi.wgrad(dy, x)
+            else:
+                dw = dy.t() @ x
+        if want_db and db is None:
             db = dy.sum(0)
         return dx, dw, db, None
 

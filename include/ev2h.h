@@ -263,6 +263,16 @@ EV2H_API int ev2h_tc_pack_weights_kc(const float *wt, int ld_w, int Cin, int Cou
 EV2H_API int ev2h_linear_relu_tc(const float *x, int64_t M, int ld_x, int Cin, const void *w_packed,
                                  const float *bias, int Cout, int pool_rows, float *y, int ld_y,
                                  int y_col_off, int mode, ev2h_stream_t stream);
+/* ---- weight gradient of a 1x1 convolution over point rows (training path) ---------------------------------
+ * dW [Cout, Cin] (row-major, contiguous) = dY^T X with dY [M, ld_dy >= Cout] and X [M, ld_x >= Cin] fp32 rows - the
+ * autograd of Conv2d(1x1) (pointnet2_utils.py:253-256) when the grouped tensor is kept as rows: a GEMM whose contraction
+ * runs over the M = B*S*K rows.  Slabs of rows are accumulated with exact fp32 FMAs and summed in a fixed order
+ * (deterministic).  db [Cout] (optional, may be NULL) = the column sums of dY, the bias gradient, accumulated in the same
+ * pass.  workspace: ev2h_wgrad_splits(M, Cout, Cin) * Cout * (Cin + 1) floats. */
+EV2H_API int ev2h_wgrad_splits(int64_t M, int Cout, int Cin);
+EV2H_API int ev2h_wgrad_f32(const float *dy, int ld_dy, const float *x, int ld_x, int64_t M, int Cout, int Cin,
+                            float *workspace, float *dw, float *db, ev2h_stream_t stream);
+
 /* ---- sampling and ball query in ranges (front-end pipelining) ---------------------------------------
  * The S iterations of farthest_point_sample are strictly sequential (pointnet2_utils.py:76-83) and only B CTAs wide,
  * but the ball query of centre s needs nothing of the centres after it.  ev2h_fps_range_f32 runs samples

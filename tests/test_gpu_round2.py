@@ -743,3 +743,21 @@ def test_bench_prints_the_contract_line():
     r = d["roofline"]
     assert r["bound"] == "tensor" and 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
     assert abs(d["ms_per_step"] * d["value"] / 1e3 - 64) < 0.5          # 64 windows per step
+
+
+@pytest.mark.parametrize("m,cout,cin,ld_x", [(4096, 64, 8, 8), (100000, 96, 64, 64), (33333, 128, 323, 324), (5000, 196, 128, 128),
+                                              (2048, 1024, 512, 512), (777, 32, 7, 8), (1500, 64, 515, 515), (64, 256, 256, 256)])
+def test_weight_gradient_kernel(m, cout, cin, ld_x):
+    """ev2h_wgrad_f32: dW = dY^T X over rows (the contraction runs over M), against fp64; strided and unaligned rows;
+    deterministic"""
+    torch.manual_seed(m)
+    dy = torch.randn(m, cout, device=DEV) * torch.pow(10.0, -4 * torch.rand(m, 1, device=DEV))      # gradient-like dynamic range
+    xbuf = torch.randn(m, ld_x, device=DEV)
+    x = xbuf[:, :cin]
+    got = _capi.wgrad(dy, x)
+    want = dy.double().t() @ x.double()
+    scale = (dy.double().abs().t() @ x.double().abs()).max()
+    assert float((got.double() - want).abs().max() / scale) < 2e-6
+    dw2, db = _capi.wgrad(dy, x, want_bias=True)
+    assert torch.equal(got, dw2)
+    assert float((db.double() - dy.double().sum(0)).abs().max() / dy.double().abs().sum(0).max()) < 2e-6
