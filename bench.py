@@ -548,10 +548,21 @@ def run_ours(args):
         dec = dec.to(device).eval()
         l3_xyz = torch.zeros((B, 3, 1), dtype=torch.float32, device=device)
 
-        def step_dec():
+        def fwd_dec(ev_, s1_, s2_):
             with torch.no_grad():
-                l3, lv = enc(ev_dev, fps_starts=(s1, s2), return_levels=True)
-                return dec(ev_dev[:, :3, :], lv["l1_xyz"], lv["l2_xyz"], l3_xyz, lv["l1_points"], lv["l2_points"], l3.unsqueeze(-1))
+                l3, lv = enc(ev_, fps_starts=(s1_, s2_), return_levels=True)
+                return dec(ev_[:, :3, :], lv["l1_xyz"], lv["l2_xyz"], l3_xyz, lv["l1_points"], lv["l2_points"], l3.unsqueeze(-1))
+
+        dec_graph = None
+        if args.graph:
+            try:                                   # one graph replay per step, like the headline (eager launches are host bound on some boxes)
+                from ev2hands_b200.encoder import GraphedForward
+                dec_graph = GraphedForward(fwd_dec, ev_dev, s1, s2)
+            except Exception as exc:      # noqa: BLE001
+                print("bench.py: decoder leg runs eager (%s)" % exc, file=sys.stderr)
+
+        def step_dec():
+            return dec_graph(ev_dev, s1, s2) if dec_graph is not None else fwd_dec(ev_dev, s1, s2)
 
         for _ in range(3):
             step_dec()
